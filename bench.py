@@ -1,0 +1,340 @@
+"""Benchmark of the Shamir hot path: BASELINE.json's metric "GF(p) Shamir share+recombine pairs/sec".
+
+    python bench.py --gpus 1 --steps 10 --warmup 3             (N > 1: launched with torch.distributed.run)
+    python bench.py --impl reference --steps 3 --warmup 1       (CPU port of the reference's algorithm)
+
+One step = one pass of the hot path over one batch: share generation of n secrets (degree t, m
+parties; coefficient matrix resident in HBM, "parity mode") followed by Lagrange recombination of
+t+1 of the resulting share rows.  One *pair* = one secret split + recombined.
+
+Workloads (--workload):
+    c3   (default, BASELINE.json configs[2]) p = 2^128-173, m=5, t=2, n = 10^8 per GPU
+    ns64 (north_star's 64-bit case)          p = 2^64-189,  m=3, t=1, n = 2*10^8 per GPU
+    c5   (configs[4] field/shape)            p = 2^256-189, m=7, t=3, n = 2*10^7 per GPU, recombine 2t+1
+    modmul (configs[1])                      p = 2^64-189 elementwise a*b, n = 10^8 (value = elem/s)
+
+The element axis is sharded over the GPUs with no data-path collective (weak scaling: n per GPU fixed).
+Printed JSON line: see the driver's contract; extra keys `roofline`, `cpu_baseline`, `e2e`, `clocks`.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'c3': dict(p=2**128 - 173, m=5, t=2, k=3, n=100_000_000, name='shamir split+recombine p=2^128-173 m=5 t=2 n=1e8/GPU (BASELINE configs[2])'),
+    'ns64': dict(p=2**64 - 189, m=3, t=1, k=2, n=200_000_000, name='shamir split+recombine p=2^64-189 m=3 t=1 n=2e8/GPU (north_star 64-bit case)'),
+    'c5': dict(p=2**256 - 189, m=7, t=3, k=7, n=20_000_000, name='shamir reshare p=2^256-189 m=7 t=3 recombine 2t+1 n=2e7/GPU (configs[4] shape)'),
+    'modmul': dict(p=2**64 - 189, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul p=2^64-189 n=1e8/GPU (BASELINE configs[1])'),
+}
+METRIC = 'GF(p) Shamir share+recombine pairs/sec'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's NumPy-object path (np_random_split + np_recombine)
+# ---------------------------------------------------------------------------------------------------
+
+def _cpu_pairs(args):
+    """One process: split+recombine `n` pairs `reps` times with the reference's own draw (secrets.randbelow)."""
+    p, m, t, k, n, reps, with_rng = args
+    import secrets
+    import numpy as np
+    from oracle import shamir_oracle as orc
+    s = np.array(orc.synth_elements(p, n, 20260923), dtype=object)
+    C = np.array(orc.np_stream_to_C(orc.synth_elements(p, t * n, 7, stream=2), t, n), dtype=object) if t else np.empty((0, n), dtype=object)
+    xs = tuple(range(1, k + 1))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        Cr = orc.np_draw_coefficients(p, t, n, secrets.randbelow) if with_rng else C
+        sh = orc.np_split(p, s, Cr, m)
+        out = orc.np_recombine(p, xs, sh[:k])
+    dt = time.perf_counter() - t0
+    if not with_rng:
+        assert out.tolist() == s.tolist()
+    return n * reps, dt
+
+
+def cpu_baseline(w, n=20000, target_s=12.0):
+    """1 core, bounded sample; returns the cpu_baseline object (kind 'port': the reference is Python and
+    cannot travel to the GPU box; oracle/shamir_oracle.py is its restatement, pinned by golden fixtures)."""
+    pairs, dt = _cpu_pairs((w['p'], w['m'], w['t'], w['k'], n, 1, True))
+    reps = max(1, int(target_s * 0.7 / max(dt, 1e-3)))
+    pairs, dt = _cpu_pairs((w['p'], w['m'], w['t'], w['k'], n, reps, True))
+    pairs2, dt2 = _cpu_pairs((w['p'], w['m'], w['t'], w['k'], n, max(1, reps // 2), False))
+    return {'value': pairs / dt, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
+            'sample': f'np_split+np_recombine (NumPy object arrays, coefficients via secrets.randbelow as the reference does) '
+                      f'on {n} elements x {reps} reps, 1 process', 'value_without_rng': pairs2 / dt2}
+
+
+def run_reference_arm(a, w):
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 4000
+    times = []
+    with mp.get_context('fork').Pool(cores) as pool:
+        for step in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_pairs, [(w['p'], w['m'], w['t'], w['k'], n, 1, True)] * cores)
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                times.append((sum(r[0] for r in res), dt))
+    pairs = sum(x for x, _ in times)
+    dt = sum(y for _, y in times)
+    val = pairs / dt
+    line = {'metric': METRIC, 'impl': 'reference', 'value': val, 'unit': 'pairs/s', 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': 1e3 * dt / max(a.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'python-int (exact)', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'sample_per_step': f'{n} pairs x {cores} processes'},
+            'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{cores} independent processes x {n} pairs per step (oracle port of thresha.np_random_split+np_recombine)'},
+            'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(a, w):
+    import torch
+    import torch.distributed as dist
+    import mpyc_b200
+    from mpyc_b200 import _cabi, device as dev
+    from mpyc_b200._cabi import lib, check
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback for the product arm)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    p, m, t, k, n = w['p'], w['m'], w['t'], w['k'], a.n or w['n']
+    ctx = mpyc_b200.context_for(p)
+    L = ctx.nlimbs
+    eb = ctx.elem_bytes
+    is_mul = w['m'] == 0
+    peak, peak_src = peaks()
+
+    # ---- device-resident inputs (synthetic, generated on the device; far larger than the 126 MB L2) ----
+    S = dev.DeviceArray.random(ctx, n, seed=20260923 + rank, stream_id=1)
+    if is_mul:
+        B = dev.DeviceArray.random(ctx, n, seed=77 + rank, stream_id=2)
+        OUT = dev.DeviceArray.empty(ctx, n)
+    else:
+        C = dev.DeviceMatrix.empty(ctx, t, n)
+        for j in range(t):
+            C.t[j].copy_(dev.DeviceArray.random(ctx, n, seed=100 + j + 10 * rank, stream_id=3).t)
+        SH = dev.DeviceMatrix.empty(ctx, m, n)
+        REC = dev.DeviceMatrix.empty(ctx, 1, n)
+        xs = list(range(1, k + 1))
+        rows = [SH.row(x - 1) for x in xs]
+    torch.cuda.synchronize()
+
+    def step():
+        if is_mul:
+            check(lib.mpyc_b200_ff_binop(ctx.handle, _cabi.OP_MUL, S.ptr, B.ptr, OUT.ptr, n, dev._stream_ptr()))
+        else:
+            dev.shamir_split(ctx, S, C, t, m, out=SH)
+            dev.shamir_recombine(ctx, xs, rows, 0, out=REC)
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    if not is_mul:   # correctness guard inside the bench: the recombined secrets are the inputs
+        assert REC.row(0).count_mismatch(S) == 0, 'recombined secrets differ from inputs'
+
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = mpyc_b200.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * a.steps + 1)]
+    ev[0].record()
+    for i in range(a.steps):
+        if is_mul:
+            step()
+            ev[2 * i + 1].record()
+        else:
+            dev.shamir_split(ctx, S, C, t, m, out=SH)
+            ev[2 * i + 1].record()
+            dev.shamir_recombine(ctx, xs, rows, 0, out=REC)
+        ev[2 * i + 2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = mpyc_b200.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    split_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(a.steps)) / a.steps
+    rec_ms = 0.0 if is_mul else sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(a.steps)) / a.steps
+    if world > 1:
+        tt = torch.tensor([total_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / a.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (share generation), algorithmic bytes / measured duration ----
+    if is_mul:
+        dom_name, dom_bytes, dom_ms = 'k_binop<mul>', 3 * eb * n, split_ms
+        sec = {}
+    else:
+        split_bytes = (1 + t + m) * eb * n
+        rec_bytes = (k + 1) * eb * n
+        dom_name, dom_bytes, dom_ms = 'k_split', split_bytes, split_ms
+        sec = {'recombine': {'kernel': 'k_recombine', 'achieved': rec_bytes / (rec_ms * 1e-3) / 1e9, 'unit': 'GB/s',
+                             'frac': rec_bytes / (rec_ms * 1e-3) / 1e9 / peak, 'ms': rec_ms, 'algorithmic_bytes': rec_bytes},
+               'step_total': {'achieved': (split_bytes + rec_bytes) / (ms_per_step * 1e-3) / 1e9, 'unit': 'GB/s',
+                              'frac': (split_bytes + rec_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
+                              'bytes_per_pair': (split_bytes + rec_bytes) / n}}
+    ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom_name, 'achieved': ach, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': None, 'ms': dom_ms, 'algorithmic_bytes': dom_bytes, **sec}
+
+    # ---- e2e: same path through the C ABI's host-buffer entry points, pinned host memory ----------------
+    e2e = None
+    if not a.no_e2e:
+        ne = a.e2e_n
+        hs = torch.empty((ne, L), dtype=torch.int64).pin_memory()
+        hs.copy_(S.t[:ne].cpu())
+        if is_mul:
+            hb = torch.empty((ne, L), dtype=torch.int64).pin_memory()
+            hb.copy_(B.t[:ne].cpu())
+            ho = torch.empty((ne, L), dtype=torch.int64).pin_memory()
+
+            def e2e_step():
+                check(lib.mpyc_b200_ff_binop_host(ctx.handle, _cabi.OP_MUL, hs.data_ptr(), hb.data_ptr(), ho.data_ptr(), ne, local))
+            h2d, d2h = 2 * eb * ne, eb * ne
+        else:
+            hc = torch.empty((t, ne, L), dtype=torch.int64).pin_memory()
+            hc.copy_(C.t[:, :ne].cpu())
+            hsh = torch.empty((m, ne, L), dtype=torch.int64).pin_memory()
+            hout = torch.empty((1, ne, L), dtype=torch.int64).pin_memory()
+            rowp = _cabi.ptr_array([hsh[x - 1].data_ptr() for x in xs])
+            xs_c, xr_c = _cabi.i64_array(xs), _cabi.i64_array([0])
+
+            def e2e_step():
+                check(lib.mpyc_b200_shamir_split_host(ctx.handle, hs.data_ptr(), hc.data_ptr(), ne, hsh.data_ptr(), ne, ne, t, m, local))
+                check(lib.mpyc_b200_shamir_recombine_host(ctx.handle, rowp, xs_c, k, xr_c, 1, hout.data_ptr(), ne, ne, local))
+            h2d, d2h = (1 + t) * eb * ne + k * eb * ne, m * eb * ne + eb * ne
+        for _ in range(max(1, min(a.warmup, 2))):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        if not is_mul:
+            assert torch.equal(hout[0], hs), 'e2e: recombined secrets differ from inputs'
+        e2e = {'value': world * ne * a.steps / dt, 'unit': 'pairs/s' if not is_mul else 'elem/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'n_per_step': ne, 'ms_per_step': 1e3 * dt / a.steps,
+               'path': 'mpyc_b200_shamir_split_host + mpyc_b200_shamir_recombine_host (pinned host buffers, copies inside)',
+               'note': 'measured on rank 0 and scaled by n_gpus' if world > 1 else 'host wall clock around blocking C-ABI calls'}
+
+    cpu = None if a.no_cpu or is_mul else cpu_baseline(w)
+    line = {'metric': METRIC if not is_mul else 'GF(p) modmul elem/sec', 'value': value,
+            'unit': 'pairs/s' if not is_mul else 'elem/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': f'u64x{L} limbs (exact integer arithmetic mod p)', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'p_bits': p.bit_length(), 'm': m, 't': t, 'recombine_k': k, 'n_per_gpu': n,
+                       'parallelism': f'element axis sharded over {world} GPU(s), no data-path collective',
+                       'l2_policy': 'inputs (>= 1.6 GB) far larger than the 126 MB L2; no flush needed',
+                       'coefficients': 'resident in HBM (parity mode)'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--n', type=int, default=0, help='elements per GPU (default: the workload size)')
+    ap.add_argument('--e2e-n', type=int, default=1 << 24)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
+    w = WORKLOADS[a.workload]
+    if a.impl == 'reference':
+        run_reference_arm(a, w)
+    else:
+        run_gpu_arm(a, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,174 @@
+/* mpyc_b200 -- C ABI of the B200 (sm_100a) batched finite-field / Shamir engine.
+ *
+ * The reference (lschoe/mpyc, pure Python) has no FFI; its "plugin boundary" for this path is a
+ * set of Python callables that mpyc/runtime.py looks up at call time.  Each entry
+ * point below is what a ctypes binding for one of those callables binds to; the reference
+ * interface it replaces is cited as file:line relative to the reference checkout.
+ *
+ * Conventions
+ *   - every function returns an int status: MPYC_B200_OK (0) or a negative MPYC_B200_E* code;
+ *     nothing throws across the ABI.  mpyc_b200_strerror() names a code; the CUDA error text of
+ *     the calling thread's last MPYC_B200_ECUDA is available via mpyc_b200_last_error().
+ *   - field elements are canonical residues in [0, p) stored as L little-endian 64-bit limbs,
+ *     L = ceil(bits(p)/64) in {1,2,3,4}, elements contiguous ("element-major").  A row of n
+ *     elements is n*L uint64.  Montgomery form never crosses the ABI.
+ *   - matrices (shares, coefficients) are given as a base pointer plus a row stride counted in
+ *     ELEMENTS (row i starts at base + i*stride*L uint64); stride >= n.
+ *   - pointers named d_* are device pointers owned by the caller; h_* are host pointers (pageable
+ *     or pinned) owned by the caller.  The library owns only the mpyc_b200_field handle and the
+ *     small per-field tables it caches (Vandermonde / Lagrange), freed by mpyc_b200_field_destroy.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device
+ *     entry points enqueue work and return without synchronising unless stated otherwise.
+ *   - a field handle is immutable after creation apart from its internally locked table cache;
+ *     calls are safe from one host thread per stream.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     MPYC_B200_ECUDA.
+ */
+#ifndef MPYC_B200_H
+#define MPYC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPYC_B200_OK            0
+#define MPYC_B200_EINVAL       -1   /* bad argument (shim raises ValueError)                     */
+#define MPYC_B200_EUNSUPPORTED -2   /* modulus / shape outside what the kernels cover (TypeError)*/
+#define MPYC_B200_EZERODIV     -3   /* inverse of zero requested (shim raises ZeroDivisionError) */
+#define MPYC_B200_ECUDA        -4   /* CUDA runtime error (RuntimeError)                         */
+#define MPYC_B200_ENOMEM       -5   /* host or device allocation failed (MemoryError)            */
+
+#define MPYC_B200_MAX_LIMBS     4
+#define MPYC_B200_MAX_POINTS    64  /* max shares per recombination call                         */
+
+/* field kinds reported by mpyc_b200_field_info */
+#define MPYC_B200_KIND_GENERIC     0   /* odd prime, Montgomery with guard limb                  */
+#define MPYC_B200_KIND_PM_ALIGNED  1   /* p = 2^(64L) - c                                        */
+#define MPYC_B200_KIND_PM_SHIFT    2   /* p = 2^k - c, k % 64 != 0                               */
+#define MPYC_B200_KIND_GF256       3   /* GF(2^8) = GF(2)[X]/(modulus), one byte per element     */
+
+/* elementwise binary ops for mpyc_b200_ff_binop* */
+#define MPYC_B200_OP_ADD 0
+#define MPYC_B200_OP_SUB 1
+#define MPYC_B200_OP_MUL 2
+
+typedef struct mpyc_b200_field mpyc_b200_field;
+
+int         mpyc_b200_version(void);
+const char* mpyc_b200_strerror(int status);
+const char* mpyc_b200_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t    mpyc_b200_launch_count(void);
+int         mpyc_b200_device_count(int* count);
+
+/* ---- field context ------------------------------------------------------------------------
+ * Replaces finfields.GF(p) / pGF (mpyc/finfields.py:23-42,347-363) as the carrier of the modulus.
+ * modulus: nlimbs little-endian limbs of an odd prime p >= 3 (primality is the caller's business,
+ * as pGF checks it with gmpy2.is_prime before this is reached). */
+int  mpyc_b200_field_create(const uint64_t* modulus, int nlimbs, mpyc_b200_field** out);
+/* GF(2^8) with the given degree-8 modulus polynomial (e.g. 283 = x^8+x^4+x^3+x+1, the AES field
+ * of demos/np_aes.py); replaces finfields.GF(gfpx.GFpX(2)(283)) (mpyc/finfields.py:1542-1563). */
+int  mpyc_b200_field_create_gf256(uint32_t modulus_poly, mpyc_b200_field** out);
+void mpyc_b200_field_destroy(mpyc_b200_field* f);
+int  mpyc_b200_field_info(const mpyc_b200_field* f, int* nlimbs, int* kind, int* bits,
+                          size_t* elem_bytes);
+
+/* ---- elementwise field arithmetic on device-resident arrays ------------------------------
+ * FiniteFieldArray.__add__/__sub__/__mul__ (mpyc/finfields.py:1056-1124): out[h] = a[h] op b[h]. */
+int mpyc_b200_ff_binop(const mpyc_b200_field* f, int op, const void* d_a, const void* d_b,
+                       void* d_out, size_t n, void* stream);
+/* same with a broadcast scalar b (host limbs, canonical) -- a op scalar (finfields.py:1045-1054) */
+int mpyc_b200_ff_binop_scalar(const mpyc_b200_field* f, int op, const void* d_a,
+                              const uint64_t* h_scalar, void* d_out, size_t n, void* stream);
+/* __neg__ (mpyc/finfields.py:1189-1192) */
+int mpyc_b200_ff_neg(const mpyc_b200_field* f, const void* d_a, void* d_out, size_t n, void* stream);
+/* PrimeFieldArray._pow with one public exponent e >= 0 (mpyc/finfields.py:1408-1414):
+ * out[h] = a[h]^e.  exponent: exp_nlimbs little-endian limbs. */
+int mpyc_b200_ff_pow(const mpyc_b200_field* f, const void* d_a, const uint64_t* h_exponent,
+                     int exp_nlimbs, void* d_out, size_t n, void* stream);
+/* PrimeFieldArray._reciprocal (mpyc/finfields.py:1416-1422): out[h] = a[h]^-1.  SYNCHRONISES the
+ * stream; returns MPYC_B200_EZERODIV if any a[h] == 0 (gmpy2.invert raises, mpyc/gmpy.py:192-213);
+ * d_out is then unspecified. */
+int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d_out, size_t n, void* stream);
+/* PrimeFieldArray._sqrt for Blum primes p % 4 == 3 (mpyc/finfields.py:1424-1438):
+ * inverse == 0: a^((p+1)/4); inverse != 0: a^((3p-5)/4) and EZERODIV if any a[h] == 0
+ * (synchronises in that case).  EUNSUPPORTED for p % 4 == 1. */
+int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int inverse, void* d_out, size_t n,
+                      void* stream);
+/* PrimeFieldArray._is_sqr (mpyc/finfields.py:1463-1470): d_out_u8[h] = legendre(a[h], p) != -1 */
+int mpyc_b200_ff_is_sqr(const mpyc_b200_field* f, const void* d_a, uint8_t* d_out_u8, size_t n,
+                        void* stream);
+
+/* ---- Shamir share generation ---------------------------------------------------------------
+ * thresha.np_random_split (mpyc/thresha.py:47-64) with the coefficient matrix C given explicitly:
+ *   shares[i][h] = sum_{j=0..t} (i+1)^j * M[j][h] mod p,   M[0] = secrets, M[j] = coeffs row j-1
+ * i.e. coeffs row j-1 holds the coefficient of X^j for every secret (the (t, n) row-major layout of
+ * thresha.py:60).  shares: m rows.  0 <= t < m.  For GF(2^8) the points are the field elements with
+ * integer encoding i+1 (thresha.py:54,61). */
+int mpyc_b200_shamir_split(const mpyc_b200_field* f, const void* d_secrets, const void* d_coeffs,
+                           size_t coeff_stride, void* d_shares, size_t share_stride, size_t n,
+                           int t, int m, void* stream);
+/* Same, coefficients generated on the device and never written to memory ("generate mode"):
+ * a ChaCha20 keystream keyed by key32/nonce (caller supplies fresh CSPRNG bytes, the role of
+ * secrets.randbelow in thresha.py:58-60), reduced to [0, p) from 64 extra bits.  Not bit-exact
+ * with anything (neither is the reference: its randomness is unseeded); shares are a valid
+ * degree-t sharing and recombine to the secrets. */
+int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secrets, void* d_shares,
+                                    size_t share_stride, size_t n, int t, int m,
+                                    const uint8_t key32[32], uint64_t nonce, void* stream);
+
+/* ---- Lagrange recombination ----------------------------------------------------------------
+ * thresha._recombination_vector (mpyc/thresha.py:67-85): lambda[r][i] for x-coordinates xs[0..k)
+ * and recombination points x_rs[0..width); written as width*k*L host limbs, canonical. */
+int mpyc_b200_recombination_vector(const mpyc_b200_field* f, const int64_t* xs, int k,
+                                   const int64_t* x_rs, int width, uint64_t* h_lambda);
+/* thresha.np_recombine (mpyc/thresha.py:119-132): out[r][h] = sum_i lambda[r][i] * shares_i[h] mod p.
+ * d_share_rows: host array of k device pointers (one row of n elements each; rows may come from
+ * different buffers, as the k received messages do in runtime.py:582-586,672-680). */
+int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* const* d_share_rows,
+                               const int64_t* xs, int k, const int64_t* x_rs, int width,
+                               void* d_out, size_t out_stride, size_t n, void* stream);
+
+/* ---- PRSS linear step ------------------------------------------------------------------------
+ * thresha.np_pseudorandom_share / np_pseudorandom_share_0 (mpyc/thresha.py:163-173,201-217) after
+ * the PRF: for each of nsub key subsets S the caller provides the raw SHAKE128 output stream
+ * (thresha.py:257) as n*d chunks of chunk_bytes little-endian bytes.  out[h] =
+ *   sum_S  f_S(i) * sum_{j<d} (chunk_{S,h,j} mod p) * w[j]   mod p
+ * with h_coef[S] = f_S(i) (thresha.py:135-141) and h_weights[j] = 1 (d = 1, share) or (i+1)^(j+1)
+ * (share_0), both canonical host limbs.  bound_bits == 0: the PRF bound is the field order (chunks are
+ * reduced mod p); bound_bits = b > 0: the bound is 2^b <= p (runtime.py:4076, chunks are masked to b
+ * bits, chunk_bytes == ceil(b/8)). */
+int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes,
+                           int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                           const uint64_t* h_weights, void* d_out, size_t n, void* stream);
+
+/* ---- utilities -------------------------------------------------------------------------------
+ * deterministic synthetic residues (tests, bench): element h = (L+1 SplitMix64 words of counter
+ * seed + (stream_id << 56) + h*(L+1) + w, truncated to bits(p)+64 bits) mod p -- same recipe as
+ * oracle/shamir_oracle.py:synth_elements. */
+int mpyc_b200_fill_random(const mpyc_b200_field* f, void* d_out, size_t n, uint64_t seed,
+                          uint64_t stream_id, void* stream);
+/* out[0] = number of positions where a and b differ (device-side compare for full-size parity) */
+int mpyc_b200_count_mismatch(const mpyc_b200_field* f, const void* d_a, const void* d_b, size_t n,
+                             uint64_t* d_count, void* stream);
+
+/* ---- host-buffer entry points (what a drop-in caller with host data uses) ---------------------
+ * Inputs and outputs are HOST buffers in the same limb layout; the library stages them through
+ * pinned buffers, overlapping H2D copy, kernel and D2H copy chunk by chunk on its own streams, and
+ * returns when the output is complete.  device = CUDA device ordinal. */
+int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
+                                size_t coeff_stride, void* h_shares, size_t share_stride, size_t n,
+                                int t, int m, int device);
+int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const void* const* h_share_rows,
+                                    const int64_t* xs, int k, const int64_t* x_rs, int width,
+                                    void* h_out, size_t out_stride, size_t n, int device);
+int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const void* h_a, const void* h_b,
+                            void* h_out, size_t n, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPYC_B200_H */

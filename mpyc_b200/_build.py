@@ -1,0 +1,70 @@
+"""In-tree build of libmpyc_b200.so (sm_100a) with nvcc.  No torch involved: the library is plain CUDA
+behind a C ABI.  Objects go to mpyc_b200/csrc/_obj/, the shared library next to this file."""
+import concurrent.futures
+import hashlib
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(CSRC, '_obj')
+LIB = os.path.join(HERE, 'libmpyc_b200.so')
+SOURCES = ['api.cu', 'inst_L1.cu', 'inst_L2.cu', 'inst_L3.cu', 'inst_L4.cu']
+HEADERS = ['ff_arith.cuh', 'kernels.cuh', 'launch.h', 'launch_impl.cuh', 'gf256.cuh',
+           os.path.join('..', '..', 'include', 'mpyc_b200.h')]
+NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    cand = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(cand):
+        raise RuntimeError('nvcc not found: cannot build libmpyc_b200.so')
+    return cand
+
+
+def _digest():
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile (if sources changed) and return the path of the shared library."""
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, 'digest.txt')
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout[-4000:], r.stderr[-8000:]))
+        return obj, r.stderr
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in results]
+    if verbose:
+        with open(os.path.join(OBJ, 'ptxas.log'), 'w') as fh:
+            for _, err in results:
+                fh.write(err)
+    r = subprocess.run([nvcc, '-shared', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lrt', '-lpthread'],
+                       capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError('link failed:\n' + r.stderr[-4000:])
+    with open(stamp, 'w') as fh:
+        fh.write(digest)
+    return LIB
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,872 @@
+// C-ABI of the mpyc_b200 engine (see include/mpyc_b200.h for the contract and the reference
+// interfaces each entry point replaces).  This translation unit holds the host logic: field
+// context construction (reduction-kind selection, Montgomery constants), Vandermonde / Lagrange
+// table preparation and caching, argument checking, and the chunked host-buffer pipelines.
+// Kernels live in kernels.cuh / gf256.cuh and are instantiated per limb count in inst_L*.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/mpyc_b200.h"
+#include "field_setup.h"
+#include "gf256.cuh"
+#include "launch.h"
+
+#define MPYC_API extern "C" __attribute__((visibility("default")))
+
+std::atomic<unsigned long long> g_mpyc_launches{0};
+
+static thread_local char tl_error[512] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(tl_error, sizeof tl_error, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();   // clear the sticky-less error state
+    if (e == cudaErrorMemoryAllocation) return MPYC_B200_ENOMEM;
+    if (e == cudaErrorMisalignedAddress) {
+        snprintf(tl_error, sizeof tl_error, "%s: buffers must be 16-byte aligned", what);
+        return MPYC_B200_EINVAL;
+    }
+    return MPYC_B200_ECUDA;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+static int fail(int code, const char* msg) {
+    snprintf(tl_error, sizeof tl_error, "%s", msg);
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------
+// grid sizing
+// ---------------------------------------------------------------------------------------
+
+int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> wave;   // (kernel, device) -> CTAs per full wave
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    int w;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto key = std::make_pair(kernel, dev);
+        auto it = wave.find(key);
+        if (it == wave.end()) {
+            int sms = 0, occ = 0;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, MPYC_THREADS, dyn_smem) != cudaSuccess)
+                return -1;
+            if (occ < 1) occ = 1;
+            w = sms * occ;
+            wave[key] = w;
+        } else {
+            w = it->second;
+        }
+    }
+    size_t need = (items + MPYC_THREADS - 1) / MPYC_THREADS;
+    if (need < 1) need = 1;
+    return (int)std::min<size_t>(need, (size_t)w);
+}
+
+// ---------------------------------------------------------------------------------------
+// field handle
+// ---------------------------------------------------------------------------------------
+
+struct DevTable {
+    u64* d = nullptr;
+    u32 bytes = 0;
+    bool full = false;
+};
+
+struct mpyc_b200_field {
+    FieldParams fp;
+    int kind;           // MPYC_B200_KIND_*
+    u32 gf_poly;        // GF(2^8): modulus polynomial (9 bits)
+    std::mutex mu;
+    std::map<std::string, DevTable> tables;   // key includes the device ordinal
+};
+
+template <int L, class Fn>
+static int with_kind(const FieldParams& fp, Fn&& fn) {
+    switch (fp.kind) {
+        case KIND_GENERIC: return fn(std::integral_constant<int, L>(), std::integral_constant<int, KIND_GENERIC>());
+        case KIND_PM_ALIGNED: return fn(std::integral_constant<int, L>(), std::integral_constant<int, KIND_PM_ALIGNED>());
+        case KIND_PM_SHIFT: return fn(std::integral_constant<int, L>(), std::integral_constant<int, KIND_PM_SHIFT>());
+    }
+    return MPYC_B200_EINVAL;
+}
+// calls fn(L_constant, KIND_constant) on the host with the field's compile-time parameters
+template <class Fn>
+static int with_field(const FieldParams& fp, Fn&& fn) {
+    switch (fp.L) {
+        case 1: return with_kind<1>(fp, fn);
+        case 2: return with_kind<2>(fp, fn);
+        case 3: return with_kind<3>(fp, fn);
+        case 4: return with_kind<4>(fp, fn);
+    }
+    return MPYC_B200_EINVAL;
+}
+template <class Fn>
+static int with_limbs(int L, Fn&& fn) {
+    switch (L) {
+        case 1: return fn(std::integral_constant<int, 1>());
+        case 2: return fn(std::integral_constant<int, 2>());
+        case 3: return fn(std::integral_constant<int, 3>());
+        case 4: return fn(std::integral_constant<int, 4>());
+    }
+    return MPYC_B200_EINVAL;
+}
+
+MPYC_API int mpyc_b200_version(void) { return 100; }
+
+MPYC_API const char* mpyc_b200_strerror(int status) {
+    switch (status) {
+        case MPYC_B200_OK: return "ok";
+        case MPYC_B200_EINVAL: return "invalid argument";
+        case MPYC_B200_EUNSUPPORTED: return "unsupported field or shape";
+        case MPYC_B200_EZERODIV: return "inverse of zero";
+        case MPYC_B200_ECUDA: return "CUDA error";
+        case MPYC_B200_ENOMEM: return "out of memory";
+    }
+    return "unknown status";
+}
+
+MPYC_API const char* mpyc_b200_last_error(void) { return tl_error; }
+
+MPYC_API uint64_t mpyc_b200_launch_count(void) { return g_mpyc_launches.load(); }
+
+MPYC_API int mpyc_b200_device_count(int* count) {
+    if (!count) return fail(MPYC_B200_EINVAL, "count is null");
+    CU(cudaGetDeviceCount(count));
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_field_create(const uint64_t* modulus, int nlimbs, mpyc_b200_field** out) {
+    if (!modulus || !out || nlimbs < 1) return fail(MPYC_B200_EINVAL, "field_create: bad arguments");
+    while (nlimbs > 1 && modulus[nlimbs - 1] == 0) nlimbs--;
+    if (nlimbs > MPYC_B200_MAX_LIMBS) return fail(MPYC_B200_EUNSUPPORTED, "modulus wider than 256 bits");
+    if (!(modulus[0] & 1) || (nlimbs == 1 && modulus[0] < 3))
+        return fail(MPYC_B200_EUNSUPPORTED, "modulus must be an odd prime >= 3");
+    mpyc_b200_field* f = new (std::nothrow) mpyc_b200_field();
+    if (!f) return fail(MPYC_B200_ENOMEM, "field_create: allocation failed");
+    FieldParams& fp = f->fp;
+    field_params_init(modulus, nlimbs, &fp);
+    f->kind = fp.kind;
+    f->gf_poly = 0;
+    *out = f;
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_field_create_gf256(uint32_t modulus_poly, mpyc_b200_field** out) {
+    if (!out) return fail(MPYC_B200_EINVAL, "out is null");
+    if ((modulus_poly >> 8) != 1) return fail(MPYC_B200_EUNSUPPORTED, "modulus polynomial must have degree 8");
+    // irreducibility check: x^(2^8) == x (mod f) and gcd conditions reduce, for degree 8, to
+    // "no root and no factor of degree <= 4": test by trial division over all polynomials of degree 1..4
+    for (u32 g = 2; g < 32; g++) {
+        u32 a = modulus_poly;
+        int dg = 31 - __builtin_clz(g);
+        while (a && (31 - __builtin_clz(a)) >= dg) a ^= g << ((31 - __builtin_clz(a)) - dg);
+        if (a == 0) return fail(MPYC_B200_EUNSUPPORTED, "modulus polynomial is reducible");
+    }
+    mpyc_b200_field* f = new (std::nothrow) mpyc_b200_field();
+    if (!f) return fail(MPYC_B200_ENOMEM, "field_create: allocation failed");
+    memset(&f->fp, 0, sizeof f->fp);
+    f->kind = MPYC_B200_KIND_GF256;
+    f->gf_poly = modulus_poly;
+    f->fp.k = 8;
+    *out = f;
+    return MPYC_B200_OK;
+}
+
+MPYC_API void mpyc_b200_field_destroy(mpyc_b200_field* f) {
+    if (!f) return;
+    for (auto& kv : f->tables)
+        if (kv.second.d) cudaFree(kv.second.d);
+    delete f;
+}
+
+MPYC_API int mpyc_b200_field_info(const mpyc_b200_field* f, int* nlimbs, int* kind, int* bits, size_t* elem_bytes) {
+    if (!f) return fail(MPYC_B200_EINVAL, "field is null");
+    const bool gf = f->kind == MPYC_B200_KIND_GF256;
+    if (nlimbs) *nlimbs = gf ? 0 : (int)f->fp.L;
+    if (kind) *kind = f->kind;
+    if (bits) *bits = (int)f->fp.k;
+    if (elem_bytes) *elem_bytes = gf ? 1 : 8 * (size_t)f->fp.L;
+    return MPYC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side field helpers (table preparation)
+// ---------------------------------------------------------------------------------------
+
+// canonical limbs of (v mod p) for a signed 64-bit integer v
+template <int L, int KIND>
+static void h_from_int(u64* r, int64_t v, const FieldParams& fp) {
+    u64 mag = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
+    zero_n<L>(r);
+    if (L == 1) mag %= fp.p[0];
+    r[0] = mag;   // L > 1: p >= 2^64 > mag
+    if (v < 0) Fp<L, KIND>::neg(r, r, fp);
+}
+
+// canonical inverse by Fermat; returns false for zero
+template <int L, int KIND>
+static bool h_inv(u64* r, const u64* a, const FieldParams& fp) {
+    if (is_zero_n<L>(a)) return false;
+    u64 e[L], two[L];
+    zero_n<L>(two);
+    two[0] = 2;
+    sub_n<L>(e, fp.p, two);
+    u64 x[L];
+    Fp<L, KIND>::to_dom(x, a, fp);
+    Fp<L, KIND>::dpow_uniform(x, x, e, (int)fp.k, fp);
+    Fp<L, KIND>::from_dom(r, x, fp);
+    return true;
+}
+
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+// look up or build a device table; `build` fills a host vector of u64 (already in final form)
+template <class Build>
+static int get_table(mpyc_b200_field* f, const std::string& key, DevTable* out, Build&& build) {
+    std::lock_guard<std::mutex> g(f->mu);
+    auto it = f->tables.find(key);
+    if (it != f->tables.end()) {
+        *out = it->second;
+        return MPYC_B200_OK;
+    }
+    std::vector<u64> host;
+    bool full = false;
+    int rc = build(host, full);
+    if (rc != MPYC_B200_OK) return rc;
+    if (host.size() % 2) host.push_back(0);   // bulk copies move multiples of 16 bytes
+    if (host.empty()) host.assign(2, 0);
+    DevTable t;
+    t.bytes = (u32)(host.size() * sizeof(u64));
+    t.full = full;
+    CU(cudaMalloc(&t.d, t.bytes));
+    cudaError_t e = cudaMemcpy(t.d, host.data(), t.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(t.d);
+        return cuda_fail(e, "table upload");
+    }
+    f->tables[key] = t;
+    *out = t;
+    return MPYC_B200_OK;
+}
+
+#define MAX_SMEM_TABLE (40u * 1024u)   // tables are staged in the default 48 KB dynamic shared memory window
+
+// Vandermonde table for share generation: row i, column j = (i+1)^j
+static int build_split_table(const FieldParams& fp, int t, int m, std::vector<u64>& host, bool& full) {
+    // 64-bit-constant form when the field is pseudo-Mersenne and m^t < 2^59
+    bool small = fp.kind != KIND_GENERIC && t <= 8;
+    if (small) {
+        long double lim = 1;
+        for (int j = 0; j < t; j++) lim *= m;
+        if (lim >= 576460752303423488.0L) small = false;   // 2^59
+    }
+    full = !small;
+    if (small) {
+        host.resize((size_t)m * (t + 1));
+        for (int i = 0; i < m; i++) {
+            u64 x = 1;
+            for (int j = 0; j <= t; j++) {
+                host[(size_t)i * (t + 1) + j] = x;
+                x *= (u64)(i + 1);
+            }
+        }
+        return MPYC_B200_OK;
+    }
+    return with_field(fp, [&](auto Lc, auto Kc) {
+        constexpr int L = decltype(Lc)::value;
+        constexpr int K = decltype(Kc)::value;
+        host.resize((size_t)m * (t + 1) * L);
+        for (int i = 0; i < m; i++) {
+            u64 pt[L], x[L];
+            h_from_int<L, K>(pt, i + 1, fp);
+            h_from_int<L, K>(x, 1, fp);
+            for (int j = 0; j <= t; j++) {
+                u64 tf[L];
+                Fp<L, K>::to_dom(tf, x, fp);
+                for (int l = 0; l < L; l++) host[((size_t)i * (t + 1) + j) * L + l] = tf[l];
+                Fp<L, K>::mul(x, x, pt, fp);
+            }
+        }
+        return MPYC_B200_OK;
+    });
+}
+
+// lambda[r][i] (canonical) for x-coordinates xs and recombination points x_rs
+static int compute_lambda(const FieldParams& fp, const int64_t* xs, int k, const int64_t* x_rs, int width,
+                          std::vector<u64>& lam) {
+    return with_field(fp, [&](auto Lc, auto Kc) {
+        constexpr int L = decltype(Lc)::value;
+        constexpr int K = decltype(Kc)::value;
+        typedef Fp<L, K> F;
+        lam.assign((size_t)width * k * L, 0);
+        std::vector<u64> X((size_t)k * L);
+        for (int i = 0; i < k; i++) h_from_int<L, K>(&X[(size_t)i * L], xs[i], fp);
+        for (int r = 0; r < width; r++) {
+            u64 xr[L];
+            h_from_int<L, K>(xr, x_rs[r], fp);
+            for (int i = 0; i < k; i++) {
+                u64 num[L], den[L], d[L];
+                h_from_int<L, K>(num, 1, fp);
+                h_from_int<L, K>(den, 1, fp);
+                for (int j = 0; j < k; j++) {
+                    if (j == i) continue;
+                    F::sub(d, xr, &X[(size_t)j * L], fp);
+                    F::mul(num, num, d, fp);
+                    F::sub(d, &X[(size_t)i * L], &X[(size_t)j * L], fp);
+                    F::mul(den, den, d, fp);
+                }
+                u64 inv[L];
+                if (!h_inv<L, K>(inv, den, fp)) return fail(MPYC_B200_EZERODIV, "recombination: repeated x-coordinate");
+                F::mul(&lam[((size_t)r * k + i) * L], num, inv, fp);
+            }
+        }
+        return MPYC_B200_OK;
+    });
+}
+
+static void to_table_form(const FieldParams& fp, std::vector<u64>& v) {
+    with_field(fp, [&](auto Lc, auto Kc) {
+        constexpr int L = decltype(Lc)::value;
+        constexpr int K = decltype(Kc)::value;
+        for (size_t i = 0; i + L <= v.size(); i += L) Fp<L, K>::to_dom(&v[i], &v[i], fp);
+        return 0;
+    });
+}
+
+static std::string key_of(const char* tag, int dev, const int64_t* a, int na, const int64_t* b, int nb) {
+    std::string s = tag;
+    s += ":" + std::to_string(dev) + ":";
+    for (int i = 0; i < na; i++) s += std::to_string(a[i]) + ",";
+    s += "|";
+    for (int i = 0; i < nb; i++) s += std::to_string(b[i]) + ",";
+    return s;
+}
+
+#define REQUIRE_PRIME(f, what) \
+    if ((f)->kind == MPYC_B200_KIND_GF256) return fail(MPYC_B200_EUNSUPPORTED, what ": not defined for GF(2^8)")
+
+// ---------------------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------------------
+
+static int launch_status(cudaError_t e, const char* what) { return e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, what); }
+
+static int binop_impl(const mpyc_b200_field* f, int op, const void* a, const void* b, const uint64_t* scal, void* out,
+                      size_t n, void* stream) {
+    if (!f || (n && (!a || !out))) return fail(MPYC_B200_EINVAL, "ff_binop: null argument");
+    if (op < 0 || op > 3) return fail(MPYC_B200_EINVAL, "ff_binop: unknown op");
+    if (n && op != OP_NEG && !b && !scal) return fail(MPYC_B200_EINVAL, "ff_binop: second operand missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256)
+        return launch_status(gf256_binop(f->gf_poly, op, (const unsigned char*)a, (const unsigned char*)b,
+                                         scal ? (int)(scal[0] & 0xFF) : -1, (unsigned char*)out, n, st),
+                             "gf256 binop");
+    if (scal && bit_length((const u64*)scal, (int)f->fp.L) > (int)f->fp.k)
+        return fail(MPYC_B200_EINVAL, "ff_binop_scalar: scalar is not a canonical residue");
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::binop(f->fp, op, (const u64*)a, (const u64*)b, (const u64*)scal, (u64*)out, n, st),
+                             "ff_binop launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_binop(const mpyc_b200_field* f, int op, const void* d_a, const void* d_b, void* d_out,
+                                  size_t n, void* stream) {
+    if (op < 0 || op > 2) return fail(MPYC_B200_EINVAL, "ff_binop: op must be ADD, SUB or MUL");
+    return binop_impl(f, op, d_a, d_b, nullptr, d_out, n, stream);
+}
+
+MPYC_API int mpyc_b200_ff_binop_scalar(const mpyc_b200_field* f, int op, const void* d_a, const uint64_t* h_scalar,
+                                         void* d_out, size_t n, void* stream) {
+    if (op < 0 || op > 2 || !h_scalar) return fail(MPYC_B200_EINVAL, "ff_binop_scalar: bad arguments");
+    return binop_impl(f, op, d_a, nullptr, h_scalar, d_out, n, stream);
+}
+
+MPYC_API int mpyc_b200_ff_neg(const mpyc_b200_field* f, const void* d_a, void* d_out, size_t n, void* stream) {
+    return binop_impl(f, OP_NEG, d_a, nullptr, nullptr, d_out, n, stream);
+}
+
+// ---- pow family ------------------------------------------------------------------------------
+
+struct ZeroFlag {   // one device int per call, freed on scope exit
+    int* d = nullptr;
+    ~ZeroFlag() {
+        if (d) cudaFree(d);
+    }
+};
+
+static int pow_impl(const mpyc_b200_field* f, const void* d_a, const u64* e, int elimbs, int mode, bool check_zero,
+                    void* d_out, unsigned char* d_out8, size_t n, cudaStream_t st) {
+    ExpParams ex;
+    memset(&ex, 0, sizeof ex);
+    if (elimbs > 8) return fail(MPYC_B200_EUNSUPPORTED, "exponent wider than 512 bits");
+    for (int i = 0; i < elimbs; i++) ex.e[i] = e[i];
+    ex.ebits = bit_length(ex.e, 8);
+    ZeroFlag zf;
+    if (check_zero) {
+        CU(cudaMalloc(&zf.d, sizeof(int)));
+        CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+    }
+    int rc = with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::pow(f->fp, ex, mode, (const u64*)d_a, (u64*)d_out, d_out8, zf.d, n, st), "ff_pow launch");
+    });
+    if (rc != MPYC_B200_OK) return rc;
+    if (check_zero) {
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, zf.d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (flag) return fail(MPYC_B200_EZERODIV, "inverse of zero");
+    }
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_ff_pow(const mpyc_b200_field* f, const void* d_a, const uint64_t* h_exponent, int exp_nlimbs,
+                                void* d_out, size_t n, void* stream) {
+    if (!f || !h_exponent || exp_nlimbs < 1 || (n && (!d_a || !d_out))) return fail(MPYC_B200_EINVAL, "ff_pow: bad arguments");
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        u64 e = h_exponent[0];
+        for (int i = 1; i < exp_nlimbs; i++)
+            if (h_exponent[i]) return fail(MPYC_B200_EUNSUPPORTED, "gf256 pow: reduce the exponent mod 255 first");
+        return launch_status(gf256_pow(f->gf_poly, (const unsigned char*)d_a, e, (unsigned char*)d_out, nullptr, n,
+                                       (cudaStream_t)stream), "gf256 pow");
+    }
+    return pow_impl(f, d_a, (const u64*)h_exponent, exp_nlimbs, 0, false, d_out, nullptr, n, (cudaStream_t)stream);
+}
+
+MPYC_API int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d_out, size_t n, void* stream) {
+    if (!f || (n && (!d_a || !d_out))) return fail(MPYC_B200_EINVAL, "ff_inv: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        ZeroFlag zf;
+        CU(cudaMalloc(&zf.d, sizeof(int)));
+        CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+        int rc = launch_status(gf256_pow(f->gf_poly, (const unsigned char*)d_a, 254, (unsigned char*)d_out, zf.d, n, st), "gf256 inv");
+        if (rc) return rc;
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, zf.d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return flag ? fail(MPYC_B200_EZERODIV, "inverse of zero") : MPYC_B200_OK;
+    }
+    u64 e[4] = {0, 0, 0, 0}, two[4] = {2, 0, 0, 0};
+    sub_n<4>(e, f->fp.p, two);
+    return pow_impl(f, d_a, e, 4, 0, true, d_out, nullptr, n, st);
+}
+
+MPYC_API int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int inverse, void* d_out, size_t n, void* stream) {
+    if (!f || (n && (!d_a || !d_out))) return fail(MPYC_B200_EINVAL, "ff_sqrt: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        // finfields.py:1552-1563: a^(q/2), inverse: a^(q/2 - 1)
+        ZeroFlag zf;
+        if (inverse) {
+            CU(cudaMalloc(&zf.d, sizeof(int)));
+            CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+        }
+        int rc = launch_status(gf256_pow(f->gf_poly, (const unsigned char*)d_a, inverse ? 127 : 128, (unsigned char*)d_out, zf.d, n, st), "gf256 sqrt");
+        if (rc || !inverse) return rc;
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, zf.d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return flag ? fail(MPYC_B200_EZERODIV, "no inverse sqrt of 0") : MPYC_B200_OK;
+    }
+    if ((f->fp.p[0] & 3) != 3) return fail(MPYC_B200_EUNSUPPORTED, "ff_sqrt: batched path needs a Blum prime (p % 4 == 3)");
+    // e = (p+1)/4, or (3p-5)/4 for the inverse square root; up to 258 bits -> 5 limbs
+    u64 e[8] = {0};
+    if (!inverse) {
+        u64 t[5] = {0}, one[5] = {1, 0, 0, 0, 0}, pp[5] = {f->fp.p[0], f->fp.p[1], f->fp.p[2], f->fp.p[3], 0};
+        add_n<5>(t, pp, one);
+        for (int i = 0; i < 5; i++) e[i] = (t[i] >> 2) | (i < 4 ? (t[i + 1] << 62) : 0);
+    } else {
+        u64 pp[5] = {f->fp.p[0], f->fp.p[1], f->fp.p[2], f->fp.p[3], 0}, t[5], five[5] = {5, 0, 0, 0, 0};
+        add_n<5>(t, pp, pp);
+        add_n<5>(t, t, pp);
+        sub_n<5>(t, t, five);
+        for (int i = 0; i < 5; i++) e[i] = (t[i] >> 2) | (i < 4 ? (t[i + 1] << 62) : 0);
+    }
+    return pow_impl(f, d_a, e, 5, 0, inverse != 0, d_out, nullptr, n, st);
+}
+
+MPYC_API int mpyc_b200_ff_is_sqr(const mpyc_b200_field* f, const void* d_a, uint8_t* d_out_u8, size_t n, void* stream) {
+    if (!f || (n && (!d_a || !d_out_u8))) return fail(MPYC_B200_EINVAL, "ff_is_sqr: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {   // every element of GF(2^8) is a square
+        CU(cudaMemsetAsync(d_out_u8, 1, n, st));
+        return MPYC_B200_OK;
+    }
+    u64 e[4];
+    for (int i = 0; i < 4; i++) e[i] = (f->fp.p[i] >> 1) | (i < 3 ? (f->fp.p[i + 1] << 63) : 0);   // (p-1)/2
+    return pow_impl(f, d_a, e, 4, 1, false, nullptr, d_out_u8, n, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// Shamir split
+// ---------------------------------------------------------------------------------------
+
+static int split_table(const mpyc_b200_field* cf, int t, int m, DevTable* tab) {
+    mpyc_b200_field* f = const_cast<mpyc_b200_field*>(cf);
+    int64_t key[2] = {t, m};
+    return get_table(f, key_of("split", current_device(), key, 2, nullptr, 0), tab,
+                     [&](std::vector<u64>& host, bool& full) { return build_split_table(f->fp, t, m, host, full); });
+}
+
+MPYC_API int mpyc_b200_shamir_split(const mpyc_b200_field* f, const void* d_secrets, const void* d_coeffs,
+                                      size_t coeff_stride, void* d_shares, size_t share_stride, size_t n, int t, int m,
+                                      void* stream) {
+    if (!f) return fail(MPYC_B200_EINVAL, "shamir_split: field is null");
+    if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
+    if (n == 0) return MPYC_B200_OK;
+    if (!d_secrets || !d_shares || (t > 0 && !d_coeffs)) return fail(MPYC_B200_EINVAL, "shamir_split: null buffer");
+    if (share_stride < n || (t > 1 && coeff_stride < n)) return fail(MPYC_B200_EINVAL, "shamir_split: stride < n");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        if (m > 255) return fail(MPYC_B200_EUNSUPPORTED, "GF(2^8) has only 255 nonzero points");
+        return launch_status(gf256_split(f->gf_poly, (const unsigned char*)d_secrets, (const unsigned char*)d_coeffs,
+                                         coeff_stride, (unsigned char*)d_shares, share_stride, n, t, m, st),
+                             "gf256 split");
+    }
+    DevTable tab;
+    int rc = split_table(f, t, m, &tab);
+    if (rc) return rc;
+    if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "shamir_split: (m, t) table exceeds shared memory");
+    const size_t L = f->fp.L;
+    return with_limbs((int)L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::split(f->fp, tab.full, (const u64*)d_secrets, (const u64*)d_coeffs,
+                                               coeff_stride * LL, (u64*)d_shares, share_stride * LL, n, t, m, tab.d,
+                                               tab.bytes, st),
+                             "shamir_split launch");
+    });
+}
+
+MPYC_API int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secrets, void* d_shares,
+                                               size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
+                                               uint64_t nonce, void* stream) {
+    (void)d_secrets; (void)d_shares; (void)share_stride; (void)n; (void)t; (void)m; (void)key32; (void)nonce; (void)stream;
+    if (!f) return fail(MPYC_B200_EINVAL, "field is null");
+    return fail(MPYC_B200_EUNSUPPORTED, "shamir_split_generate: not built in this revision");
+}
+
+// ---------------------------------------------------------------------------------------
+// recombination
+// ---------------------------------------------------------------------------------------
+
+MPYC_API int mpyc_b200_recombination_vector(const mpyc_b200_field* f, const int64_t* xs, int k, const int64_t* x_rs,
+                                              int width, uint64_t* h_lambda) {
+    if (!f || !xs || !x_rs || !h_lambda || k < 1 || width < 1) return fail(MPYC_B200_EINVAL, "recombination_vector: bad arguments");
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        std::vector<unsigned char> lam((size_t)width * k);
+        int rc = gf256_lambda(f->gf_poly, xs, k, x_rs, width, lam.data());
+        if (rc) return fail(rc, "recombination: repeated x-coordinate");
+        for (size_t i = 0; i < lam.size(); i++) h_lambda[i] = lam[i];
+        return MPYC_B200_OK;
+    }
+    std::vector<u64> lam;
+    int rc = compute_lambda(f->fp, xs, k, x_rs, width, lam);
+    if (rc) return rc;
+    memcpy(h_lambda, lam.data(), lam.size() * sizeof(u64));
+    return MPYC_B200_OK;
+}
+
+static int recombine_table(const mpyc_b200_field* cf, const int64_t* xs, int k, const int64_t* x_rs, int width, DevTable* tab) {
+    mpyc_b200_field* f = const_cast<mpyc_b200_field*>(cf);
+    return get_table(f, key_of("rec", current_device(), xs, k, x_rs, width), tab, [&](std::vector<u64>& host, bool& full) {
+        full = true;
+        int rc = compute_lambda(f->fp, xs, k, x_rs, width, host);
+        if (rc) return rc;
+        to_table_form(f->fp, host);
+        return MPYC_B200_OK;
+    });
+}
+
+MPYC_API int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* const* d_share_rows, const int64_t* xs,
+                                          int k, const int64_t* x_rs, int width, void* d_out, size_t out_stride, size_t n,
+                                          void* stream) {
+    if (!f || !d_share_rows || !xs || !x_rs) return fail(MPYC_B200_EINVAL, "shamir_recombine: null argument");
+    if (k < 1 || width < 1) return fail(MPYC_B200_EINVAL, "shamir_recombine: need k >= 1 and width >= 1");
+    if (k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EUNSUPPORTED, "shamir_recombine: more than MPYC_B200_MAX_POINTS shares");
+    if (n == 0) return MPYC_B200_OK;
+    if (!d_out || (width > 1 && out_stride < n)) return fail(MPYC_B200_EINVAL, "shamir_recombine: bad output");
+    for (int i = 0; i < k; i++)
+        if (!d_share_rows[i]) return fail(MPYC_B200_EINVAL, "shamir_recombine: null share row");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        std::vector<unsigned char> lam((size_t)width * k);
+        int rc = gf256_lambda(f->gf_poly, xs, k, x_rs, width, lam.data());
+        if (rc) return fail(rc, "recombination: repeated x-coordinate");
+        return launch_status(gf256_recombine(f->gf_poly, (const unsigned char* const*)d_share_rows, k, width, lam.data(),
+                                             (unsigned char*)d_out, out_stride, n, st), "gf256 recombine");
+    }
+    DevTable tab;
+    int rc = recombine_table(f, xs, k, x_rs, width, &tab);
+    if (rc) return rc;
+    if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "shamir_recombine: table exceeds shared memory");
+    RowPtrs rows;
+    memset(&rows, 0, sizeof rows);
+    for (int i = 0; i < k; i++) rows.p[i] = (const u64*)d_share_rows[i];
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::recombine(f->fp, rows, k, width, tab.d, tab.bytes, (u64*)d_out, out_stride * LL, n, st),
+                             "shamir_recombine launch");
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// PRSS linear step
+// ---------------------------------------------------------------------------------------
+
+MPYC_API int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes,
+                                      int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                                      const uint64_t* h_weights, void* d_out, size_t n, void* stream) {
+    if (!f || !h_coef || !h_weights || nsub < 1 || d < 1 || chunk_bytes < 1) return fail(MPYC_B200_EINVAL, "prss_combine: bad arguments");
+    if (n == 0) return MPYC_B200_OK;
+    if (!d_prf_bytes || !d_out) return fail(MPYC_B200_EINVAL, "prss_combine: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        if (chunk_bytes != 1 || (bound_bits != 0 && bound_bits != 8)) return fail(MPYC_B200_EINVAL, "prss_combine: GF(2^8) PRF chunks are one byte");
+        std::vector<unsigned char> tab((size_t)nsub + d);
+        for (int i = 0; i < nsub; i++) tab[i] = (unsigned char)h_coef[i];
+        for (int j = 0; j < d; j++) tab[nsub + j] = (unsigned char)h_weights[j];
+        return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.data(), (unsigned char*)d_out, n, st), "gf256 prss");
+    }
+    if (chunk_bytes > 8 * (int)f->fp.L + 32) return fail(MPYC_B200_EINVAL, "prss_combine: chunk too wide for this field");
+    if (bound_bits < 0 || bound_bits >= (int)f->fp.k) return fail(MPYC_B200_EINVAL, "prss_combine: need 2^bound_bits <= p");
+    if (bound_bits > 0 && chunk_bytes != (bound_bits + 7) / 8) return fail(MPYC_B200_EINVAL, "prss_combine: chunk_bytes != ceil(bound_bits/8)");
+    if ((unsigned)nsub > FF_MAX_LAZY_TERMS || (unsigned)d > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "prss_combine: too many terms");
+    const size_t L = f->fp.L;
+    std::vector<u64> host(((size_t)nsub + d) * L);
+    memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
+    memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
+    to_table_form(f->fp, host);
+    if (host.size() % 2) host.push_back(0);
+    const u32 bytes = (u32)(host.size() * sizeof(u64));
+    if (bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss_combine: coefficient table exceeds shared memory");
+    // per-call table (coefficients depend on the party and subset layout): stream-ordered allocation
+    u64* d_tab = nullptr;
+    CU(cudaMallocAsync(&d_tab, bytes, st));
+    cudaError_t e = cudaMemcpyAsync(d_tab, host.data(), bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vector goes out of scope
+    int rc = e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "prss table upload");
+    if (rc == MPYC_B200_OK)
+        rc = with_limbs((int)L, [&](auto Lc) {
+            constexpr int LL = decltype(Lc)::value;
+            return launch_status(Launch<LL>::prss(f->fp, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, d_tab, bytes,
+                                                  (u64*)d_out, n, st), "prss_combine launch");
+        });
+    cudaFreeAsync(d_tab, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------
+
+MPYC_API int mpyc_b200_fill_random(const mpyc_b200_field* f, void* d_out, size_t n, uint64_t seed, uint64_t stream_id,
+                                     void* stream) {
+    if (!f || (n && !d_out)) return fail(MPYC_B200_EINVAL, "fill_random: bad arguments");
+    const u64 base = seed + (stream_id << 56);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256)
+        return launch_status(gf256_fill(base, (unsigned char*)d_out, n, st), "gf256 fill");
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::fill_random(f->fp, (u64*)d_out, n, base, st), "fill_random launch");
+    });
+}
+
+MPYC_API int mpyc_b200_count_mismatch(const mpyc_b200_field* f, const void* d_a, const void* d_b, size_t n,
+                                        uint64_t* d_count, void* stream) {
+    if (!f || !d_count || (n && (!d_a || !d_b))) return fail(MPYC_B200_EINVAL, "count_mismatch: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (n == 0) return MPYC_B200_OK;
+    if (f->kind == MPYC_B200_KIND_GF256)
+        return launch_status(gf256_mismatch((const unsigned char*)d_a, (const unsigned char*)d_b, n, (unsigned long long*)d_count, st), "gf256 mismatch");
+    int grid = mpyc_grid_size((const void*)k_count_mismatch, n, 0);
+    if (grid <= 0) return fail(MPYC_B200_ECUDA, "count_mismatch: no device");
+    k_count_mismatch<<<grid, MPYC_THREADS, 0, st>>>((const u64*)d_a, (const u64*)d_b, n, (int)f->fp.L, (unsigned long long*)d_count);
+    g_mpyc_launches.fetch_add(1);
+    return launch_status(cudaGetLastError(), "count_mismatch launch");
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer pipelines: H2D copy, kernel and D2H copy of successive chunks overlap on
+// three streams; device staging buffers are kept per device and grown on demand.
+// ---------------------------------------------------------------------------------------
+
+namespace {
+
+constexpr int kSlots = 3;
+
+struct Workspace {
+    int device = -1;
+    cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+    void* d_in[kSlots] = {nullptr, nullptr, nullptr};
+    void* d_out[kSlots] = {nullptr, nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+    std::mutex mu;
+};
+
+Workspace g_ws[16];
+std::mutex g_ws_mu;
+
+int acquire_workspace(int device, size_t in_bytes, size_t out_bytes, Workspace** out) {
+    if (device < 0 || device >= 16) return fail(MPYC_B200_EINVAL, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    Workspace& w = g_ws[device];
+    {
+        std::lock_guard<std::mutex> g(g_ws_mu);
+        if (w.device < 0) {
+            for (int s = 0; s < kSlots; s++) CU(cudaStreamCreateWithFlags(&w.streams[s], cudaStreamNonBlocking));
+            w.device = device;
+        }
+    }
+    if (in_bytes > w.in_cap) {
+        for (int s = 0; s < kSlots; s++) {
+            if (w.d_in[s]) cudaFree(w.d_in[s]);
+            w.d_in[s] = nullptr;
+        }
+        w.in_cap = 0;
+        for (int s = 0; s < kSlots; s++) CU(cudaMalloc(&w.d_in[s], in_bytes));
+        w.in_cap = in_bytes;
+    }
+    if (out_bytes > w.out_cap) {
+        for (int s = 0; s < kSlots; s++) {
+            if (w.d_out[s]) cudaFree(w.d_out[s]);
+            w.d_out[s] = nullptr;
+        }
+        w.out_cap = 0;
+        for (int s = 0; s < kSlots; s++) CU(cudaMalloc(&w.d_out[s], out_bytes));
+        w.out_cap = out_bytes;
+    }
+    *out = &w;
+    return MPYC_B200_OK;
+}
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// elements per pipeline chunk: ~32 MiB of traffic per chunk, multiple of 16 elements
+size_t chunk_elems(size_t n, size_t bytes_per_elem_total) {
+    size_t c = (32u << 20) / std::max<size_t>(bytes_per_elem_total, 1);
+    c = std::max<size_t>(c / 16 * 16, 16);
+    return std::min(c, round_up(n, 16));
+}
+
+}   // namespace
+
+MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
+                                           size_t coeff_stride, void* h_shares, size_t share_stride, size_t n, int t, int m,
+                                           int device) {
+    if (!f) return fail(MPYC_B200_EINVAL, "field is null");
+    if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
+    if (n == 0) return MPYC_B200_OK;
+    if (!h_secrets || !h_shares || (t > 0 && !h_coeffs)) return fail(MPYC_B200_EINVAL, "shamir_split_host: null buffer");
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    const size_t ch = chunk_elems(n, eb * (size_t)(t + 1 + m));
+    Workspace* w;
+    int rc = acquire_workspace(device, ch * eb * (size_t)(t + 1), ch * eb * (size_t)m, &w);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(w->mu);
+    size_t c = 0;
+    for (size_t off = 0; off < n; off += ch, c++) {
+        const int s = (int)(c % kSlots);
+        const size_t cn = std::min(ch, n - off);
+        cudaStream_t st = w->streams[s];
+        char* din = (char*)w->d_in[s];
+        char* dout = (char*)w->d_out[s];
+        CU(cudaMemcpyAsync(din, (const char*)h_secrets + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+        if (t > 0)
+            CU(cudaMemcpy2DAsync(din + ch * eb, ch * eb, (const char*)h_coeffs + off * eb, coeff_stride * eb, cn * eb, t,
+                                 cudaMemcpyHostToDevice, st));
+        rc = mpyc_b200_shamir_split(f, din, din + ch * eb, ch, dout, ch, cn, t, m, st);
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m,
+                             cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const void* const* h_share_rows, const int64_t* xs,
+                                               int k, const int64_t* x_rs, int width, void* h_out, size_t out_stride,
+                                               size_t n, int device) {
+    if (!f || !h_share_rows || !xs || !x_rs) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: null argument");
+    if (k < 1 || width < 1 || k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: bad k/width");
+    if (n == 0) return MPYC_B200_OK;
+    if (!h_out) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: null output");
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    const size_t ch = chunk_elems(n, eb * (size_t)(k + width));
+    Workspace* w;
+    int rc = acquire_workspace(device, ch * eb * (size_t)k, ch * eb * (size_t)width, &w);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(w->mu);
+    size_t c = 0;
+    for (size_t off = 0; off < n; off += ch, c++) {
+        const int s = (int)(c % kSlots);
+        const size_t cn = std::min(ch, n - off);
+        cudaStream_t st = w->streams[s];
+        char* din = (char*)w->d_in[s];
+        char* dout = (char*)w->d_out[s];
+        const void* rows[MPYC_B200_MAX_POINTS];
+        for (int i = 0; i < k; i++) {
+            CU(cudaMemcpyAsync(din + (size_t)i * ch * eb, (const char*)h_share_rows[i] + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+            rows[i] = din + (size_t)i * ch * eb;
+        }
+        rc = mpyc_b200_shamir_recombine(f, rows, xs, k, x_rs, width, dout, ch, cn, st);
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync((char*)h_out + off * eb, out_stride * eb, dout, ch * eb, cn * eb, width, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const void* h_a, const void* h_b, void* h_out,
+                                       size_t n, int device) {
+    if (!f || (n && (!h_a || !h_b || !h_out))) return fail(MPYC_B200_EINVAL, "ff_binop_host: null argument");
+    if (n == 0) return MPYC_B200_OK;
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    const size_t ch = chunk_elems(n, eb * 3);
+    Workspace* w;
+    int rc = acquire_workspace(device, ch * eb * 2, ch * eb, &w);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(w->mu);
+    size_t c = 0;
+    for (size_t off = 0; off < n; off += ch, c++) {
+        const int s = (int)(c % kSlots);
+        const size_t cn = std::min(ch, n - off);
+        cudaStream_t st = w->streams[s];
+        char* din = (char*)w->d_in[s];
+        char* dout = (char*)w->d_out[s];
+        CU(cudaMemcpyAsync(din, (const char*)h_a + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(din + ch * eb, (const char*)h_b + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+        rc = mpyc_b200_ff_binop(f, op, din, din + ch * eb, dout, cn, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync((char*)h_out + off * eb, dout, cn * eb, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    return MPYC_B200_OK;
+}

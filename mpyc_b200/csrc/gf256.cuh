@@ -1,0 +1,270 @@
+// GF(2^8) = GF(2)[X]/(poly) kernels: one byte per element (the AES field of demos/np_aes.py when
+// poly = 283).  Replaces BinaryFieldArray over gfpx.BinaryPolynomial objects
+// (reference mpyc/finfields.py:1542-1563, mpyc/gfpx.py:983-1045,1085-1096) and the GF(2^8)
+// instances of thresha.np_random_split / np_recombine (points are the field elements whose
+// integer encoding is the party index, thresha.py:54,61).
+//
+// Bulk kernels work on 8 packed bytes per 64-bit word (SWAR shift-and-add multiplication);
+// constant multipliers (Vandermonde / Lagrange entries) only XOR the needed x^b multiples.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+extern std::atomic<unsigned long long> g_mpyc_launches;
+int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem);
+
+#define GF_THREADS 256
+#define GF_MAX_TAB 2048
+
+struct GfTab {
+    unsigned char v[GF_MAX_TAB];
+};
+struct GfRows {
+    const unsigned char* p[64];
+};
+
+__host__ __device__ __forceinline__ unsigned gf_mul1(unsigned a, unsigned b, unsigned poly) {
+    unsigned acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        acc ^= (b & 1u) ? a : 0u;
+        b >>= 1;
+        a <<= 1;
+        if (a & 0x100u) a ^= poly;
+    }
+    return acc & 0xFFu;
+}
+
+__host__ __device__ __forceinline__ unsigned gf_pow1(unsigned a, unsigned long long e, unsigned poly) {
+    unsigned r = 1;
+    for (int i = 63; i >= 0; i--) {
+        r = gf_mul1(r, r, poly);
+        if ((e >> i) & 1ull) r = gf_mul1(r, a, poly);
+    }
+    return r;
+}
+
+// 8 bytes at a time: multiply every byte of a by x
+__device__ __forceinline__ unsigned long long gf_xtime8(unsigned long long a, unsigned long long red) {
+    unsigned long long hi = (a >> 7) & 0x0101010101010101ull;
+    return ((a & 0x7F7F7F7F7F7F7F7Full) << 1) ^ (hi * red);
+}
+// bytewise product of two packed words
+__device__ __forceinline__ unsigned long long gf_mul8(unsigned long long a, unsigned long long b, unsigned long long red) {
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        unsigned long long m = ((b >> i) & 0x0101010101010101ull) * 0xFFull;
+        acc ^= a & m;
+        a = gf_xtime8(a, red);
+    }
+    return acc;
+}
+// packed word times one constant byte c (warp-uniform)
+__device__ __forceinline__ unsigned long long gf_mulc8(unsigned long long a, unsigned c, unsigned long long red) {
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if ((c >> i) & 1u) acc ^= a;
+        a = gf_xtime8(a, red);
+    }
+    return acc;
+}
+
+// ---- elementwise: op 0/1 xor, 2 mul, 3 neg(copy); scalar >= 0 broadcasts b -----------------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_binop(unsigned poly, int op, const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, int scalar,
+           unsigned char* __restrict__ out, size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long red = poly & 0xFFu;
+    const bool al = (((uintptr_t)a | (uintptr_t)out | (scalar >= 0 || op == 3 ? 0 : (uintptr_t)b)) & 7u) == 0;
+    const size_t nw = al ? n / 8 : 0;
+    for (size_t w = tid; w < nw; w += nth) {
+        unsigned long long x = ((const unsigned long long*)a)[w];
+        unsigned long long y = (scalar >= 0) ? (unsigned long long)scalar * 0x0101010101010101ull
+                                             : (op == 3 ? 0ull : ((const unsigned long long*)b)[w]);
+        unsigned long long r = op == 2 ? gf_mul8(x, y, red) : (op == 3 ? x : x ^ y);
+        ((unsigned long long*)out)[w] = r;
+    }
+    for (size_t h = nw * 8 + tid; h < n; h += nth) {
+        unsigned x = a[h], y = scalar >= 0 ? (unsigned)scalar : (op == 3 ? 0u : b[h]);
+        out[h] = (unsigned char)(op == 2 ? gf_mul1(x, y, poly) : (op == 3 ? x : x ^ y));
+    }
+}
+
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_pow(unsigned poly, const unsigned char* __restrict__ a, unsigned long long e, unsigned char* __restrict__ out,
+         int* zero_flag, size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        unsigned x = a[h];
+        if (zero_flag && x == 0) *zero_flag = 1;
+        out[h] = (unsigned char)gf_pow1(x, e, poly);
+    }
+}
+
+// ---- split: shares[i][h] = sum_j (i+1)^j M[j][h]; tab[i*(t+1)+j] = (i+1)^j ------------------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_split(unsigned poly, GfTab tab, const unsigned char* __restrict__ secrets, const unsigned char* __restrict__ coeffs,
+           size_t cstride, unsigned char* __restrict__ shares, size_t sstride, size_t n, int t, int m) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long red = poly & 0xFFu;
+    const bool al = ((((uintptr_t)secrets | (uintptr_t)shares | (t ? (uintptr_t)coeffs : 0)) & 7u) == 0) &&
+                    (cstride % 8 == 0 || t <= 1) && (sstride % 8 == 0 || m <= 1);
+    const size_t nw = al ? n / 8 : 0;
+    for (size_t w = tid; w < nw; w += nth) {
+        for (int i = 0; i < m; i++) {
+            unsigned long long acc = ((const unsigned long long*)secrets)[w];
+            for (int j = 1; j <= t; j++) {
+                unsigned long long x = ((const unsigned long long*)(coeffs + (size_t)(j - 1) * cstride))[w];
+                acc ^= gf_mulc8(x, tab.v[i * (t + 1) + j], red);
+            }
+            ((unsigned long long*)(shares + (size_t)i * sstride))[w] = acc;
+        }
+    }
+    for (size_t h = nw * 8 + tid; h < n; h += nth) {
+        for (int i = 0; i < m; i++) {
+            unsigned acc = secrets[h];
+            for (int j = 1; j <= t; j++) acc ^= gf_mul1(coeffs[(size_t)(j - 1) * cstride + h], tab.v[i * (t + 1) + j], poly);
+            shares[(size_t)i * sstride + h] = (unsigned char)acc;
+        }
+    }
+}
+
+// ---- recombine: out[r][h] = sum_i lam[r*k+i] * rows[i][h] --------------------------------------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_recombine(unsigned poly, GfTab lam, GfRows rows, int k, int width, unsigned char* __restrict__ out, size_t ostride,
+               size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long red = poly & 0xFFu;
+    uintptr_t bits = (uintptr_t)out;
+    for (int i = 0; i < k; i++) bits |= (uintptr_t)rows.p[i];
+    const bool al = ((bits & 7u) == 0) && (ostride % 8 == 0 || width <= 1);
+    const size_t nw = al ? n / 8 : 0;
+    for (size_t w = tid; w < nw; w += nth) {
+        for (int r = 0; r < width; r++) {
+            unsigned long long acc = 0;
+            for (int i = 0; i < k; i++) acc ^= gf_mulc8(((const unsigned long long*)rows.p[i])[w], lam.v[r * k + i], red);
+            ((unsigned long long*)(out + (size_t)r * ostride))[w] = acc;
+        }
+    }
+    for (size_t h = nw * 8 + tid; h < n; h += nth) {
+        for (int r = 0; r < width; r++) {
+            unsigned acc = 0;
+            for (int i = 0; i < k; i++) acc ^= gf_mul1(rows.p[i][h], lam.v[r * k + i], poly);
+            out[(size_t)r * ostride + h] = (unsigned char)acc;
+        }
+    }
+}
+
+// ---- PRSS: out[h] = sum_S coef[S] * sum_j bytes[S][h*d+j] * w[j]; tab = coef | w ---------------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_prss(unsigned poly, GfTab tab, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
+          unsigned char* __restrict__ out, size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        unsigned acc = 0;
+        for (int S = 0; S < nsub; S++) {
+            unsigned y = 0;
+            for (int j = 0; j < d; j++) y ^= gf_mul1(bytes[(size_t)S * subset_stride + h * d + j], tab.v[nsub + j], poly);
+            acc ^= gf_mul1(y, tab.v[S], poly);
+        }
+        out[h] = (unsigned char)acc;
+    }
+}
+
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_fill(unsigned long long base, unsigned char* __restrict__ out, size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        unsigned long long z = base + h + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        out[h] = (unsigned char)((z ^ (z >> 31)) & 0xFF);
+    }
+}
+
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_mismatch(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, size_t n, unsigned long long* count) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) local += a[h] != b[h];
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+// ---- host wrappers ---------------------------------------------------------------------------------
+
+#define GF_LAUNCH(kernel, items, st, ...)                                                   \
+    do {                                                                                    \
+        if ((items) == 0) return cudaSuccess;                                               \
+        int grid__ = mpyc_grid_size((const void*)kernel, (items), 0);                       \
+        if (grid__ <= 0) return cudaErrorLaunchFailure;                                     \
+        kernel<<<grid__, GF_THREADS, 0, st>>>(__VA_ARGS__);                                 \
+        g_mpyc_launches.fetch_add(1, std::memory_order_relaxed);                            \
+        return cudaGetLastError();                                                          \
+    } while (0)
+
+static inline cudaError_t gf256_binop(unsigned poly, int op, const unsigned char* a, const unsigned char* b, int scalar,
+                                      unsigned char* out, size_t n, cudaStream_t st) {
+    GF_LAUNCH(k_gf_binop, (n + 7) / 8, st, poly, op, a, b, scalar, out, n);
+}
+static inline cudaError_t gf256_pow(unsigned poly, const unsigned char* a, unsigned long long e, unsigned char* out,
+                                    int* zero_flag, size_t n, cudaStream_t st) {
+    GF_LAUNCH(k_gf_pow, n, st, poly, a, e, out, zero_flag, n);
+}
+static inline cudaError_t gf256_split(unsigned poly, const unsigned char* secrets, const unsigned char* coeffs,
+                                      size_t cstride, unsigned char* shares, size_t sstride, size_t n, int t, int m,
+                                      cudaStream_t st) {
+    if ((size_t)m * (t + 1) > GF_MAX_TAB) return cudaErrorNotSupported;
+    GfTab tab;
+    for (int i = 0; i < m; i++) {
+        unsigned x = 1;
+        for (int j = 0; j <= t; j++) {
+            tab.v[i * (t + 1) + j] = (unsigned char)x;
+            x = gf_mul1(x, (unsigned)(i + 1), poly);
+        }
+    }
+    GF_LAUNCH(k_gf_split, (n + 7) / 8, st, poly, tab, secrets, coeffs, cstride, shares, sstride, n, t, m);
+}
+// Lagrange coefficients over GF(2^8); returns 0 or MPYC_B200_EZERODIV (-3)
+static inline int gf256_lambda(unsigned poly, const int64_t* xs, int k, const int64_t* x_rs, int width, unsigned char* lam) {
+    for (int r = 0; r < width; r++)
+        for (int i = 0; i < k; i++) {
+            unsigned num = 1, den = 1;
+            for (int j = 0; j < k; j++) {
+                if (j == i) continue;
+                num = gf_mul1(num, (unsigned)((x_rs[r] ^ xs[j]) & 0xFF), poly);
+                den = gf_mul1(den, (unsigned)((xs[i] ^ xs[j]) & 0xFF), poly);
+            }
+            if (den == 0) return -3;
+            lam[r * k + i] = (unsigned char)gf_mul1(num, gf_pow1(den, 254, poly), poly);
+        }
+    return 0;
+}
+static inline cudaError_t gf256_recombine(unsigned poly, const unsigned char* const* rows, int k, int width,
+                                          const unsigned char* lam, unsigned char* out, size_t ostride, size_t n,
+                                          cudaStream_t st) {
+    if ((size_t)k * width > GF_MAX_TAB || k > 64) return cudaErrorNotSupported;
+    GfTab tab;
+    for (int i = 0; i < k * width; i++) tab.v[i] = lam[i];
+    GfRows r;
+    for (int i = 0; i < 64; i++) r.p[i] = i < k ? rows[i] : nullptr;
+    GF_LAUNCH(k_gf_recombine, (n + 7) / 8, st, poly, tab, r, k, width, out, ostride, n);
+}
+static inline cudaError_t gf256_prss(unsigned poly, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+                                     const unsigned char* coef_w, unsigned char* out, size_t n, cudaStream_t st) {
+    if ((size_t)nsub + d > GF_MAX_TAB) return cudaErrorNotSupported;
+    GfTab tab;
+    for (int i = 0; i < nsub + d; i++) tab.v[i] = coef_w[i];
+    GF_LAUNCH(k_gf_prss, n, st, poly, tab, bytes, subset_stride, nsub, d, out, n);
+}
+static inline cudaError_t gf256_fill(unsigned long long base, unsigned char* out, size_t n, cudaStream_t st) {
+    GF_LAUNCH(k_gf_fill, n, st, base, out, n);
+}
+static inline cudaError_t gf256_mismatch(const unsigned char* a, const unsigned char* b, size_t n, unsigned long long* count,
+                                         cudaStream_t st) {
+    GF_LAUNCH(k_gf_mismatch, n, st, a, b, n, count);
+}

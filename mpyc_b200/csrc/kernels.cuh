@@ -1,0 +1,450 @@
+// sm_100a kernels for the GF(p) Shamir hot path.  All kernels are persistent grid-stride
+// streamers: one CTA wave sized from the SM count, 128-bit global loads/stores on the limb
+// arrays (read-once data bypasses L1 allocation), per-call constant tables (Vandermonde /
+// Lagrange, a few hundred bytes) staged global -> shared memory once per CTA with a TMA bulk
+// copy (cp.async.bulk + mbarrier; UBLKCP in SASS).  Integer modular work: no tensor cores.
+//
+//   K1  k_binop / k_binop_scalar / k_neg     finfields.py:1056-1124,1189-1192
+//   K1b k_pow (pow / inverse / sqrt / is_sqr) finfields.py:1408-1470
+//   K2  k_split_small / k_split_full          thresha.py:47-64
+//   K3  k_recombine                           thresha.py:119-132
+//   K4  k_prss_combine                        thresha.py:163-173,201-217
+#pragma once
+#include "ff_arith.cuh"
+
+#define MPYC_MAX_POINTS 64
+#define MPYC_THREADS 256
+
+struct RowPtrs {
+    const u64* p[MPYC_MAX_POINTS];
+};
+
+struct ScalarParam {
+    u64 v[4];
+};
+
+struct ExpParams {
+    u64 e[8];
+    int ebits;
+};
+
+// ---------------------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void ldg_v2(u64& x, u64& y, const u64* p) {
+    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p));
+}
+__device__ __forceinline__ u64 ldg_1(const u64* p) {
+    u64 x;
+    asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(x) : "l"(p));
+    return x;
+}
+__device__ __forceinline__ void stg_v2(u64* p, u64 x, u64 y) {
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+__device__ __forceinline__ void stg_1(u64* p, u64 x) {
+    asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
+}
+
+// load / store NL limbs (NL even when VEC) starting at p
+template <int NL, bool VEC>
+__device__ __forceinline__ void load_limbs(u64* v, const u64* p) {
+    if constexpr (VEC) {
+        static_assert(NL % 2 == 0, "vector path moves limb pairs");
+#pragma unroll
+        for (int q = 0; q < NL / 2; q++) ldg_v2(v[2 * q], v[2 * q + 1], p + 2 * q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NL; q++) v[q] = ldg_1(p + q);
+    }
+}
+template <int NL, bool VEC>
+__device__ __forceinline__ void store_limbs(u64* p, const u64* v) {
+    if constexpr (VEC) {
+#pragma unroll
+        for (int q = 0; q < NL / 2; q++) stg_v2(p + 2 * q, v[2 * q], v[2 * q + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NL; q++) stg_1(p + q, v[q]);
+    }
+}
+
+// elements per vector item: the smallest E with E*L even
+template <int L>
+struct VecItem {
+    static constexpr int E = (L % 2 == 0) ? 1 : 2;
+};
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy of a small table into shared memory (whole CTA waits on the mbarrier)
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// bytes must be a multiple of 16; src and dst 16-byte aligned.  Call from all threads.
+__device__ __forceinline__ void tma_stage_table(void* smem_dst, const void* gmem_src, u32 bytes, u64* mbar) {
+    if (bytes == 0) return;
+    const u32 bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(smem_dst)),
+            "l"(gmem_src), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: elementwise
+// ---------------------------------------------------------------------------------------
+
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_NEG = 3 };
+
+template <int L, int KIND, int OP>
+__device__ __forceinline__ void apply_op(u64* r, const u64* a, const u64* b, const FieldParams& f) {
+    if constexpr (OP == OP_ADD) Fp<L, KIND>::add(r, a, b, f);
+    else if constexpr (OP == OP_SUB) Fp<L, KIND>::sub(r, a, b, f);
+    else if constexpr (OP == OP_MUL) Fp<L, KIND>::mul(r, a, b, f);
+    else Fp<L, KIND>::neg(r, a, f);
+}
+
+// SCALAR: b is one broadcast element (canonical) in sc; NEG ignores b.
+// U items are processed together: all loads are issued before the first multiply.
+template <int L, int KIND, int OP, bool SCALAR, int E, bool VEC, int U>
+__device__ __forceinline__ void binop_items(const FieldParams& f, const u64* a, const u64* b, const u64* sc,
+                                            u64* out, size_t item0, size_t item_step) {
+    u64 x[U][E * L], y[U][E * L];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const size_t off = (item0 + u * item_step) * (size_t)(E * L);
+        load_limbs<E * L, VEC>(x[u], a + off);
+        if constexpr (!SCALAR && OP != OP_NEG) load_limbs<E * L, VEC>(y[u], b + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        u64 r[E * L];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if constexpr (SCALAR) apply_op<L, KIND, OP>(r + e * L, x[u] + e * L, sc, f);
+            else apply_op<L, KIND, OP>(r + e * L, x[u] + e * L, y[u] + e * L, f);
+        }
+        store_limbs<E * L, VEC>(out + (item0 + u * item_step) * (size_t)(E * L), r);
+    }
+}
+
+template <int L, int KIND, int OP, bool SCALAR, bool VEC>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_binop(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, ScalarParam scal,
+        u64* __restrict__ out, size_t n) {
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    constexpr int U = (L <= 2) ? 4 : 2;   // items in flight per thread
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
+    u64 sc[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) sc[i] = scal.v[i];
+    size_t it = tid;
+    for (; it + (U - 1) * nth < n_items; it += U * nth)
+        binop_items<L, KIND, OP, SCALAR, E, VEC, U>(f, a, b, sc, out, it, nth);
+    for (; it < n_items; it += nth) binop_items<L, KIND, OP, SCALAR, E, VEC, 1>(f, a, b, sc, out, it, nth);
+    if constexpr (E > 1) {   // leftover elements
+        for (size_t h = n_items * E + tid; h < n; h += nth)
+            binop_items<L, KIND, OP, SCALAR, 1, false, 1>(f, a, b, sc, out, h, nth);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1b: out = a^e (uniform public exponent).  MODE 0: pow; 1: is_sqr (u8 out, e = (p-1)/2);
+// zero_flag (may be null): set to 1 if any input element is zero (inverse / inverse sqrt).
+// ---------------------------------------------------------------------------------------
+
+template <int L, int KIND, int MODE>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ out, unsigned char* __restrict__ out_u8,
+      int* zero_flag, size_t n) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        u64 x[L], r[L];
+        load_limbs<L, false>(x, a + h * L);
+        if (zero_flag != nullptr && is_zero_n<L>(x)) *zero_flag = 1;
+        Fp<L, KIND>::to_dom(x, x, f);
+        Fp<L, KIND>::dpow_uniform(r, x, ex.e, ex.ebits, f);
+        Fp<L, KIND>::from_dom(r, r, f);
+        if constexpr (MODE == 0) {
+            store_limbs<L, false>(out + h * L, r);
+        } else {
+            // legendre(a, p) == -1  <=>  a^((p-1)/2) == p - 1
+            u64 pm1[L];
+            copy_n<L>(pm1, f.p);
+            pm1[0] -= 1;   // p odd
+            u64 d = 0;
+#pragma unroll
+            for (int i = 0; i < L; i++) d |= r[i] ^ pm1[i];
+            out_u8[h] = d != 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: Shamir share generation.  M[0] = secrets, M[j] = coefficient row j-1.
+//   small: table entry (i, j) is the plain integer (i+1)^j < 2^59 (pseudo-Mersenne fields):
+//          acc (L+1 limbs) = M[0] + sum_j M[j] * v  -> one fold per share
+//   full : table entry is a full field element in table form; acc (2L+1 limbs), one reduction
+// ---------------------------------------------------------------------------------------
+
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
+__device__ __forceinline__ void split_item(const FieldParams& f, const u64* secrets, const u64* coeffs,
+                                           size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
+                                           size_t limb_off) {
+    static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
+    u64 M[TP1][E * L];
+    load_limbs<E * L, VEC>(M[0], secrets + limb_off);
+#pragma unroll
+    for (int j = 1; j < TP1; j++) load_limbs<E * L, VEC>(M[j], coeffs + (size_t)(j - 1) * cstride + limb_off);
+    for (int i = 0; i < m; i++) {
+        u64 r[E * L];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if constexpr (FULL) {
+                u64 acc[2 * L + 1];
+                zero_n<2 * L + 1>(acc);
+#pragma unroll
+                for (int j = 0; j < TP1; j++) Fp<L, KIND>::mac(acc, M[j] + e * L, tab + (size_t)(i * TP1 + j) * L);
+                Fp<L, KIND>::finish(r + e * L, acc, f);
+            } else {
+                u64 acc[L + 1];
+                copy_n<L>(acc, M[0] + e * L);
+                acc[L] = 0;
+#pragma unroll
+                for (int j = 1; j < TP1; j++) mac_1<L, L + 1>(acc, M[j] + e * L, tab[i * TP1 + j]);
+                if constexpr (TP1 > 1) Fp<L, KIND>::template pm_reduce<L + 1>(r + e * L, acc, f);
+                else copy_n<L>(r + e * L, acc);
+            }
+        }
+        store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off, r);
+    }
+}
+
+template <int L, int KIND, int TP1, bool FULL, bool VEC>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
+        u64* __restrict__ shares, size_t sstride, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
+    extern __shared__ __align__(16) u64 stab[];
+    __shared__ __align__(8) u64 mbar;
+    tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
+    for (size_t it = tid; it < n_items; it += nth)
+        split_item<L, KIND, TP1, FULL, E, VEC>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+                                               it * (size_t)(E * L));
+    if constexpr (E > 1) {
+        for (size_t h = n_items * E + tid; h < n; h += nth)
+            split_item<L, KIND, TP1, FULL, 1, false>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+                                                     h * (size_t)L);
+    }
+}
+
+// any t: streams the t+1 input rows per output row (re-reads hit L1/L2); full tables
+template <int L, int KIND>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_split_dyn(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
+            u64* __restrict__ shares, size_t sstride, size_t n, int m, int tp1, const u64* __restrict__ gtab) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        for (int i = 0; i < m; i++) {
+            u64 acc[2 * L + 1];
+            zero_n<2 * L + 1>(acc);
+            for (int j = 0; j < tp1; j++) {
+                u64 x[L], w[L];
+                const u64* src = j == 0 ? secrets + h * L : coeffs + (size_t)(j - 1) * cstride + h * L;
+#pragma unroll
+                for (int l = 0; l < L; l++) {
+                    x[l] = src[l];
+                    w[l] = gtab[(size_t)(i * tp1 + j) * L + l];
+                }
+                Fp<L, KIND>::mac(acc, x, w);
+            }
+            u64 r[L];
+            Fp<L, KIND>::finish(r, acc, f);
+            store_limbs<L, false>(shares + (size_t)i * sstride + h * L, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: Lagrange recombination.  tab[(r*k + i)*L ..] = lambda[r][i] in table form.
+// ---------------------------------------------------------------------------------------
+
+template <int L, int KIND, int E, bool VEC>
+__device__ __forceinline__ void recombine_item(const FieldParams& f, const RowPtrs& rows, int k, int width,
+                                               const u64* tab, u64* out, size_t ostride, size_t limb_off) {
+    constexpr int RB = 4;   // rows loaded per batch (loads issued before the multiplies)
+    for (int r = 0; r < width; r++) {
+        u64 acc[E][2 * L + 1];
+#pragma unroll
+        for (int e = 0; e < E; e++) zero_n<2 * L + 1>(acc[e]);
+        for (int i0 = 0; i0 < k; i0 += RB) {
+            u64 x[RB][E * L];
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (i0 + b < k) load_limbs<E * L, VEC>(x[b], rows.p[i0 + b] + limb_off);
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (i0 + b < k) {
+                    const u64* lam = tab + (size_t)(r * k + i0 + b) * L;
+#pragma unroll
+                    for (int e = 0; e < E; e++) Fp<L, KIND>::mac(acc[e], x[b] + e * L, lam);
+                }
+        }
+        u64 res[E * L];
+#pragma unroll
+        for (int e = 0; e < E; e++) Fp<L, KIND>::finish(res + e * L, acc[e], f);
+        store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off, res);
+    }
+}
+
+template <int L, int KIND, bool VEC>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,
+            u64* __restrict__ out, size_t ostride, size_t n) {
+    extern __shared__ __align__(16) u64 stab[];
+    __shared__ __align__(8) u64 mbar;
+    tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
+    for (size_t it = tid; it < n_items; it += nth)
+        recombine_item<L, KIND, E, VEC>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L));
+    if constexpr (E > 1) {
+        for (size_t h = n_items * E + tid; h < n; h += nth)
+            recombine_item<L, KIND, 1, false>(f, rows, k, width, stab, out, ostride, h * (size_t)L);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: PRSS linear step.  For element h and subset S the PRF output is d chunks of chunk_bytes
+// little-endian bytes at bytes + S*subset_stride + (h*d + j)*chunk_bytes.
+// tab = [coef_S (nsub entries) | weight_j (d entries)], table form.
+// ---------------------------------------------------------------------------------------
+
+template <int L, int KIND>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
+               int chunk_bytes, int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out,
+               size_t n) {
+    extern __shared__ __align__(16) u64 stab[];
+    __shared__ __align__(8) u64 mbar;
+    tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    const u64* coef = stab;
+    const u64* wts = stab + (size_t)nsub * L;
+    const int nl = (chunk_bytes + 7) >> 3;   // limbs per chunk
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        u64 outer[2 * L + 1];
+        zero_n<2 * L + 1>(outer);
+        for (int S = 0; S < nsub; S++) {
+            u64 inner[2 * L + 1];
+            zero_n<2 * L + 1>(inner);
+            for (int j = 0; j < d; j++) {
+                const unsigned char* src = bytes + (size_t)S * subset_stride + (h * d + j) * (size_t)chunk_bytes;
+                // value = little-endian integer of chunk_bytes bytes, reduced limb by limb from the top:
+                // v <- (v * 2^64 + limb) mod p   ((L+1)-limb value < 2^64 p)
+                u64 v[L];
+                zero_n<L>(v);
+                for (int w = nl - 1; w >= 0; w--) {
+                    u64 limb = 0;
+                    int lo = w * 8, hi = min(lo + 8, chunk_bytes);
+                    for (int bb = hi - 1; bb >= lo; bb--) limb = (limb << 8) | src[bb];
+                    if (bound_bits > 0) {   // bound 2^b <= p: mask, no reduction (nl <= L)
+                        int top = bound_bits - 64 * w;
+                        if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
+#pragma unroll
+                        for (int l = 0; l < L; l++)
+                            if (l == w) v[l] = limb;
+                    } else {
+                        u64 x[L + 1];
+                        x[0] = limb;
+#pragma unroll
+                        for (int l = 0; l < L; l++) x[l + 1] = v[l];
+                        Fp<L, KIND>::reduce_small(v, x, f);
+                    }
+                }
+                Fp<L, KIND>::mac(inner, v, wts + (size_t)j * L);
+            }
+            u64 y[L];
+            Fp<L, KIND>::finish(y, inner, f);
+            Fp<L, KIND>::mac(outer, y, coef + (size_t)S * L);
+        }
+        u64 r[L];
+        Fp<L, KIND>::finish(r, outer, f);
+        store_limbs<L, false>(out + h * L, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u64 splitmix64_dev(u64 x) {
+    u64 z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <int L, int KIND>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_fill_random(FieldParams f, u64* __restrict__ out, size_t n, u64 base) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
+        u64 x[L + 1], r[L];
+#pragma unroll
+        for (int w = 0; w <= L; w++) x[w] = splitmix64_dev(base + h * (L + 1) + w);
+        // keep bits(p)+64 bits so that the value is < 2^64 p (precondition of reduce_small)
+        const u32 keep = f.k + 64;   // <= 64 (L+1)
+        if (keep < 64u * (L + 1)) {
+            const u32 top = keep >> 6, sh = keep & 63;
+#pragma unroll
+            for (int w = 0; w <= L; w++) {
+                if ((u32)w > top) x[w] = 0;
+                else if ((u32)w == top) x[w] = sh ? (x[w] & ((1ull << sh) - 1)) : 0;
+            }
+        }
+        Fp<L, KIND>::reduce_small(r, x, f);
+        store_limbs<L, false>(out + h * L, r);
+    }
+}
+
+static __global__ void __launch_bounds__(MPYC_THREADS)
+k_count_mismatch(const u64* __restrict__ a, const u64* __restrict__ b, size_t n_elems, int L, unsigned long long* count) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_elems; h += nth) {
+        u64 d = 0;
+        for (int l = 0; l < L; l++) d |= a[h * L + l] ^ b[h * L + l];
+        local += d != 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}

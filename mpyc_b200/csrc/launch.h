@@ -1,0 +1,35 @@
+// Host-side launch interface between the C-ABI translation unit (api.cu) and the per-limb-count
+// kernel instantiation units (inst_L{1,2,3,4}.cu), which are compiled in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include "kernels.cuh"
+
+extern std::atomic<unsigned long long> g_mpyc_launches;
+
+// persistent-grid sizing: enough CTAs to cover the items, capped at one full wave
+int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem);
+
+template <int L>
+struct Launch {
+    // op in {OP_ADD, OP_SUB, OP_MUL, OP_NEG}; scal != nullptr -> broadcast second operand (host limbs)
+    static cudaError_t binop(const FieldParams& fp, int op, const u64* a, const u64* b, const u64* scal, u64* out,
+                             size_t n, cudaStream_t st);
+    // mode 0: out = a^e; mode 1: out8 = (a^e != p-1)
+    static cudaError_t pow(const FieldParams& fp, const ExpParams& ex, int mode, const u64* a, u64* out,
+                           unsigned char* out8, int* zero_flag, size_t n, cudaStream_t st);
+    static cudaError_t split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
+                             u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
+                             cudaStream_t st);
+    static cudaError_t recombine(const FieldParams& fp, const RowPtrs& rows, int k, int width, const u64* gtab,
+                                 u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st);
+    static cudaError_t prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+                            int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
+                            cudaStream_t st);
+    static cudaError_t fill_random(const FieldParams& fp, u64* out, size_t n, u64 base, cudaStream_t st);
+};
+
+extern template struct Launch<1>;
+extern template struct Launch<2>;
+extern template struct Launch<3>;
+extern template struct Launch<4>;

@@ -1,0 +1,212 @@
+// Definitions of Launch<L>: picks the kernel instantiation (reduction kind, vector/scalar memory
+// path, compile-time t+1) and launches it on a persistent grid.
+#pragma once
+#include "launch.h"
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_kernel(void (*kernel)(KArgs...), size_t items, size_t smem, cudaStream_t st, Args... args) {
+    if (items == 0) return cudaSuccess;
+    int grid = mpyc_grid_size(reinterpret_cast<const void*>(kernel), items, smem);
+    if (grid <= 0) return cudaErrorLaunchFailure;
+    kernel<<<grid, MPYC_THREADS, smem, st>>>(args...);
+    g_mpyc_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+#define KIND_SWITCH(kind, MACRO)                       \
+    switch (kind) {                                    \
+        case KIND_GENERIC: MACRO(KIND_GENERIC); break; \
+        case KIND_PM_ALIGNED: MACRO(KIND_PM_ALIGNED); break; \
+        case KIND_PM_SHIFT: MACRO(KIND_PM_SHIFT); break; \
+        default: return cudaErrorInvalidValue;         \
+    }
+
+// ---- elementwise ---------------------------------------------------------------------------
+
+template <int L, int KIND, bool VEC>
+static cudaError_t binop_k(const FieldParams& fp, int op, const u64* a, const u64* b, const u64* scal, u64* out,
+                           size_t n, cudaStream_t st) {
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    ScalarParam sp = {};
+    if (scal)
+        for (int i = 0; i < L; i++) sp.v[i] = scal[i];
+    size_t items = (n + E - 1) / E;
+#define BINOP_CASE(OPC, SC) return launch_kernel(k_binop<L, KIND, OPC, SC, VEC>, items, 0, st, fp, a, b, sp, out, n)
+    if (scal) {
+        switch (op) {
+            case OP_ADD: BINOP_CASE(OP_ADD, true);
+            case OP_SUB: BINOP_CASE(OP_SUB, true);
+            case OP_MUL: BINOP_CASE(OP_MUL, true);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    switch (op) {
+        case OP_ADD: BINOP_CASE(OP_ADD, false);
+        case OP_SUB: BINOP_CASE(OP_SUB, false);
+        case OP_MUL: BINOP_CASE(OP_MUL, false);
+        case OP_NEG: BINOP_CASE(OP_NEG, false);
+        default: return cudaErrorInvalidValue;
+    }
+#undef BINOP_CASE
+}
+
+template <int L>
+cudaError_t Launch<L>::binop(const FieldParams& fp, int op, const u64* a, const u64* b, const u64* scal, u64* out,
+                             size_t n, cudaStream_t st) {
+    bool vec = aligned16(a) && aligned16(out) && (scal || op == OP_NEG || aligned16(b));
+    if constexpr (L % 2 == 0) {
+        if (!vec) return cudaErrorMisalignedAddress;
+#define M(K) return binop_k<L, K, true>(fp, op, a, b, scal, out, n, st)
+        KIND_SWITCH(fp.kind, M)
+#undef M
+    } else {
+        if (vec) {
+#define M(K) return binop_k<L, K, true>(fp, op, a, b, scal, out, n, st)
+            KIND_SWITCH(fp.kind, M)
+#undef M
+        } else {
+#define M(K) return binop_k<L, K, false>(fp, op, a, b, scal, out, n, st)
+            KIND_SWITCH(fp.kind, M)
+#undef M
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- pow family ----------------------------------------------------------------------------
+
+template <int L>
+cudaError_t Launch<L>::pow(const FieldParams& fp, const ExpParams& ex, int mode, const u64* a, u64* out,
+                           unsigned char* out8, int* zero_flag, size_t n, cudaStream_t st) {
+#define M(K)                                                                                              \
+    if (mode == 0) return launch_kernel(k_pow<L, K, 0>, n, 0, st, fp, ex, a, out, out8, zero_flag, n);    \
+    return launch_kernel(k_pow<L, K, 1>, n, 0, st, fp, ex, a, out, out8, zero_flag, n)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+// ---- split ----------------------------------------------------------------------------------
+
+template <int L, int KIND, bool FULL, bool VEC>
+static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, u64* shares,
+                           size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    size_t items = (n + E - 1) / E;
+    constexpr int MAXT = FULL ? 5 : 9;
+#define SPLIT_CASE(T)                                                                                            \
+    case T:                                                                                                      \
+        if constexpr (T <= MAXT)                                                                                 \
+            return launch_kernel(k_split<L, KIND, T, FULL, VEC>, items, tab_bytes, st, fp, secrets, coeffs,      \
+                                 cstride, shares, sstride, n, m, gtab, tab_bytes);                               \
+        break
+    switch (t + 1) {
+        SPLIT_CASE(1);
+        SPLIT_CASE(2);
+        SPLIT_CASE(3);
+        SPLIT_CASE(4);
+        SPLIT_CASE(5);
+        SPLIT_CASE(6);
+        SPLIT_CASE(7);
+        SPLIT_CASE(8);
+        SPLIT_CASE(9);
+        default: break;
+    }
+#undef SPLIT_CASE
+    return cudaErrorNotSupported;   // caller falls back to k_split_dyn
+}
+
+template <int L, bool FULL, bool VEC>
+static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, u64* shares,
+                              size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+    if constexpr (FULL) {
+#define M(K) return split_k<L, K, true, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
+        KIND_SWITCH(fp.kind, M)
+#undef M
+    } else {
+        if (fp.kind == KIND_PM_ALIGNED)
+            return split_k<L, KIND_PM_ALIGNED, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab,
+                                                           tab_bytes, st);
+        if (fp.kind == KIND_PM_SHIFT)
+            return split_k<L, KIND_PM_SHIFT, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab,
+                                                         tab_bytes, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
+                             u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
+                             cudaStream_t st) {
+    const bool vec = aligned16(secrets) && aligned16(shares) && (t == 0 || aligned16(coeffs)) &&
+                     ((cstride * L) % 2 == 0) && ((sstride * L) % 2 == 0);
+    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
+    const int maxt = full ? 5 : 9;
+    if (t + 1 > maxt) {
+        if (!full) return cudaErrorInvalidValue;   // api.cu asks for full tables whenever t > 8
+#define M(K) return launch_kernel(k_split_dyn<L, K>, n, 0, st, fp, secrets, coeffs, cstride, shares, sstride, n, m, t + 1, gtab)
+        KIND_SWITCH(fp.kind, M)
+#undef M
+    }
+#define GO(VECF)                                                                                                   \
+    return full ? split_kind<L, true, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st) \
+                : split_kind<L, false, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
+    if constexpr (L % 2 == 0) {
+        GO(true);
+    } else if constexpr (L == 1) {
+        if (vec) {
+            GO(true);
+        }
+        GO(false);
+    } else {   // L == 3: 24-byte elements use the scalar-limb path only (keeps the binary small)
+        GO(false);
+    }
+#undef GO
+}
+
+// ---- recombine ------------------------------------------------------------------------------
+
+template <int L>
+cudaError_t Launch<L>::recombine(const FieldParams& fp, const RowPtrs& rows, int k, int width, const u64* gtab,
+                                 u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st) {
+    bool vec = aligned16(out) && ((ostride * L) % 2 == 0);
+    for (int i = 0; i < k; i++) vec = vec && aligned16(rows.p[i]);
+    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
+    if (L == 3) vec = false;
+    constexpr int EV = VecItem<L>::E;
+    if constexpr (L != 3) {
+        if (vec) {
+#define M(K) return launch_kernel(k_recombine<L, K, true>, (n + EV - 1) / EV, tab_bytes, st, fp, rows, k, width, gtab, tab_bytes, out, ostride, n)
+            KIND_SWITCH(fp.kind, M)
+#undef M
+        }
+    }
+    if constexpr (L % 2 == 1) {
+#define M(K) return launch_kernel(k_recombine<L, K, false>, n, tab_bytes, st, fp, rows, k, width, gtab, tab_bytes, out, ostride, n)
+        KIND_SWITCH(fp.kind, M)
+#undef M
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- PRSS / utilities ---------------------------------------------------------------------------
+
+template <int L>
+cudaError_t Launch<L>::prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+                            int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
+                            cudaStream_t st) {
+#define M(K) return launch_kernel(k_prss_combine<L, K>, n, tab_bytes, st, fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::fill_random(const FieldParams& fp, u64* out, size_t n, u64 base, cudaStream_t st) {
+#define M(K) return launch_kernel(k_fill_random<L, K>, n, 0, st, fp, out, n, base)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}

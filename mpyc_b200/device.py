@@ -1,0 +1,274 @@
+"""Device-resident field arrays: limb tensors that stay in HBM between operations.
+
+torch is used for what it is good at here -- device memory, streams, (later) torch.distributed --
+while every computation goes through the C ABI (mpyc_b200._cabi) on the tensor's data pointer and
+torch's current CUDA stream.  A DeviceArray mirrors the operator surface of the reference's
+PrimeFieldArray / BinaryFieldArray (mpyc/finfields.py:1056-1281,1371-1470) for 1-D arrays.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from mpyc_b200 import _cabi, codec
+from mpyc_b200._cabi import lib, check
+from mpyc_b200.field import FieldContext
+
+
+def _stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
+
+
+def _alloc(ctx, rows, n, device):
+    """Uninitialised limb storage: int64 (rows, n, L) or uint8 (rows, n); row stride padded to 16 bytes."""
+    _require_cuda()
+    if ctx.binary:
+        stride = (n + 15) // 16 * 16
+        return torch.empty((rows, stride), dtype=torch.uint8, device=device)[:, :n]
+    L = ctx.nlimbs
+    stride = n + (n & 1) if L % 2 else n
+    return torch.empty((rows, stride, L), dtype=torch.int64, device=device)[:, :n]
+
+
+class DeviceArray:
+    """n elements of one field in device memory (1-D)."""
+
+    __slots__ = ('ctx', 't')
+
+    def __init__(self, ctx: FieldContext, tensor):
+        self.ctx = ctx
+        self.t = tensor   # int64 (n, L) contiguous, or uint8 (n,)
+
+    # ---- construction / extraction ---------------------------------------------------------------
+    @classmethod
+    def empty(cls, ctx, n, device='cuda'):
+        return cls(ctx, _alloc(ctx, 1, n, device)[0])
+
+    @classmethod
+    def from_limbs(cls, ctx, limbs, device='cuda'):
+        _require_cuda()
+        a = np.ascontiguousarray(limbs)
+        src = torch.from_numpy(a if ctx.binary else a.view(np.int64))
+        out = cls.empty(ctx, a.shape[0], device)
+        out.t.copy_(src)
+        return out
+
+    @classmethod
+    def from_ints(cls, ctx, values, device='cuda', reduce=True):
+        return cls.from_limbs(ctx, codec.ints_to_limbs(values, ctx, reduce=reduce), device)
+
+    @classmethod
+    def random(cls, ctx, n, seed, stream_id=0, device='cuda'):
+        """Deterministic synthetic residues (same recipe as oracle.synth_elements)."""
+        out = cls.empty(ctx, n, device)
+        check(lib.mpyc_b200_fill_random(ctx.handle, out.ptr, n, seed & (2**64 - 1), stream_id, _stream_ptr()))
+        return out
+
+    def to_limbs(self):
+        a = self.t.contiguous().cpu().numpy()
+        return a if self.ctx.binary else a.view(np.uint64)
+
+    def to_ints(self):
+        return codec.limbs_to_ints(self.to_limbs(), self.ctx)
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    @property
+    def n(self):
+        return self.t.shape[0]
+
+    def _like(self):
+        return DeviceArray.empty(self.ctx, self.n, self.t.device)
+
+    def _check_contiguous(self):
+        if not self.t.is_contiguous():
+            self.t = self.t.contiguous()
+
+    # ---- arithmetic (finfields.py:1056-1124,1189-1281) ---------------------------------------------
+    def _binop(self, other, op):
+        self._check_contiguous()
+        out = self._like()
+        if isinstance(other, DeviceArray):
+            if other.ctx is not self.ctx or other.n != self.n:
+                raise ValueError('operands must share field and length')
+            other._check_contiguous()
+            check(lib.mpyc_b200_ff_binop(self.ctx.handle, op, self.ptr, other.ptr, out.ptr, self.n, _stream_ptr()))
+        elif isinstance(other, (int, np.integer)):
+            check(lib.mpyc_b200_ff_binop_scalar(self.ctx.handle, op, self.ptr, self.ctx.scalar_limbs(other), out.ptr,
+                                                self.n, _stream_ptr()))
+        else:
+            return NotImplemented
+        return out
+
+    def __add__(self, other):
+        return self._binop(other, _cabi.OP_ADD)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._binop(other, _cabi.OP_SUB)
+
+    def __rsub__(self, other):
+        return (-self)._binop(other, _cabi.OP_ADD)
+
+    def __mul__(self, other):
+        return self._binop(other, _cabi.OP_MUL)
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        self._check_contiguous()
+        out = self._like()
+        check(lib.mpyc_b200_ff_neg(self.ctx.handle, self.ptr, out.ptr, self.n, _stream_ptr()))
+        return out
+
+    def __pow__(self, e):
+        """a ** e for one public integer exponent (negative allowed: powmod semantics, finfields.py:1408-1414)."""
+        if not isinstance(e, (int, np.integer)):
+            return NotImplemented
+        e = int(e)
+        base = self
+        if e < 0:
+            base, e = self.reciprocal(), -e
+        base._check_contiguous()
+        q1 = self.ctx.order - 1
+        if e > q1:   # a^(q-1) = 1 for a != 0, and 0^e = 0 for e > 0: keep the exponent in 1..q-1
+            e = e % q1 or q1
+        out = base._like()
+        nl = max(1, (e.bit_length() + 63) // 64)
+        check(lib.mpyc_b200_ff_pow(self.ctx.handle, base.ptr, _cabi.u64_array(_cabi.int_to_limbs(e, nl)), nl, out.ptr,
+                                   self.n, _stream_ptr()))
+        return out
+
+    def reciprocal(self):
+        """Elementwise inverse; ZeroDivisionError if any element is 0 (gmpy2.invert, finfields.py:1416-1422)."""
+        self._check_contiguous()
+        out = self._like()
+        check(lib.mpyc_b200_ff_inv(self.ctx.handle, self.ptr, out.ptr, self.n, _stream_ptr()))
+        return out
+
+    def __truediv__(self, other):
+        if isinstance(other, DeviceArray):
+            return self * other.reciprocal()
+        if isinstance(other, (int, np.integer)):
+            return self * pow(int(other), -1, self.ctx.order)
+        return NotImplemented
+
+    def __lshift__(self, k):
+        return self * pow(2, int(k), self.ctx.order)
+
+    def __rshift__(self, k):
+        """'>> k' multiplies by (2^k)^-1 mod p (finfields.py:1250-1259) -- not a bit shift."""
+        return self * pow(pow(2, int(k), self.ctx.order), -1, self.ctx.order)
+
+    def sqrt(self, INV=False):
+        self._check_contiguous()
+        out = self._like()
+        check(lib.mpyc_b200_ff_sqrt(self.ctx.handle, self.ptr, 1 if INV else 0, out.ptr, self.n, _stream_ptr()))
+        return out
+
+    def is_sqr(self):
+        self._check_contiguous()
+        out = torch.empty(self.n, dtype=torch.uint8, device=self.t.device)
+        check(lib.mpyc_b200_ff_is_sqr(self.ctx.handle, self.ptr, ctypes.c_void_p(out.data_ptr()), self.n, _stream_ptr()))
+        return out.bool()
+
+    def signed_(self):
+        """Host-side signed representatives (finfields.py:1395-1398)."""
+        p = self.ctx.modulus
+        v = self.to_ints()
+        return np.where(v > p >> 1, v - p, v)
+
+    def count_mismatch(self, other):
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.t.device)
+        self._check_contiguous()
+        other._check_contiguous()
+        check(lib.mpyc_b200_count_mismatch(self.ctx.handle, self.ptr, other.ptr, self.n,
+                                           ctypes.c_void_p(cnt.data_ptr()), _stream_ptr()))
+        return int(cnt.item())
+
+
+class DeviceMatrix:
+    """rows x n elements (row-major, row stride in elements) -- share or coefficient matrices."""
+
+    __slots__ = ('ctx', 't')
+
+    def __init__(self, ctx, tensor):
+        self.ctx = ctx
+        self.t = tensor   # int64 (rows, n, L) with stride(0) = row stride * L, or uint8 (rows, n)
+
+    @classmethod
+    def empty(cls, ctx, rows, n, device='cuda'):
+        return cls(ctx, _alloc(ctx, rows, n, device))
+
+    @classmethod
+    def from_ints(cls, ctx, rows_of_values, device='cuda'):
+        rows = [codec.ints_to_limbs(r, ctx) for r in rows_of_values]
+        out = cls.empty(ctx, len(rows), rows[0].shape[0] if rows else 0, device)
+        for i, r in enumerate(rows):
+            out.t[i].copy_(torch.from_numpy(r if ctx.binary else r.view(np.int64)))
+        return out
+
+    @property
+    def rows(self):
+        return self.t.shape[0]
+
+    @property
+    def n(self):
+        return self.t.shape[1]
+
+    @property
+    def stride(self):
+        """row stride in elements"""
+        if self.t.shape[0] <= 1:
+            return max(self.n, 1)
+        return self.t.stride(0) // (1 if self.ctx.binary else self.ctx.nlimbs)
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    def row(self, i):
+        return DeviceArray(self.ctx, self.t[i])
+
+    def to_ints(self):
+        return [self.row(i).to_ints() for i in range(self.rows)]
+
+
+def shamir_split(ctx, secrets: DeviceArray, coeffs, t, m, out=None):
+    """Device-resident np_random_split with explicit coefficients (mpyc/thresha.py:47-64).
+
+    coeffs: DeviceMatrix with t rows (row j-1 = coefficient of X^j), or None when t == 0."""
+    n = secrets.n
+    secrets._check_contiguous()
+    if out is None:
+        out = DeviceMatrix.empty(ctx, m, n, secrets.t.device)
+    cptr, cstride = (coeffs.ptr, coeffs.stride) if t > 0 else (ctypes.c_void_p(0), n)
+    check(lib.mpyc_b200_shamir_split(ctx.handle, secrets.ptr, cptr, cstride, out.ptr, out.stride, n, t, m, _stream_ptr()))
+    return out
+
+
+def shamir_recombine(ctx, xs, rows, x_rs=0, out=None):
+    """Device-resident np_recombine (mpyc/thresha.py:119-132). rows: list of DeviceArray (one per x in xs)."""
+    single = not isinstance(x_rs, (list, tuple))
+    pts = [x_rs] if single else list(x_rs)
+    n = rows[0].n
+    for r in rows:
+        r._check_contiguous()
+    if out is None:
+        out = DeviceMatrix.empty(ctx, len(pts), n, rows[0].t.device)
+    check(lib.mpyc_b200_shamir_recombine(ctx.handle, _cabi.ptr_array([r.t.data_ptr() for r in rows]),
+                                         _cabi.i64_array([int(x) for x in xs]), len(rows),
+                                         _cabi.i64_array([int(x) for x in pts]), len(pts), out.ptr, out.stride, n,
+                                         _stream_ptr()))
+    return out.row(0) if single else out

@@ -1,0 +1,324 @@
+"""Drop-in replacements for the reference's secret-sharing module, backed by the sm_100a engine.
+
+Same names, argument meaning, return types and error behaviour as mpyc/thresha.py:
+    random_split :23, np_random_split :47, _recombination_vector :67, recombine :88,
+    np_recombine :119, _f_S_i :135, pseudorandom_share :144, np_pseudorandom_share :163,
+    pseudorandom_share_zero :176, np_pseudorandom_share_0 :201, PRF :220
+so that mpyc/runtime.py (which looks these up as module attributes at call time,
+runtime.py:478-485,565-572,647-656,4057,4099) runs unchanged after mpyc_b200.install().
+
+`field` is an MPyC field class (finfields.GF(...)) or anything with .modulus/.order/.array.
+Data arrive as the reference hands them over -- Python ints in lists or NumPy object arrays -- are
+packed into limb buffers (mpyc_b200.codec), pushed through the C ABI's host-buffer entry points
+(H2D copy, kernel, D2H copy pipelined inside the library) and unpacked again.  The arithmetic runs
+on the GPU only; there is no CPU fallback.
+
+Randomness.  The reference draws coefficients with secrets.randbelow per element
+(thresha.py:37,58-60).  `coefficient_source`, when set to a callable (order, count) -> ints, is
+used instead -- the parity tests inject deterministic streams this way, in the reference's own
+consumption order (np: (t, n) row-major; list: element-major, Horner order).  When None (default)
+the coefficients come from the OS CSPRNG in bulk (os.urandom, 64 bits wider than the modulus) and
+are reduced on the device, or -- for device-resident data -- are generated inside the kernel
+(mpyc_b200_shamir_split_generate).
+"""
+import ctypes
+import os
+from hashlib import shake_128
+from math import prod
+
+import numpy as np
+
+from mpyc_b200 import _cabi, codec
+from mpyc_b200._cabi import lib, check
+from mpyc_b200.field import context_of_field
+
+__all__ = ['random_split', 'recombine', 'pseudorandom_share', 'pseudorandom_share_zero',
+           'np_random_split', 'np_recombine', 'np_pseudorandom_share', 'np_pseudorandom_share_0', 'PRF']
+
+coefficient_source = None     # callable(order, count) -> sequence of ints, or None (CSPRNG)
+device = 0                    # CUDA device ordinal used by the host-buffer entry points
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _values_of(field, s):
+    """Plain values of s: list/array of ints or field elements, or a field array."""
+    arr_t = getattr(field, 'array', None)
+    if arr_t is not None and isinstance(s, arr_t):
+        s = s.value
+    if isinstance(s, np.ndarray):
+        return s.reshape(-1)
+    s = list(s)
+    if s and isinstance(s[0], field):
+        s = [a.value for a in s]
+    return s
+
+
+def _wrap_poly(field, ctx, ints):
+    """GF(2^8): hand values back as the reference's polynomial objects (gfpx.BinaryPolynomial)."""
+    if not ctx.binary:
+        return ints
+    tp = type(field.modulus)
+    out = np.empty(len(ints), dtype=object)
+    out[:] = [tp(int(v)) for v in ints]
+    return out
+
+
+def _draw(ctx, order, count):
+    """count uniform residues as a limb array (count, L) / uint8 (count,)."""
+    if coefficient_source is not None:
+        return codec.ints_to_limbs(list(coefficient_source(order, count)), ctx)
+    if ctx.binary:
+        return np.frombuffer(os.urandom(count), dtype=np.uint8).copy()
+    # 64 extra bits make the bias of the modular reduction < 2^-64
+    nb = (ctx.bits + 64 + 7) // 8
+    raw = os.urandom(count * nb)
+    vals = [int.from_bytes(raw[i:i + nb], 'little') % order for i in range(0, count * nb, nb)]
+    return codec.ints_to_limbs(vals, ctx, reduce=False)
+
+
+def _split_limbs(ctx, sec, C, t, m):
+    """sec: limbs (n, L); C: limbs (t, n, L) -> shares limbs (m, n, L) via the host-buffer ABI."""
+    n = sec.shape[0]
+    shape = (m, n) if ctx.binary else (m, n, ctx.nlimbs)
+    shares = np.empty(shape, dtype=np.uint8 if ctx.binary else np.uint64)
+    sec = np.ascontiguousarray(sec)
+    C = np.ascontiguousarray(C)
+    check(lib.mpyc_b200_shamir_split_host(ctx.handle, _ptr(sec), _ptr(C) if t else None, n, _ptr(shares), n, n, t, m,
+                                          device))
+    return shares
+
+
+def np_random_split(field, s, t, m):
+    """Split each secret in s into m Shamir shares of degree t (0 <= t < m): object ndarray (m, n)."""
+    ctx = context_of_field(field)
+    s = _values_of(field, s)
+    n = len(s)
+    sec = codec.ints_to_limbs(s, ctx)
+    C = _draw(ctx, field.order, t * n)
+    C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
+    shares = _split_limbs(ctx, sec, C, t, m)
+    out = np.empty((m, n), dtype=object)
+    for i in range(m):
+        out[i] = _wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))
+    return out
+
+
+def random_split(field, s, t, m):
+    """List form: m lists of n ints.  A draw stream is consumed element by element, and the Horner
+    evaluation of thresha.py:39-43 makes the FIRST value drawn for a secret the coefficient of X^t."""
+    ctx = context_of_field(field)
+    s = _values_of(field, s)
+    n = len(s)
+    sec = codec.ints_to_limbs(s, ctx)
+    c = _draw(ctx, field.order, t * n)
+    c = c.reshape((n, t) if ctx.binary else (n, t, ctx.nlimbs))
+    # element-major draws, first draw = highest power  ->  row j-1 = coefficient of X^j
+    C = np.ascontiguousarray(np.swapaxes(c, 0, 1)[::-1])
+    shares = _split_limbs(ctx, sec, C, t, m)
+    return [list(_wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))) for i in range(m)]
+
+
+def _recombination_vector(field, xs, x_r):
+    """Lagrange coefficients for x-coordinates xs at x_r (canonical values)."""
+    ctx = context_of_field(field)
+    lam = ctx.recombination_vector(xs, [x_r])[0]
+    return list(_wrap_poly(field, ctx, lam)) if ctx.binary else lam
+
+
+def _recombine_limbs(ctx, xs, rows, pts):
+    n = rows[0].shape[0]
+    width = len(pts)
+    shape = (width, n) if ctx.binary else (width, n, ctx.nlimbs)
+    out = np.empty(shape, dtype=np.uint8 if ctx.binary else np.uint64)
+    rows = [np.ascontiguousarray(r) for r in rows]
+    check(lib.mpyc_b200_shamir_recombine_host(ctx.handle, _cabi.ptr_array([r.ctypes.data for r in rows]),
+                                              _cabi.i64_array([int(x) for x in xs]), len(rows),
+                                              _cabi.i64_array([int(x) for x in pts]), width, _ptr(out), n, n, device))
+    return out
+
+
+def np_recombine(field, points, x_rs=0):
+    """Recombine shares given by points [(x_i, share_i), ...] at x_rs: field.array (n,) or (width, n)."""
+    ctx = context_of_field(field)
+    xs, shares = zip(*points)
+    single = not isinstance(x_rs, list)
+    pts = [x_rs] if single else x_rs
+    rows = [codec.ints_to_limbs(_values_of(field, sh), ctx) for sh in shares]
+    out = _recombine_limbs(ctx, xs, rows, pts)
+    n = rows[0].shape[0]
+    vals = np.empty((len(pts), n), dtype=object)
+    for r in range(len(pts)):
+        vals[r] = _wrap_poly(field, ctx, codec.limbs_to_ints(out[r], ctx))
+    return field.array(vals[0] if single else vals, check=False)
+
+
+def recombine(field, points, x_rs=0):
+    """List form.  Returns reduced values (the reference leaves plain-int sums unreduced,
+    thresha.py:109, and every caller reduces them: runtime.py:588,682); field elements in,
+    field elements out (thresha.py:110-113)."""
+    ctx = context_of_field(field)
+    xs, shares = zip(*points)
+    single = not isinstance(x_rs, list)
+    pts = [x_rs] if single else x_rs
+    is_elt = len(shares[0]) > 0 and isinstance(shares[0][0], field)
+    rows = [codec.ints_to_limbs(_values_of(field, sh), ctx) for sh in shares]
+    out = _recombine_limbs(ctx, xs, rows, pts)
+    sums = []
+    for r in range(len(pts)):
+        vals = list(_wrap_poly(field, ctx, codec.limbs_to_ints(out[r], ctx)))
+        sums.append([field(v) for v in vals] if is_elt else vals)
+    return sums[0] if single else sums
+
+
+# ---------------------------------------------------------------------------------------------
+# PRF and pseudorandom secret sharing
+# ---------------------------------------------------------------------------------------------
+
+class PRF:
+    """Pseudorandom function: SHAKE128(key + input) cut into fixed-width little-endian chunks,
+    each reduced modulo `bound` (same construction and attributes as mpyc/thresha.py:220-266)."""
+
+    def __init__(self, key, bound):
+        self.key = key
+        self.max = bound
+        width = ((bound - 1).bit_length() + 7) // 8
+        if bound & (bound - 1):
+            width += len(key)   # extra key-length bytes make the reduction bias negligible
+        self.byte_length = width
+
+    def stream(self, s, count):
+        """Raw XOF output for `count` values."""
+        return shake_128(self.key + s).digest(count * self.byte_length) if self.byte_length and count else b''
+
+    def __call__(self, s, n=None):
+        shape = n if isinstance(n, tuple) else None
+        count = 1 if n is None else (prod(shape) if shape is not None else n)
+        w = self.byte_length
+        if count == 0:
+            vals = []
+        elif w == 0:
+            vals = [0] * count
+        else:
+            raw, bound = self.stream(s, count), self.max
+            vals = [int.from_bytes(raw[k:k + w], 'little') % bound for k in range(0, count * w, w)]
+        if shape is not None:
+            arr = np.empty(count, dtype=object)
+            arr[:] = vals
+            return arr.reshape(shape)
+        return vals[0] if n is None else vals
+
+
+def _f_S_i(field, m, i, S):
+    """f_S(i+1) for the degree-t polynomial with f_S(0) = 1 and f_S(j+1) = 0 for j outside S."""
+    ctx = context_of_field(field)
+    xs = [0] + [x + 1 for x in range(m) if x not in S]
+    lam = ctx.recombination_vector(xs, [i + 1])[0]
+    return _wrap_poly(field, ctx, lam[:1])[0] if ctx.binary else lam[0]
+
+
+def _prss(field, m, i, prfs, uci, n, d, weights):
+    """Shared engine call: sum_S f_S(i) * sum_j PRF_S[h*d + j] * weights[j]  as a limb array (n, L)."""
+    import torch
+    ctx = context_of_field(field)
+    subsets = list(prfs.items())
+    bound = subsets[0][1].max
+    width = subsets[0][1].byte_length
+    if any(f.max != bound for _, f in subsets):
+        raise ValueError('all PRFs of one call must share their bound')
+    if bound == field.order:
+        bound_bits = 0
+    elif bound & (bound - 1) == 0 and bound <= field.order:
+        bound_bits = bound.bit_length() - 1
+    else:
+        raise _cabi.UnsupportedFieldError('PRF bound must be the field order or a power of two below it')
+    nl = max(ctx.nlimbs, 1)
+    if n == 0:
+        return np.zeros((0,) if ctx.binary else (0, nl), dtype=np.uint8 if ctx.binary else np.uint64)
+    if width == 0:   # bound == 1: all PRF values are 0
+        return np.zeros((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
+    if not torch.cuda.is_available():
+        raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
+    stride = (n * d * width + 15) // 16 * 16
+    buf = bytearray(stride * len(subsets))
+    coef = []
+    for k, (S, f) in enumerate(subsets):
+        raw = shake_128(f.key + uci).digest(n * d * width)
+        buf[k * stride:k * stride + len(raw)] = raw
+        c = _f_S_i(field, m, i, S)
+        coef.extend(_cabi.int_to_limbs(int(c), nl))
+    wl = []
+    for w in weights:
+        wl.extend(_cabi.int_to_limbs(int(w), nl))
+    dev = torch.device('cuda', device)
+    d_bytes = torch.frombuffer(buf, dtype=torch.uint8).to(dev)
+    out = torch.empty((n,) if ctx.binary else (n, nl), dtype=torch.uint8 if ctx.binary else torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib.mpyc_b200_prss_combine(ctx.handle, ctypes.c_void_p(d_bytes.data_ptr()), stride, len(subsets), d, width,
+                                         bound_bits if not ctx.binary else 0, _cabi.u64_array(coef), _cabi.u64_array(wl),
+                                         ctypes.c_void_p(out.data_ptr()), n, st))
+        res = out.cpu().numpy()
+    return res if ctx.binary else res.view(np.uint64)
+
+
+def np_pseudorandom_share(field, m, i, prfs, uci, n):
+    """Pseudorandom Shamir shares of n random values for party i: field.array (n,)."""
+    ctx = context_of_field(field)
+    limbs = _prss(field, m, i, prfs, uci, n, 1, [1])
+    return field.array(_wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx)), check=False)
+
+
+def pseudorandom_share(field, m, i, prfs, uci, n):
+    """List form: n field elements."""
+    ctx = context_of_field(field)
+    limbs = _prss(field, m, i, prfs, uci, n, 1, [1])
+    return [field(v) for v in _wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx))]
+
+
+def _powers(field, ctx, i, d, horner):
+    """Weights for the d PRF values of one zero-share: np order (i+1)^(j+1), list (Horner) order (i+1)^(d-j)."""
+    if ctx.binary:
+        poly = ctx.modulus
+
+        def mul(a, b):
+            r = 0
+            for _ in range(8):
+                if b & 1:
+                    r ^= a
+                b >>= 1
+                a <<= 1
+                if a & 0x100:
+                    a ^= poly
+            return r
+        pw, cur = [], 1
+        for _ in range(d):
+            cur = mul(cur, i + 1)
+            pw.append(cur)
+    else:
+        pw = [pow(i + 1, j, ctx.modulus) for j in range(1, d + 1)]
+    return pw[::-1] if horner else pw
+
+
+def np_pseudorandom_share_0(field, m, i, prfs, uci, n):
+    """Pseudorandom degree-2t... sharings of 0 (NumPy order: PRF value (h, j) multiplies (i+1)^(j+1))."""
+    ctx = context_of_field(field)
+    d = m - len(next(iter(prfs.keys())))
+    limbs = _prss(field, m, i, prfs, uci, n, d, _powers(field, ctx, i, d, horner=False)) if d else None
+    if limbs is None:
+        return field.array(np.zeros(n, dtype=object), check=False)
+    return field.array(_wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx)), check=False)
+
+
+def pseudorandom_share_zero(field, m, i, prfs, uci, n):
+    """List form (Horner order: PRF value h*d+j multiplies (i+1)^(d-j), thresha.py:191-195)."""
+    ctx = context_of_field(field)
+    subsets = list(prfs.keys())
+    d = m - len(subsets[0]) if subsets else 0
+    if d == 0 or n == 0:
+        zero = 0 if not ctx.binary else type(field.modulus)(0)
+        return [field(zero) for _ in range(n)]
+    limbs = _prss(field, m, i, prfs, uci, n, d, _powers(field, ctx, i, d, horner=True))
+    return [field(v) for v in _wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx))]

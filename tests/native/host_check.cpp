@@ -1,0 +1,151 @@
+// Host-only checker for the algorithms in mpyc_b200/csrc/ff_arith.cuh (compiled with g++; the
+// __int128 host path of the n-limb primitives, everything above them shared with the kernels).
+// Reads commands from stdin, one per line, all integers in hex without 0x:
+//   field <p>                         -> prints "kind L k"
+//   mul|add|sub <a> <b> ; neg <a>
+//   lazy <K> a1 b1 ... aK bK          -> sum a_i*b_i mod p via mac (b in table form) + finish
+//   small <K> <s> a1 v1 ... aK vK     -> (s + sum a_i*v_i) mod p via mac_1 + pm_reduce<L+1> (PM fields)
+//   redsmall <x>                      -> x mod p for x < 2^(k+64) via reduce_small
+//   pow <a> <e>
+// TEST INFRASTRUCTURE: not part of the shipped library.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <sstream>
+#include "../../mpyc_b200/csrc/field_setup.h"
+
+static void parse_hex(const std::string& s, u64* out, int n) {
+    for (int i = 0; i < n; i++) out[i] = 0;
+    int pos = 0;
+    for (int i = (int)s.size() - 1; i >= 0; i--, pos++) {
+        char c = s[i];
+        u64 v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        if (pos / 16 < n) out[pos / 16] |= v << (4 * (pos % 16));
+    }
+}
+static std::string to_hex(const u64* x, int n) {
+    char buf[32];
+    std::string s;
+    bool started = false;
+    for (int i = n - 1; i >= 0; i--) {
+        if (!started) {
+            if (x[i] == 0 && i > 0) continue;
+            snprintf(buf, sizeof buf, "%llx", x[i]);
+            started = true;
+        } else snprintf(buf, sizeof buf, "%016llx", x[i]);
+        s += buf;
+    }
+    return s;
+}
+
+static FieldParams fp;
+
+template <int L, int K>
+static std::string run(const std::string& cmd, std::istringstream& in) {
+    typedef Fp<L, K> F;
+    std::string t;
+    u64 a[L], b[L], r[L];
+    if (cmd == "mul" || cmd == "add" || cmd == "sub") {
+        in >> t; parse_hex(t, a, L);
+        in >> t; parse_hex(t, b, L);
+        if (cmd == "mul") F::mul(r, a, b, fp);
+        else if (cmd == "add") F::add(r, a, b, fp);
+        else F::sub(r, a, b, fp);
+        return to_hex(r, L);
+    }
+    if (cmd == "neg") {
+        in >> t; parse_hex(t, a, L);
+        F::neg(r, a, fp);
+        return to_hex(r, L);
+    }
+    if (cmd == "lazy") {
+        int cnt; in >> cnt;
+        u64 acc[2 * L + 1];
+        zero_n<2 * L + 1>(acc);
+        for (int i = 0; i < cnt; i++) {
+            in >> t; parse_hex(t, a, L);
+            in >> t; parse_hex(t, b, L);
+            u64 tb[L];
+            F::to_dom(tb, b, fp);
+            F::mac(acc, a, tb);
+        }
+        F::finish(r, acc, fp);
+        return to_hex(r, L);
+    }
+    if (cmd == "small") {
+        if (K == KIND_GENERIC) return "n/a";
+        int cnt; in >> cnt;
+        u64 acc[L + 1];
+        in >> t; parse_hex(t, acc, L);
+        acc[L] = 0;
+        for (int i = 0; i < cnt; i++) {
+            u64 v;
+            in >> t; parse_hex(t, a, L);
+            in >> t; parse_hex(t, &v, 1);
+            mac_1<L, L + 1>(acc, a, v);
+        }
+        if constexpr (K != KIND_GENERIC) F::template pm_reduce<L + 1>(r, acc, fp);
+        return to_hex(r, L);
+    }
+    if (cmd == "redsmall") {
+        u64 x[L + 1];
+        in >> t; parse_hex(t, x, L + 1);
+        F::reduce_small(r, x, fp);
+        return to_hex(r, L);
+    }
+    if (cmd == "pow") {
+        u64 e[8];
+        in >> t; parse_hex(t, a, L);
+        in >> t; parse_hex(t, e, 8);
+        u64 x[L];
+        F::to_dom(x, a, fp);
+        F::dpow_uniform(x, x, e, bit_length(e, 8), fp);
+        F::from_dom(r, x, fp);
+        std::string r1 = to_hex(r, L);
+        F::to_dom(x, a, fp);
+        F::dpow(x, x, e, bit_length(e, 8), fp);
+        F::from_dom(r, x, fp);
+        return r1 == to_hex(r, L) ? r1 : std::string("MISMATCH");
+    }
+    return "?";
+}
+
+template <int L>
+static std::string run_kind(const std::string& cmd, std::istringstream& in) {
+    switch (fp.kind) {
+        case KIND_GENERIC: return run<L, KIND_GENERIC>(cmd, in);
+        case KIND_PM_ALIGNED: return run<L, KIND_PM_ALIGNED>(cmd, in);
+        default: return run<L, KIND_PM_SHIFT>(cmd, in);
+    }
+}
+
+int main() {
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        std::istringstream in(line);
+        std::string cmd, t;
+        in >> cmd;
+        if (cmd.empty()) continue;
+        if (cmd == "field") {
+            u64 p[4];
+            in >> t; parse_hex(t, p, 4);
+            int n = 4;
+            while (n > 1 && p[n - 1] == 0) n--;
+            field_params_init((const uint64_t*)p, n, &fp);
+            printf("%u %u %u\n", fp.kind, fp.L, fp.k);
+            continue;
+        }
+        std::string out;
+        switch (fp.L) {
+            case 1: out = run_kind<1>(cmd, in); break;
+            case 2: out = run_kind<2>(cmd, in); break;
+            case 3: out = run_kind<3>(cmd, in); break;
+            default: out = run_kind<4>(cmd, in); break;
+        }
+        printf("%s\n", out.c_str());
+    }
+    return 0;
+}

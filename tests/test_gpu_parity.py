@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures
+generated from the real reference.  Bit-exact everywhere (integer work).  Run on the B200 box:
+    python -m pytest tests -m gpu -x -q
+"""
+import itertools
+import random
+
+import numpy as np
+import pytest
+
+from golden_util import load, unhex
+from oracle import shamir_oracle as orc
+import fakefield
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+if not torch.cuda.is_available():
+    pytest.skip('no CUDA device', allow_module_level=True)
+
+import mpyc_b200                                   # noqa: E402
+from mpyc_b200 import thresha, device as dev, codec   # noqa: E402
+from mpyc_b200.device import DeviceArray, DeviceMatrix   # noqa: E402
+
+SPLIT = load('split_recombine.json')
+PRSS = load('prss.json')
+FF = load('finfields.json')
+G256 = load('gf256.json')
+
+P61, P64, P69, P127, P128, P256 = 2**61 - 1, 2**64 - 189, 2**69 - 93, 2**127 - 1, 2**128 - 173, 2**256 - 189
+P64G = 9409569905028393239
+GEN = {k: int(v, 16) for k, v in SPLIT['meta']['generic_primes'].items()}
+
+
+class inject:
+    """thresha.coefficient_source <- fixed stream (the role of patching secrets.randbelow in the reference)."""
+
+    def __init__(self, stream):
+        self.stream = list(stream)
+
+    def __enter__(self):
+        it = iter(self.stream)
+        thresha.coefficient_source = lambda order, count: list(itertools.islice(it, count))
+
+    def __exit__(self, *exc):
+        thresha.coefficient_source = None
+
+
+# ---- golden fixtures from the reference ------------------------------------------------------------
+
+@pytest.mark.parametrize('case', SPLIT['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_{c['p'][-4:]}_m{c['m']}t{c['t']}")
+def test_golden_split_recombine_dropin(case):
+    p, m, t = int(case['p'], 16), case['m'], case['t']
+    F = fakefield.make_prime_field(p)
+    s, stream = unhex(case['secrets']), unhex(case['stream'])
+    with inject(stream):
+        sh_np = thresha.np_random_split(F, F.array(np.array(s, dtype=object)), t, m)
+    assert sh_np.dtype == object and sh_np.shape == (m, len(s))
+    assert sh_np.tolist() == unhex(case['shares_np'])
+    with inject(stream):
+        sh_li = thresha.random_split(F, list(s), t, m)
+    assert sh_li == unhex(case['shares_list'])
+    with inject(stream):
+        sh_el = thresha.random_split(F, [F(x) for x in s], t, m)   # field elements in
+    assert sh_el == unhex(case['shares_list'])
+    for rec in case['recombine']:
+        xs = rec['xs']
+        pts = [(x, sh_np[x - 1]) for x in xs]
+        assert thresha._recombination_vector(F, tuple(xs), 0) == unhex(rec['lambda0'])
+        y0 = thresha.np_recombine(F, pts)
+        assert isinstance(y0, F.array) and y0.value.tolist() == unhex(rec['y0'])
+        yw = thresha.np_recombine(F, pts, rec['x_rs'])
+        assert yw.value.tolist() == unhex(rec['yw'])
+        yl = thresha.recombine(F, [(x, sh_li[x - 1]) for x in xs])
+        ylr = thresha.recombine(F, [(x, unhex(case['shares_np'])[x - 1]) for x in xs])
+        assert ylr == unhex(rec['y0'])
+        if len(xs) >= t + 1:
+            assert yl == s and y0.value.tolist() == s
+        ye = thresha.recombine(F, [(x, [F(v) for v in sh_li[x - 1]]) for x in xs], [0])
+        assert all(isinstance(v, F) for v in ye[0])
+
+
+@pytest.mark.parametrize('case', FF['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_{c['p'][-4:]}")
+def test_golden_finfields_device(case):
+    p = int(case['p'], 16)
+    ctx = mpyc_b200.context_for(p)
+    a, b, nz = unhex(case['a']), unhex(case['b']), unhex(case['nz'])
+    A, B, NZ = (DeviceArray.from_ints(ctx, v) for v in (a, b, nz))
+    g = lambda x: x.to_ints().tolist()
+    assert g(A + B) == unhex(case['add'])
+    assert g(A - B) == unhex(case['sub'])
+    assert g(A * B) == unhex(case['mul'])
+    assert g(-A) == unhex(case['neg'])
+    assert g(NZ.reciprocal()) == unhex(case['inv_nz'])
+    assert g(A / NZ) == unhex(case['div'])
+    assert g(A << 7) == unhex(case['lshift7'])
+    assert g(A >> 7) == unhex(case['rshift7'])
+    assert g(A ** 5) == unhex(case['pow5'])
+    assert g(NZ ** -3) == unhex(case['powm3_nz'])
+    assert g(A ** ((p - 1) // 2 + 3)) == unhex(case['pow_big'])
+    assert A.is_sqr().cpu().tolist() == case['is_sqr']
+    assert [int(x) for x in A.signed_()] == [int(x) for x in case['signed']]
+    assert g(A * 12345678901234567890123) == unhex(case['mul_scalar'])
+    assert g(A + (p - 5)) == unhex(case['add_scalar'])
+    assert g(5 - A) == orc.ff_sub(p, [5] * len(a), a)
+    if 'sqrt_a' in case:
+        assert g(A.sqrt()) == unhex(case['sqrt_a'])
+        assert g((A * A).sqrt()) == unhex(case['sqrt_of_sq'])
+        assert g((NZ * NZ).sqrt(INV=True)) == unhex(case['invsqrt_of_nzsq'])
+        with pytest.raises(ZeroDivisionError):
+            A.sqrt(INV=True)
+    with pytest.raises(ZeroDivisionError):
+        A.reciprocal()          # a contains 0
+
+
+@pytest.mark.parametrize('case', PRSS['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_m{c['m']}t{c['t']}")
+def test_golden_prss_dropin(case):
+    p, m, t, n = int(case['p'], 16), case['m'], case['t'], case['n']
+    F = fakefield.make_prime_field(p)
+    uci = bytes.fromhex(case['uci'])
+    keys = {tuple(int(x) for x in k.split(',')): bytes.fromhex(v) for k, v in case['keys'].items()}
+    for party in case['parties']:
+        i = party['i']
+        prfs = {S: thresha.PRF(k, p) for S, k in keys.items() if i in S}
+        for S in prfs:
+            assert thresha._f_S_i(F, m, i, S) == int(party['f_S_i'][','.join(map(str, S))], 16) % p
+        a_np = thresha.np_pseudorandom_share(F, m, i, prfs, uci, n)
+        assert isinstance(a_np, F.array) and a_np.value.tolist() == unhex(party['share_np'])
+        a_li = thresha.pseudorandom_share(F, m, i, prfs, uci, n)
+        assert [x.value for x in a_li] == unhex(party['share_list'])
+        z_li = thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)
+        assert [x.value for x in z_li] == unhex(party['zero_list'])
+        if t:
+            z_np = thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n)
+            assert z_np.value.tolist() == unhex(party['zero_np'])
+
+
+def test_prss_power_of_two_bound_and_prf():
+    """bounded PRSS (runtime.py:4076: bound = power of two) and the PRF class itself."""
+    key = bytes.fromhex(load('prf.json')['key'])
+    for c in load('prf.json')['cases']:
+        F = thresha.PRF(key, int(c['bound'], 16))
+        assert F.byte_length == c['l']
+        assert F(bytes.fromhex(c['s']), c['n']) == unhex(c['values'])
+    p = P69
+    Fld = fakefield.make_prime_field(p)
+    m, t, n = 5, 2, 33
+    Fo = orc.field_of(p)
+    from itertools import combinations
+    for bound in (1, 2, 1 << 13, 1 << 40, 1 << 64):
+        for i in range(m):
+            prfs = {S: thresha.PRF(bytes([sum(S) + 7] * 16), bound) for S in combinations(range(m), m - t) if i in S}
+            got = thresha.np_pseudorandom_share(Fld, m, i, prfs, b'uci-0001', n).value.tolist()
+            prl = {S: orc.prf_values(f.key, bound, b'uci-0001', n) for S, f in prfs.items()}
+            assert got == orc.prss_share(Fo, m, i, prl, n)
+
+
+def test_golden_gf256():
+    f = G256['modulus']
+    ctx = mpyc_b200.context_for(f, binary=True)
+    tab = np.frombuffer(bytes.fromhex(G256['mul_table_hex']), dtype=np.uint8).reshape(256, 256)
+    a = np.repeat(np.arange(256, dtype=np.uint8), 256)
+    b = np.tile(np.arange(256, dtype=np.uint8), 256)
+    A, B = DeviceArray.from_limbs(ctx, a), DeviceArray.from_limbs(ctx, b)
+    assert np.array_equal((A * B).to_limbs(), tab.reshape(-1))
+    assert np.array_equal((A + B).to_limbs(), a ^ b)
+    assert np.array_equal((A - B).to_limbs(), a ^ b)
+    # odd offsets / lengths exercise the byte tail and the unaligned path
+    A3, B3 = DeviceArray.from_limbs(ctx, a[:1003]), DeviceArray.from_limbs(ctx, b[:1003])
+    assert np.array_equal((A3 * B3).to_limbs(), tab.reshape(-1)[:1003])
+    assert np.array_equal((A3 * 0x53).to_limbs(), tab[a[:1003], 0x53])
+    nzv = np.arange(1, 256, dtype=np.uint8)
+    assert DeviceArray.from_limbs(ctx, nzv).reciprocal().to_limbs().tolist() == G256['inv'][1:]
+    with pytest.raises(ZeroDivisionError):
+        DeviceArray.from_limbs(ctx, np.arange(0, 9, dtype=np.uint8)).reciprocal()
+    F = fakefield.make_gf256(f)
+    for case in G256['split']:
+        m, t = case['m'], case['t']
+        s, stream = unhex(case['secrets']), unhex(case['stream'])
+        with inject(stream):
+            sh = thresha.np_random_split(F, np.array([fakefield.Poly(x) for x in s], dtype=object), t, m)
+        assert [[int(v) for v in row] for row in sh] == unhex(case['shares_np'])
+        with inject(stream):
+            sl = thresha.random_split(F, [F(x) for x in s], t, m)
+        assert [[int(v) for v in row] for row in sl] == unhex(case['shares_list'])
+        xs = case['xs']
+        assert [int(v) for v in thresha._recombination_vector(F, tuple(xs), 0)] == unhex(case['lambda0'])
+        y = thresha.np_recombine(F, [(x, sh[x - 1]) for x in xs])
+        assert [int(v) for v in y.value] == unhex(case['y0'])
+
+
+# ---- seeded random parity against the oracle ----------------------------------------------------------
+
+PARITY_PRIMES = [P61, P64, P64G, P69, GEN['96'], P127, P128, GEN['128'], GEN['192'], 2**192 - 237, GEN['250'], P256, GEN['256'], 101, 65537]
+
+
+@pytest.mark.parametrize('p', PARITY_PRIMES, ids=lambda p: f'p{p.bit_length()}_{p & 0xffff:x}')
+@pytest.mark.parametrize('n', [0, 1, 2, 3, 7, 64, 1001, 4096 + 5])
+def test_split_recombine_vs_oracle(p, n):
+    ctx = mpyc_b200.context_for(p)
+    F = orc.field_of(p)
+    rnd = random.Random(n * 7919 + p % 10007)
+    for (m, t) in ((1, 0), (3, 1), (5, 2), (7, 3), (4, 3), (13, 5), (17, 8), (12, 9), (24, 11)):
+        if n > 100 and (m, t) in ((12, 9), (24, 11), (13, 5)):
+            continue
+        s = (orc.edge_block(p) + orc.synth_elements(p, max(n - 8, 0), 11 * m + t))[:n]
+        C = [orc.synth_elements(p, n, 1000 + 31 * j + m, stream=5) for j in range(t)]
+        want = orc.split_np_order(F, s, C, m)
+        S = DeviceArray.from_ints(ctx, s)
+        CM = DeviceMatrix.from_ints(ctx, C) if t else None
+        sh = dev.shamir_split(ctx, S, CM, t, m)
+        assert [r.tolist() for r in sh.to_ints()] == want
+        if n == 0:
+            continue
+        k = rnd.choice([t + 1, min(m, 2 * t + 1), m])
+        xs = sorted(rnd.sample(range(1, m + 1), k))
+        rows = [sh.row(x - 1) for x in xs]
+        got = dev.shamir_recombine(ctx, xs, rows)
+        assert got.to_ints().tolist() == orc.recombine(F, xs, [want[x - 1] for x in xs]) == s
+        x_rs = [0, m + 1, xs[0]]
+        gw = dev.shamir_recombine(ctx, xs, rows, x_rs)
+        assert [r.tolist() for r in gw.to_ints()] == orc.recombine(F, xs, [want[x - 1] for x in xs], x_rs)
+
+
+@pytest.mark.parametrize('p', PARITY_PRIMES, ids=lambda p: f'p{p.bit_length()}_{p & 0xffff:x}')
+def test_elementwise_vs_oracle(p):
+    ctx = mpyc_b200.context_for(p)
+    for n in (1, 2, 5, 255, 256, 257, 10007):
+        a = (orc.edge_block(p) + orc.synth_elements(p, n, 5))[:n]
+        b = (list(reversed(orc.edge_block(p))) + orc.synth_elements(p, n, 6))[:n]
+        A, B = DeviceArray.from_ints(ctx, a), DeviceArray.from_ints(ctx, b)
+        assert (A * B).to_ints().tolist() == orc.ff_mul(p, a, b)
+        assert (A + B).to_ints().tolist() == orc.ff_add(p, a, b)
+        assert (A - B).to_ints().tolist() == orc.ff_sub(p, a, b)
+        assert (-A).to_ints().tolist() == orc.ff_neg(p, a)
+        assert (A * (p - 1)).to_ints().tolist() == orc.ff_mul(p, a, [p - 1] * n)
+
+
+def test_device_fill_random_matches_oracle_recipe():
+    for p in PARITY_PRIMES:
+        ctx = mpyc_b200.context_for(p)
+        got = DeviceArray.random(ctx, 300, seed=20260923, stream_id=3).to_ints().tolist()
+        assert got == orc.synth_elements(p, 300, 20260923, stream=3)
+
+
+def test_host_buffer_abi_large_chunked():
+    """The host-buffer entry points (what the drop-in uses) across several pipeline chunks."""
+    p = P128
+    ctx = mpyc_b200.context_for(p)
+    F = fakefield.make_prime_field(p)
+    n, m, t = 3_000_001, 5, 2       # > one 32 MiB chunk, odd
+    rng = np.random.default_rng(1)
+    sec = rng.integers(0, 2**63, size=(n, 2), dtype=np.uint64)
+    sec[:, 1] >>= 1
+    C = rng.integers(0, 2**63, size=(t, n, 2), dtype=np.uint64)
+    shares = thresha._split_limbs(ctx, sec, C, t, m)
+    out = thresha._recombine_limbs(ctx, [2, 4, 5], [shares[1], shares[3], shares[4]], [0])
+    assert np.array_equal(out[0], sec)
+    idx = [0, 1, n // 2, n - 1]
+    s_int = codec.limbs_to_ints(sec[idx], ctx).tolist()
+    C_int = [codec.limbs_to_ints(C[j][idx], ctx).tolist() for j in range(t)]
+    want = orc.split_np_order(orc.field_of(p), s_int, C_int, m)
+    assert [codec.limbs_to_ints(shares[i][idx], ctx).tolist() for i in range(m)] == want
+
+
+# ---- size-independent properties at full benchmark sizes ---------------------------------------------
+
+@pytest.mark.parametrize('p,m,t,n', [(P64, 3, 1, 20_000_000), (P128, 5, 2, 10_000_000), (P256, 7, 3, 2_000_000),
+                                      (P64G, 3, 1, 10_000_000), (GEN['128'], 5, 2, 4_000_000), (P61, 3, 1, 10_000_001)])
+def test_full_size_roundtrip_and_linearity(p, m, t, n):
+    ctx = mpyc_b200.context_for(p)
+    S = DeviceArray.random(ctx, n, seed=1, stream_id=1)
+    S2 = DeviceArray.random(ctx, n, seed=2, stream_id=2)
+    C = DeviceMatrix.empty(ctx, t, n)
+    C2 = DeviceMatrix.empty(ctx, t, n)
+    for j in range(t):
+        C.t[j].copy_(DeviceArray.random(ctx, n, seed=10 + j, stream_id=3).t)
+        C2.t[j].copy_(DeviceArray.random(ctx, n, seed=20 + j, stream_id=4).t)
+    sh = dev.shamir_split(ctx, S, C, t, m)
+    sh2 = dev.shamir_split(ctx, S2, C2, t, m)
+    # encode -> erase -> decode: any t+1 shares return the secrets
+    for xs in ([1 + i for i in range(t + 1)], [m - i for i in range(t + 1)]):
+        rec = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs])
+        assert rec.count_mismatch(S) == 0
+    # all m shares (degree t < m) as well
+    rec = dev.shamir_recombine(ctx, list(range(1, m + 1)), [sh.row(i) for i in range(m)])
+    assert rec.count_mismatch(S) == 0
+    # linearity: shares of (S + S2) with coefficients (C + C2) are the sums of the shares
+    Ssum = S + S2
+    Csum = DeviceMatrix.empty(ctx, t, n)
+    for j in range(t):
+        Csum.t[j].copy_((C.row(j) + C2.row(j)).t)
+    shsum = dev.shamir_split(ctx, Ssum, Csum, t, m)
+    for i in range(m):
+        assert shsum.row(i).count_mismatch(sh.row(i) + sh2.row(i)) == 0
+    # recombining at a party's own point returns that party's share
+    xs = list(range(1, t + 2))
+    own = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs], [m])
+    assert own.row(0).count_mismatch(sh.row(m - 1)) == 0
+    # spot-check against the oracle at a few positions
+    idx = [0, 1, n // 3, n - 2, n - 1]
+    lim = S.to_limbs()[idx]
+    s_int = codec.limbs_to_ints(lim, ctx).tolist()
+    C_int = [codec.limbs_to_ints(C.row(j).to_limbs()[idx], ctx).tolist() for j in range(t)]
+    want = orc.split_np_order(orc.field_of(p), s_int, C_int, m)
+    got = [codec.limbs_to_ints(sh.row(i).to_limbs()[idx], ctx).tolist() for i in range(m)]
+    assert got == want
+
+
+def test_error_behaviour():
+    ctx = mpyc_b200.context_for(P61)
+    S = DeviceArray.from_ints(ctx, [1, 2, 3])
+    with pytest.raises(ValueError):
+        dev.shamir_split(ctx, S, None, 3, 3)        # t >= m
+    with pytest.raises(ZeroDivisionError):
+        dev.shamir_recombine(ctx, [1, 1], [S, S])   # repeated x-coordinate
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):
+        mpyc_b200.context_for(2**300 + 157)
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):
+        mpyc_b200.context_for(2)
+    assert mpyc_b200.launch_count() > 0
