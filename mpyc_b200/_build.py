@@ -32,8 +32,17 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile (if sources changed) and return the path of the shared library."""
+def build(force=False, verbose=False, defines=(), lib=None):
+    """Compile (if sources changed) and return the path of the shared library.
+    defines/lib: build a tuning variant (-D flags) under another file name (kernel experiments)."""
+    global OBJ, LIB
+    if lib is not None:
+        saved = (OBJ, LIB)
+        OBJ, LIB = os.path.join(CSRC, '_obj_' + os.path.basename(lib)), os.path.join(HERE, lib)
+        try:
+            return build(force=True, verbose=verbose, defines=defines)
+        finally:
+            OBJ, LIB = saved
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, 'digest.txt')
     digest = _digest()
@@ -43,7 +52,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout[-4000:], r.stderr[-8000:]))
@@ -67,4 +76,6 @@ def build(force=False, verbose=False):
 
 if __name__ == '__main__':
     import sys
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    out = [a[2:] for a in sys.argv[1:] if a.startswith('-o')]
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, lib=out[0] if out else None))

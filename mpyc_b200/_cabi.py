@@ -11,6 +11,7 @@ from ctypes import POINTER, c_char_p, c_int, c_int64, c_size_t, c_uint8, c_uint3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmpyc_b200.so')
+_VARIANT = os.environ.get('MPYC_B200_LIB')   # kernel-tuning builds (mpyc_b200/_build.py -D... -o<name>)
 
 OK, EINVAL, EUNSUPPORTED, EZERODIV, ECUDA, ENOMEM = 0, -1, -2, -3, -4, -5
 KIND_GENERIC, KIND_PM_ALIGNED, KIND_PM_SHIFT, KIND_GF256 = 0, 1, 2, 3
@@ -34,7 +35,7 @@ def _load():
     except RuntimeError:
         if not os.path.exists(LIB_PATH):
             raise
-    return ctypes.CDLL(LIB_PATH)
+    return ctypes.CDLL(os.path.join(_HERE, _VARIANT) if _VARIANT else LIB_PATH)
 
 
 lib = _load()

@@ -210,36 +210,53 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 //   full : table entry is a full field element in table form; acc (2L+1 limbs), one reduction
 // ---------------------------------------------------------------------------------------
 
-template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
-__device__ __forceinline__ void split_item(const FieldParams& f, const u64* secrets, const u64* coeffs,
-                                           size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
-                                           size_t limb_off) {
+#ifndef MPYC_SPLIT_U
+#define MPYC_SPLIT_U 2
+#endif
+#ifndef MPYC_REC_U
+#define MPYC_REC_U 2
+#endif
+
+// U items (item u at limb offset limb_off + u*limb_step) are processed together: every load is
+// issued before the first multiply so that U*(t+1) 16-byte requests per thread are in flight.
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, int U>
+__device__ __forceinline__ void split_items(const FieldParams& f, const u64* secrets, const u64* coeffs,
+                                            size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
+                                            size_t limb_off, size_t limb_step) {
     static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
-    u64 M[TP1][E * L];
-    load_limbs<E * L, VEC>(M[0], secrets + limb_off);
+    u64 M[U][TP1][E * L];
 #pragma unroll
-    for (int j = 1; j < TP1; j++) load_limbs<E * L, VEC>(M[j], coeffs + (size_t)(j - 1) * cstride + limb_off);
+    for (int u = 0; u < U; u++) {
+        const size_t off = limb_off + u * limb_step;
+        load_limbs<E * L, VEC>(M[u][0], secrets + off);
+#pragma unroll
+        for (int j = 1; j < TP1; j++) load_limbs<E * L, VEC>(M[u][j], coeffs + (size_t)(j - 1) * cstride + off);
+    }
     for (int i = 0; i < m; i++) {
-        u64 r[E * L];
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            if constexpr (FULL) {
-                u64 acc[2 * L + 1];
-                zero_n<2 * L + 1>(acc);
+        for (int u = 0; u < U; u++) {
+            u64 r[E * L];
 #pragma unroll
-                for (int j = 0; j < TP1; j++) Fp<L, KIND>::mac(acc, M[j] + e * L, tab + (size_t)(i * TP1 + j) * L);
-                Fp<L, KIND>::finish(r + e * L, acc, f);
-            } else {
-                u64 acc[L + 1];
-                copy_n<L>(acc, M[0] + e * L);
-                acc[L] = 0;
+            for (int e = 0; e < E; e++) {
+                if constexpr (FULL) {
+                    u64 acc[2 * L + 1];
+                    zero_n<2 * L + 1>(acc);
 #pragma unroll
-                for (int j = 1; j < TP1; j++) mac_1<L, L + 1>(acc, M[j] + e * L, tab[i * TP1 + j]);
-                if constexpr (TP1 > 1) Fp<L, KIND>::template pm_reduce<L + 1>(r + e * L, acc, f);
-                else copy_n<L>(r + e * L, acc);
+                    for (int j = 0; j < TP1; j++)
+                        Fp<L, KIND>::mac(acc, M[u][j] + e * L, tab + (size_t)(i * TP1 + j) * L);
+                    Fp<L, KIND>::finish(r + e * L, acc, f);
+                } else {
+                    u64 acc[L + 1];
+                    copy_n<L>(acc, M[u][0] + e * L);
+                    acc[L] = 0;
+#pragma unroll
+                    for (int j = 1; j < TP1; j++) mac_1<L, L + 1>(acc, M[u][j] + e * L, tab[i * TP1 + j]);
+                    if constexpr (TP1 > 1) Fp<L, KIND>::template pm_reduce<L + 1>(r + e * L, acc, f);
+                    else copy_n<L>(r + e * L, acc);
+                }
             }
+            store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off + u * limb_step, r);
         }
-        store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off, r);
     }
 }
 
@@ -251,16 +268,21 @@ k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ 
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
     constexpr int E = VEC ? VecItem<L>::E : 1;
+    constexpr int U = (TP1 * L <= 8) ? MPYC_SPLIT_U : 1;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
-    for (size_t it = tid; it < n_items; it += nth)
-        split_item<L, KIND, TP1, FULL, E, VEC>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
-                                               it * (size_t)(E * L));
+    size_t it = tid;
+    for (; it + (U - 1) * nth < n_items; it += U * nth)
+        split_items<L, KIND, TP1, FULL, E, VEC, U>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+                                                   it * (size_t)(E * L), nth * (size_t)(E * L));
+    for (; it < n_items; it += nth)
+        split_items<L, KIND, TP1, FULL, E, VEC, 1>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+                                                   it * (size_t)(E * L), 0);
     if constexpr (E > 1) {
         for (size_t h = n_items * E + tid; h < n; h += nth)
-            split_item<L, KIND, TP1, FULL, 1, false>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
-                                                     h * (size_t)L);
+            split_items<L, KIND, TP1, FULL, 1, false, 1>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+                                                         h * (size_t)L, 0);
     }
 }
 
@@ -295,31 +317,43 @@ k_split_dyn(FieldParams f, const u64* __restrict__ secrets, const u64* __restric
 // K3: Lagrange recombination.  tab[(r*k + i)*L ..] = lambda[r][i] in table form.
 // ---------------------------------------------------------------------------------------
 
-template <int L, int KIND, int E, bool VEC>
-__device__ __forceinline__ void recombine_item(const FieldParams& f, const RowPtrs& rows, int k, int width,
-                                               const u64* tab, u64* out, size_t ostride, size_t limb_off) {
-    constexpr int RB = 4;   // rows loaded per batch (loads issued before the multiplies)
+template <int L, int KIND, int E, bool VEC, int U>
+__device__ __forceinline__ void recombine_items(const FieldParams& f, const RowPtrs& rows, int k, int width,
+                                                const u64* tab, u64* out, size_t ostride, size_t limb_off,
+                                                size_t limb_step) {
+    constexpr int RB = (U * E * L <= 4) ? 4 : 2;   // rows loaded per batch (loads issued before the multiplies)
     for (int r = 0; r < width; r++) {
-        u64 acc[E][2 * L + 1];
+        u64 acc[U][E][2 * L + 1];
 #pragma unroll
-        for (int e = 0; e < E; e++) zero_n<2 * L + 1>(acc[e]);
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int e = 0; e < E; e++) zero_n<2 * L + 1>(acc[u][e]);
         for (int i0 = 0; i0 < k; i0 += RB) {
-            u64 x[RB][E * L];
+            u64 x[RB][U][E * L];
 #pragma unroll
             for (int b = 0; b < RB; b++)
-                if (i0 + b < k) load_limbs<E * L, VEC>(x[b], rows.p[i0 + b] + limb_off);
+                if (i0 + b < k) {
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        load_limbs<E * L, VEC>(x[b][u], rows.p[i0 + b] + limb_off + u * limb_step);
+                }
 #pragma unroll
             for (int b = 0; b < RB; b++)
                 if (i0 + b < k) {
                     const u64* lam = tab + (size_t)(r * k + i0 + b) * L;
 #pragma unroll
-                    for (int e = 0; e < E; e++) Fp<L, KIND>::mac(acc[e], x[b] + e * L, lam);
+                    for (int u = 0; u < U; u++)
+#pragma unroll
+                        for (int e = 0; e < E; e++) Fp<L, KIND>::mac(acc[u][e], x[b][u] + e * L, lam);
                 }
         }
-        u64 res[E * L];
 #pragma unroll
-        for (int e = 0; e < E; e++) Fp<L, KIND>::finish(res + e * L, acc[e], f);
-        store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off, res);
+        for (int u = 0; u < U; u++) {
+            u64 res[E * L];
+#pragma unroll
+            for (int e = 0; e < E; e++) Fp<L, KIND>::finish(res + e * L, acc[u][e], f);
+            store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);
+        }
     }
 }
 
@@ -331,14 +365,19 @@ k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
     constexpr int E = VEC ? VecItem<L>::E : 1;
+    constexpr int U = (L <= 2) ? MPYC_REC_U : 1;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
-    for (size_t it = tid; it < n_items; it += nth)
-        recombine_item<L, KIND, E, VEC>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L));
+    size_t it = tid;
+    for (; it + (U - 1) * nth < n_items; it += U * nth)
+        recombine_items<L, KIND, E, VEC, U>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L),
+                                            nth * (size_t)(E * L));
+    for (; it < n_items; it += nth)
+        recombine_items<L, KIND, E, VEC, 1>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L), 0);
     if constexpr (E > 1) {
         for (size_t h = n_items * E + tid; h < n; h += nth)
-            recombine_item<L, KIND, 1, false>(f, rows, k, width, stab, out, ostride, h * (size_t)L);
+            recombine_items<L, KIND, 1, false, 1>(f, rows, k, width, stab, out, ostride, h * (size_t)L, 0);
     }
 }
 

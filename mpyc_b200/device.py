@@ -253,7 +253,7 @@ def shamir_split(ctx, secrets: DeviceArray, coeffs, t, m, out=None):
     secrets._check_contiguous()
     if out is None:
         out = DeviceMatrix.empty(ctx, m, n, secrets.t.device)
-    cptr, cstride = (coeffs.ptr, coeffs.stride) if t > 0 else (ctypes.c_void_p(0), n)
+    cptr, cstride = (coeffs.ptr, coeffs.stride) if (t > 0 and coeffs is not None) else (ctypes.c_void_p(0), n)
     check(lib.mpyc_b200_shamir_split(ctx.handle, secrets.ptr, cptr, cstride, out.ptr, out.stride, n, t, m, _stream_ptr()))
     return out
 

@@ -88,10 +88,8 @@ def context_of_field(field):
     """FieldContext for an MPyC field class (finfields.GF(...)): prime fields by .modulus int,
     GF(2^8) by a gfpx.BinaryPolynomial modulus (integer encoding via int())."""
     modulus = field.modulus
-    if isinstance(modulus, int):
-        if getattr(field, 'ext_deg', 1) != 1:
-            raise _cabi.UnsupportedFieldError('extension fields other than GF(2^8) are not supported')
-        return context_for(modulus)
     if getattr(field, 'characteristic', None) == 2 and getattr(field, 'ext_deg', None) == 8:
         return context_for(int(modulus), binary=True)
+    if isinstance(modulus, int) and getattr(field, 'ext_deg', 1) == 1:
+        return context_for(modulus)
     raise _cabi.UnsupportedFieldError(f'field {getattr(field, "__name__", field)} is not supported by mpyc_b200')
