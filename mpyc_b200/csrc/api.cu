@@ -212,28 +212,33 @@ MPYC_API int mpyc_b200_field_info(const mpyc_b200_field* f, int* nlimbs, int* ki
 
 // canonical limbs of (v mod p) for a signed 64-bit integer v
 template <int L, int KIND>
-static void h_from_int(u64* r, int64_t v, const FieldParams& fp) {
+static void h_from_int(u32* r, int64_t v, const FieldParams& fp) {
     u64 mag = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
-    zero_n<L>(r);
+    zero_n<2 * L>(r);
     if (L == 1) mag %= fp.p[0];
-    r[0] = mag;   // L > 1: p >= 2^64 > mag
+    set64(r, 0, mag);   // L > 1: p >= 2^64 > mag
     if (v < 0) Fp<L, KIND>::neg(r, r, fp);
 }
 
 // canonical inverse by Fermat; returns false for zero
 template <int L, int KIND>
-static bool h_inv(u64* r, const u64* a, const FieldParams& fp) {
-    if (is_zero_n<L>(a)) return false;
-    u64 e[L], two[L];
-    zero_n<L>(two);
+static bool h_inv(u32* r, const u32* a, const FieldParams& fp) {
+    constexpr int N = 2 * L;
+    if (is_zero_n<N>(a)) return false;
+    u32 e32[N], two[N];
+    zero_n<N>(two);
     two[0] = 2;
-    sub_n<L>(e, fp.p, two);
-    u64 x[L];
+    sub_n<N>(e32, as32(fp.p), two);
+    u64 e[L];
+    for (int i = 0; i < L; i++) e[i] = get64(e32, i);
+    u32 x[N];
     Fp<L, KIND>::to_dom(x, a, fp);
     Fp<L, KIND>::dpow_uniform(x, x, e, (int)fp.k, fp);
     Fp<L, KIND>::from_dom(r, x, fp);
     return true;
 }
+
+static inline u32* w32(u64* x) { return reinterpret_cast<u32*>(x); }
 
 static int current_device() {
     int dev = 0;
@@ -298,13 +303,13 @@ static int build_split_table(const FieldParams& fp, int t, int m, std::vector<u6
         constexpr int K = decltype(Kc)::value;
         host.resize((size_t)m * (t + 1) * L);
         for (int i = 0; i < m; i++) {
-            u64 pt[L], x[L];
+            u32 pt[2 * L], x[2 * L];
             h_from_int<L, K>(pt, i + 1, fp);
             h_from_int<L, K>(x, 1, fp);
             for (int j = 0; j <= t; j++) {
-                u64 tf[L];
+                u32 tf[2 * L];
                 Fp<L, K>::to_dom(tf, x, fp);
-                for (int l = 0; l < L; l++) host[((size_t)i * (t + 1) + j) * L + l] = tf[l];
+                for (int l = 0; l < L; l++) host[((size_t)i * (t + 1) + j) * L + l] = get64(tf, l);
                 Fp<L, K>::mul(x, x, pt, fp);
             }
         }
@@ -319,26 +324,27 @@ static int compute_lambda(const FieldParams& fp, const int64_t* xs, int k, const
         constexpr int L = decltype(Lc)::value;
         constexpr int K = decltype(Kc)::value;
         typedef Fp<L, K> F;
+        constexpr int N = 2 * L;
         lam.assign((size_t)width * k * L, 0);
         std::vector<u64> X((size_t)k * L);
-        for (int i = 0; i < k; i++) h_from_int<L, K>(&X[(size_t)i * L], xs[i], fp);
+        for (int i = 0; i < k; i++) h_from_int<L, K>(w32(&X[(size_t)i * L]), xs[i], fp);
         for (int r = 0; r < width; r++) {
-            u64 xr[L];
+            u32 xr[N];
             h_from_int<L, K>(xr, x_rs[r], fp);
             for (int i = 0; i < k; i++) {
-                u64 num[L], den[L], d[L];
+                u32 num[N], den[N], d[N];
                 h_from_int<L, K>(num, 1, fp);
                 h_from_int<L, K>(den, 1, fp);
                 for (int j = 0; j < k; j++) {
                     if (j == i) continue;
-                    F::sub(d, xr, &X[(size_t)j * L], fp);
+                    F::sub(d, xr, w32(&X[(size_t)j * L]), fp);
                     F::mul(num, num, d, fp);
-                    F::sub(d, &X[(size_t)i * L], &X[(size_t)j * L], fp);
+                    F::sub(d, w32(&X[(size_t)i * L]), w32(&X[(size_t)j * L]), fp);
                     F::mul(den, den, d, fp);
                 }
-                u64 inv[L];
+                u32 inv[N];
                 if (!h_inv<L, K>(inv, den, fp)) return fail(MPYC_B200_EZERODIV, "recombination: repeated x-coordinate");
-                F::mul(&lam[((size_t)r * k + i) * L], num, inv, fp);
+                F::mul(w32(&lam[((size_t)r * k + i) * L]), num, inv, fp);
             }
         }
         return MPYC_B200_OK;
@@ -349,7 +355,7 @@ static void to_table_form(const FieldParams& fp, std::vector<u64>& v) {
     with_field(fp, [&](auto Lc, auto Kc) {
         constexpr int L = decltype(Lc)::value;
         constexpr int K = decltype(Kc)::value;
-        for (size_t i = 0; i + L <= v.size(); i += L) Fp<L, K>::to_dom(&v[i], &v[i], fp);
+        for (size_t i = 0; i + L <= v.size(); i += L) Fp<L, K>::to_dom(w32(&v[i]), w32(&v[i]), fp);
         return 0;
     });
 }
@@ -408,6 +414,25 @@ MPYC_API int mpyc_b200_ff_neg(const mpyc_b200_field* f, const void* d_a, void* d
 }
 
 // ---- pow family ------------------------------------------------------------------------------
+
+// tiny host helpers on little-endian u64 arrays (exponent arithmetic)
+static void wide_copy(u64* r, const u64* a, int n) { for (int i = 0; i < n; i++) r[i] = a[i]; }
+static void wide_add(u64* r, const u64* a, int n) {
+    unsigned __int128 cy = 0;
+    for (int i = 0; i < n; i++) { cy += (unsigned __int128)r[i] + a[i]; r[i] = (u64)cy; cy >>= 64; }
+}
+static void wide_add_small(u64* r, int n, u64 v) {
+    unsigned __int128 cy = v;
+    for (int i = 0; i < n; i++) { cy += r[i]; r[i] = (u64)cy; cy >>= 64; }
+}
+static void wide_sub_small(u64* r, int n, u64 v) {
+    for (int i = 0; i < n; i++) {
+        u64 before = r[i];
+        r[i] = before - v;
+        v = before < v ? 1 : 0;
+        if (!v) break;
+    }
+}
 
 struct ZeroFlag {   // one device int per call, freed on scope exit
     int* d = nullptr;
@@ -469,8 +494,9 @@ MPYC_API int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d
         CU(cudaStreamSynchronize(st));
         return flag ? fail(MPYC_B200_EZERODIV, "inverse of zero") : MPYC_B200_OK;
     }
-    u64 e[4] = {0, 0, 0, 0}, two[4] = {2, 0, 0, 0};
-    sub_n<4>(e, f->fp.p, two);
+    u64 e[4];
+    wide_copy(e, f->fp.p, 4);
+    wide_sub_small(e, 4, 2);   // p - 2
     return pow_impl(f, d_a, e, 4, 0, true, d_out, nullptr, n, st);
 }
 
@@ -493,18 +519,17 @@ MPYC_API int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int in
     }
     if ((f->fp.p[0] & 3) != 3) return fail(MPYC_B200_EUNSUPPORTED, "ff_sqrt: batched path needs a Blum prime (p % 4 == 3)");
     // e = (p+1)/4, or (3p-5)/4 for the inverse square root; up to 258 bits -> 5 limbs
-    u64 e[8] = {0};
+    u64 e[8] = {0}, t[5] = {f->fp.p[0], f->fp.p[1], f->fp.p[2], f->fp.p[3], 0};
     if (!inverse) {
-        u64 t[5] = {0}, one[5] = {1, 0, 0, 0, 0}, pp[5] = {f->fp.p[0], f->fp.p[1], f->fp.p[2], f->fp.p[3], 0};
-        add_n<5>(t, pp, one);
-        for (int i = 0; i < 5; i++) e[i] = (t[i] >> 2) | (i < 4 ? (t[i + 1] << 62) : 0);
+        wide_add_small(t, 5, 1);
     } else {
-        u64 pp[5] = {f->fp.p[0], f->fp.p[1], f->fp.p[2], f->fp.p[3], 0}, t[5], five[5] = {5, 0, 0, 0, 0};
-        add_n<5>(t, pp, pp);
-        add_n<5>(t, t, pp);
-        sub_n<5>(t, t, five);
-        for (int i = 0; i < 5; i++) e[i] = (t[i] >> 2) | (i < 4 ? (t[i + 1] << 62) : 0);
+        u64 pp[5];
+        wide_copy(pp, t, 5);
+        wide_add(t, pp, 5);
+        wide_add(t, pp, 5);        // 3p
+        wide_sub_small(t, 5, 5);   // 3p - 5
     }
+    for (int i = 0; i < 5; i++) e[i] = (t[i] >> 2) | (i < 4 ? (t[i + 1] << 62) : 0);
     return pow_impl(f, d_a, e, 5, 0, inverse != 0, d_out, nullptr, n, st);
 }
 

@@ -1,5 +1,9 @@
-// Multi-limb prime-field arithmetic for sm_100a (and, for table preparation and
-// algorithm tests, the host).  Little-endian 64-bit limbs, L in {1,2,3,4}.
+// Multi-limb prime-field arithmetic for sm_100a (and, for table preparation and algorithm
+// tests, the host).  Elements are L little-endian 64-bit limbs in memory (L in {1,2,3,4}); in
+// registers they are handled as N = 2L 32-bit limbs, because the native multiplier is
+// IMAD.WIDE.U32 (32x32+64 with carry in/out): every mad.lo.cc.u32 / madc.hi.cc.u32 pair below is
+// one such instruction, and products are accumulated in two interleaved carry chains (even and
+// odd columns) so that no extra additions are spent on carries.
 //
 // Two reduction families, chosen per modulus when the field context is created:
 //   * pseudo-Mersenne p = 2^k - c with c < 2^16 and k >= 56  (MPyC's default primes from
@@ -42,322 +46,397 @@ struct FieldParams {
     u64 c;       // PM: 2^k - p
     u32 k;       // bit length of p (PM: the exponent)
     u32 s;       // k % 64
-    u32 L;       // limbs
+    u32 L;       // 64-bit limbs
     u32 kind;
 };
 
+// 32-bit view of a little-endian u64 array (kernel parameters and tables are stored as u64)
+FF_HD const u32* as32(const u64* x) { return reinterpret_cast<const u32*>(x); }
+
 // ---------------------------------------------------------------------------------------
-// n-limb primitives.  Device: PTX carry chains (add.cc / madc.hi.cc ...), one instruction per
-// asm statement, fully unrolled so limbs stay in registers.  Host: unsigned __int128.
+// n-limb primitives on 32-bit limbs.  Device: PTX carry chains, one instruction per asm statement,
+// fully unrolled so limbs stay in registers.  Host: portable 64-bit arithmetic.
 // ---------------------------------------------------------------------------------------
 
 template <int N>
-FF_HD u64 add_n(u64* r, const u64* a, const u64* b) {
+FF_HD u32 add_n(u32* r, const u32* a, const u32* b) {
 #ifdef __CUDA_ARCH__
-    asm volatile("add.cc.u64 %0, %1, %2;" : "=l"(r[0]) : "l"(a[0]), "l"(b[0]));
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(a[0]), "r"(b[0]));
 #pragma unroll
     for (int i = 1; i < N; i++)
-        asm volatile("addc.cc.u64 %0, %1, %2;" : "=l"(r[i]) : "l"(a[i]), "l"(b[i]));
-    u64 cy;
-    asm volatile("addc.u64 %0, 0, 0;" : "=l"(cy));
+        asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(a[i]), "r"(b[i]));
+    u32 cy;
+    asm volatile("addc.u32 %0, 0, 0;" : "=r"(cy));
     return cy;
 #else
-    unsigned __int128 acc = 0;
+    u64 acc = 0;
     for (int i = 0; i < N; i++) {
-        acc += (unsigned __int128)a[i] + b[i];
-        r[i] = (u64)acc;
-        acc >>= 64;
+        acc += (u64)a[i] + b[i];
+        r[i] = (u32)acc;
+        acc >>= 32;
     }
-    return (u64)acc;
+    return (u32)acc;
 #endif
 }
 
 // r = a - b, returns 1 on borrow
 template <int N>
-FF_HD u64 sub_n(u64* r, const u64* a, const u64* b) {
+FF_HD u32 sub_n(u32* r, const u32* a, const u32* b) {
 #ifdef __CUDA_ARCH__
-    asm volatile("sub.cc.u64 %0, %1, %2;" : "=l"(r[0]) : "l"(a[0]), "l"(b[0]));
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r[0]) : "r"(a[0]), "r"(b[0]));
 #pragma unroll
     for (int i = 1; i < N; i++)
-        asm volatile("subc.cc.u64 %0, %1, %2;" : "=l"(r[i]) : "l"(a[i]), "l"(b[i]));
-    u64 bw;
-    asm volatile("subc.u64 %0, 0, 0;" : "=l"(bw));
-    return bw & 1ull;
+        asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r[i]) : "r"(a[i]), "r"(b[i]));
+    u32 bw;
+    asm volatile("subc.u32 %0, 0, 0;" : "=r"(bw));
+    return bw & 1u;
 #else
-    u64 bw = 0;
+    u32 bw = 0;
     for (int i = 0; i < N; i++) {
-        unsigned __int128 d = (unsigned __int128)a[i] - b[i] - bw;
-        r[i] = (u64)d;
-        bw = (u64)(d >> 64) & 1ull;
+        u64 d = (u64)a[i] - b[i] - bw;
+        r[i] = (u32)d;
+        bw = (u32)(d >> 32) & 1u;
     }
     return bw;
 #endif
 }
 
-// acc[0..REM) += a[0..N) * b   (REM >= N+1; a carry out of acc[REM-1] must be impossible)
-template <int N, int REM>
-FF_HD void mac_1(u64* acc, const u64* a, u64 b) {
-    static_assert(REM >= N + 1, "accumulator too short");
+// acc[0..W) += x[0..NX)   (NX <= W; the carry is propagated to the top of acc)
+template <int NX, int W>
+FF_HD void acc_add(u32* acc, const u32* x) {
+    static_assert(NX <= W, "accumulator too short");
 #ifdef __CUDA_ARCH__
-    asm volatile("mad.lo.cc.u64 %0, %1, %2, %0;" : "+l"(acc[0]) : "l"(a[0]), "l"(b));
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(acc[0]) : "r"(x[0]));
 #pragma unroll
-    for (int i = 1; i < N; i++)
-        asm volatile("madc.lo.cc.u64 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(a[i]), "l"(b));
+    for (int i = 1; i < NX; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(x[i]));
 #pragma unroll
-    for (int i = N; i < REM; i++)
-        asm volatile("addc.cc.u64 %0, %0, 0;" : "+l"(acc[i]));
-    asm volatile("mad.hi.cc.u64 %0, %1, %2, %0;" : "+l"(acc[1]) : "l"(a[0]), "l"(b));
-#pragma unroll
-    for (int i = 1; i < N; i++)
-        asm volatile("madc.hi.cc.u64 %0, %1, %2, %0;" : "+l"(acc[i + 1]) : "l"(a[i]), "l"(b));
-#pragma unroll
-    for (int i = N + 1; i < REM; i++)
-        asm volatile("addc.cc.u64 %0, %0, 0;" : "+l"(acc[i]));
+    for (int i = NX; i < W; i++) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(acc[i]));
 #else
-    unsigned __int128 cy = 0;
-    for (int i = 0; i < N; i++) {
-        cy += (unsigned __int128)a[i] * b + acc[i];
-        acc[i] = (u64)cy;
-        cy >>= 64;
-    }
-    for (int i = N; i < REM; i++) {
-        cy += acc[i];
-        acc[i] = (u64)cy;
-        cy >>= 64;
+    u64 cy = 0;
+    for (int i = 0; i < W; i++) {
+        cy += (u64)acc[i] + (i < NX ? x[i] : 0u);
+        acc[i] = (u32)cy;
+        cy >>= 32;
     }
 #endif
 }
 
-// acc[0..W) += a[0..LA) * b[0..LB)      (W >= LA + LB); row J of the schoolbook product
-template <int LA, int LB, int W, int J = 0>
-FF_HD void mac_n(u64* acc, const u64* a, const u64* b) {
-    static_assert(W >= LA + LB, "accumulator too short");
-    if constexpr (J < LB) {
-        mac_1<LA, W - J>(acc + J, a, b[J]);
-        mac_n<LA, LB, W, J + 1>(acc, a, b);
+// One carry chain: acc[i, i+1] += a[i] * b for i = I0, I0+2, ... < N, then the carry is added into
+// the following limbs up to W.  Each (mad.lo.cc, madc.hi.cc) pair is one IMAD.WIDE.U32.
+template <int N, int W, int I0>
+FF_HD void mad_chain(u32* acc, const u32* a, u32 b) {
+    if constexpr (I0 < N) {
+#ifdef __CUDA_ARCH__
+        asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc[I0]) : "r"(a[I0]), "r"(b));
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(acc[I0 + 1]) : "r"(a[I0]), "r"(b));
+#pragma unroll
+        for (int i = I0 + 2; i < N; i += 2) {
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(acc[i + 1]) : "r"(a[i]), "r"(b));
+        }
+        constexpr int LAST = I0 + 2 * ((N - 1 - I0) / 2);   // last index multiplied
+#pragma unroll
+        for (int c = LAST + 2; c < W; c++) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(acc[c]));
+#else
+        u64 cy = 0;
+        int c = I0;
+        for (int i = I0; i < N; i += 2) {
+            u64 prod = (u64)a[i] * b;
+            cy += (u64)acc[i] + (u32)prod;
+            acc[i] = (u32)cy;
+            cy >>= 32;
+            cy += (u64)acc[i + 1] + (prod >> 32);
+            acc[i + 1] = (u32)cy;
+            cy >>= 32;
+            c = i + 2;
+        }
+        for (; c < W; c++) {
+            cy += acc[c];
+            acc[c] = (u32)cy;
+            cy >>= 32;
+        }
+#endif
     }
 }
 
+// acc[0..W) += a[0..N) * b  (b one 32-bit limb).  W >= N+1; a carry out of acc[W-1] must be
+// impossible by construction (every caller's magnitude bound guarantees it).
+template <int N, int W>
+FF_HD void mac_small(u32* acc, const u32* a, u32 b) {
+    static_assert(W >= N + 1, "accumulator too short");
+    mad_chain<N, W, 0>(acc, a, b);
+    mad_chain<N, W, 1>(acc, a, b);
+}
+
+// r[0..NA+NB) = a[0..NA) * b[0..NB): products accumulated in two interleaved accumulators (E: pairs
+// starting at even columns, O: at odd columns), merged by one addition at the end.
+template <int NA, int NB, int J>
+FF_HD void mul_rows(u32* E, u32* O, const u32* a, const u32* b) {
+    if constexpr (J < NB) {
+        // row J: a[i]*b[J] lands in columns (i+J, i+J+1); the parity of i+J picks the accumulator.
+        // The limb above each chain holds at most earlier carry bits, so one more limb suffices.
+        constexpr int WE = ((NA - 1) / 2) * 2 + 3;            // even i: last i = 2*((NA-1)/2), + pair + carry
+        constexpr int WO = ((NA - 2) / 2) * 2 + 1 + 3;        // odd  i: last i = 1 + 2*((NA-2)/2)
+        if constexpr (J % 2 == 0) {
+            mad_chain<NA, WE, 0>(E + J, a, b[J]);
+            if constexpr (NA > 1) mad_chain<NA, WO, 1>(O + J, a, b[J]);
+        } else {
+            mad_chain<NA, WE, 0>(O + J, a, b[J]);
+            if constexpr (NA > 1) mad_chain<NA, WO, 1>(E + J, a, b[J]);
+        }
+        mul_rows<NA, NB, J + 1>(E, O, a, b);
+    }
+}
+
+template <int NA, int NB>
+FF_HD void mul_fresh(u32* r, const u32* a, const u32* b) {
+    u32 E[NA + NB + 2], O[NA + NB + 2];
+#pragma unroll
+    for (int i = 0; i < NA + NB + 2; i++) E[i] = O[i] = 0;
+    mul_rows<NA, NB, 0>(E, O, a, b);
+    add_n<NA + NB>(r, E, O);
+}
+
 template <int N>
-FF_HD void zero_n(u64* r) {
+FF_HD void zero_n(u32* r) {
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = 0;
 }
 
 template <int N>
-FF_HD void copy_n(u64* r, const u64* a) {
+FF_HD void copy_n(u32* r, const u32* a) {
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = a[i];
 }
 
 template <int N>
-FF_HD bool is_zero_n(const u64* a) {
-    u64 t = 0;
+FF_HD bool is_zero_n(const u32* a) {
+    u32 t = 0;
 #pragma unroll
     for (int i = 0; i < N; i++) t |= a[i];
     return t == 0;
 }
 
-// r = take ? t : r   (branch-free select)
+// r = take ? t : r
 template <int N>
-FF_HD void select_n(u64* r, const u64* t, bool take) {
-    u64 m = take ? ~0ull : 0ull;
+FF_HD void select_n(u32* r, const u32* t, bool take) {
 #pragma unroll
-    for (int i = 0; i < N; i++) r[i] = (t[i] & m) | (r[i] & ~m);
+    for (int i = 0; i < N; i++) r[i] = take ? t[i] : r[i];
+}
+
+FF_HD u64 get64(const u32* x, int i) { return (u64)x[2 * i] | ((u64)x[2 * i + 1] << 32); }
+FF_HD void set64(u32* x, int i, u64 v) {
+    x[2 * i] = (u32)v;
+    x[2 * i + 1] = (u32)(v >> 32);
 }
 
 // ---------------------------------------------------------------------------------------
-// Field<L, KIND>
+// Field<L, KIND>: all element arguments are N = 2L 32-bit limbs
 // ---------------------------------------------------------------------------------------
 
 template <int L, int KIND>
 struct Fp {
-    static constexpr int WACC = 2 * L + 1;   // lazy accumulator width (full products)
-    static constexpr int WSM = L + 1;        // lazy accumulator width (element * 64-bit constant)
+    static constexpr int N = 2 * L;          // 32-bit limbs per element
+    static constexpr int WACC = 2 * N + 2;   // lazy accumulator of full products   (2L+1 64-bit limbs)
+    static constexpr int WSM = N + 2;        // lazy accumulator of element * 64-bit constants (L+1)
 
-    // a in [0, 2p) (as L limbs plus an explicit carry bit `hi`)  ->  [0, p)
-    static FF_HD void csub(u64* a, u64 hi, const FieldParams& f) {
-        u64 t[L];
-        u64 bw = sub_n<L>(t, a, f.p);
-        select_n<L>(a, t, (hi != 0) | (bw == 0));
+    // a in [0, 2p) (N limbs plus an explicit carry `hi`)  ->  [0, p)
+    static FF_HD void csub(u32* a, u32 hi, const FieldParams& f) {
+        u32 t[N];
+        u32 bw = sub_n<N>(t, a, as32(f.p));
+        select_n<N>(a, t, (hi != 0) | (bw == 0));
     }
 
-    static FF_HD void add(u64* r, const u64* a, const u64* b, const FieldParams& f) {
-        u64 cy = add_n<L>(r, a, b);
+    static FF_HD void add(u32* r, const u32* a, const u32* b, const FieldParams& f) {
+        u32 cy = add_n<N>(r, a, b);
         csub(r, cy, f);
     }
 
-    static FF_HD void sub(u64* r, const u64* a, const u64* b, const FieldParams& f) {
-        u64 t[L];
-        u64 bw = sub_n<L>(r, a, b);
-        add_n<L>(t, r, f.p);
-        select_n<L>(r, t, bw != 0);
+    static FF_HD void sub(u32* r, const u32* a, const u32* b, const FieldParams& f) {
+        u32 t[N];
+        u32 bw = sub_n<N>(r, a, b);
+        add_n<N>(t, r, as32(f.p));
+        select_n<N>(r, t, bw != 0);
     }
 
-    static FF_HD void neg(u64* r, const u64* a, const FieldParams& f) {
-        u64 t[L];
-        bool z = is_zero_n<L>(a);
-        sub_n<L>(t, f.p, a);
-        zero_n<L>(r);
-        select_n<L>(r, t, !z);
+    static FF_HD void neg(u32* r, const u32* a, const FieldParams& f) {
+        u32 t[N];
+        bool z = is_zero_n<N>(a);
+        sub_n<N>(t, as32(f.p), a);
+        zero_n<N>(r);
+        select_n<N>(r, t, !z);
     }
 
-    // ---- pseudo-Mersenne: true reduction of a W-limb value ---------------------------
+    // ---- pseudo-Mersenne: true reduction of a W-limb value (W 32-bit limbs) ------------------
     // Precondition (met by every caller in this library): x < 2^(2k+20), k = bit length of p
     // (covers products < p^2, lazy sums of < 2^20 products, and 64-bit-constant sums < 2^64 p).
     template <int W>
-    static FF_HD void pm_reduce(u64* r, const u64* x, const FieldParams& f) {
-        static_assert(W > L && W <= 2 * L + 1, "unsupported width");
-        const u64 c = f.c;
-        u64 r1[L + 1];
+    static FF_HD void pm_reduce(u32* r, const u32* x, const FieldParams& f) {
+        static_assert(W == N + 2 || W == 2 * N || W == 2 * N + 2, "unsupported width");
+        const u32 c = (u32)f.c;
+        // number of 32-bit limbs of the part above the fold point that can be non-zero
+        constexpr int HM = (W == N + 2) ? 2 : (W == 2 * N ? N : N + 1);
+        u32 r1[N + 2];
         if constexpr (KIND == KIND_PM_ALIGNED) {
-            constexpr int H = W - L;                     // limbs above the fold point
-            copy_n<L>(r1, x);
-            r1[L] = 0;
-            constexpr int HM = H <= L ? H : L;
-            mac_1<HM, L + 1>(r1, x + L, c);
-            if constexpr (H == L + 1) r1[L] += x[2 * L] * c;       // top limb of a lazy sum is < 2^20
-            u64 u = r1[L] * c;                           // < 2^64 by the preconditions
-            u64 uu[L];
-            zero_n<L>(uu);
-            uu[0] = u;
-            u64 cy = add_n<L>(r, r1, uu);
-            zero_n<L>(uu);
-            uu[0] = cy ? c : 0;                          // 2^(64L) = c (mod p); cannot carry again
-            add_n<L>(r, r, uu);
+            copy_n<N>(r1, x);
+            r1[N] = r1[N + 1] = 0;
+            mac_small<HM, N + 2>(r1, x + N, c);
+            const u64 u = get64(r1, L) * c;              // < 2^64 by the precondition
+            u32 uu[N];
+            zero_n<N>(uu);
+            uu[0] = (u32)u;
+            uu[1] = (u32)(u >> 32);
+            u32 cy = add_n<N>(r, r1, uu);
+            if (cy) {                                    // 2^(64L) = c (mod p); cannot carry again.  Rare.
+                zero_n<N>(uu);
+                uu[0] = c;
+                add_n<N>(r, r, uu);
+            }
             csub(r, 0, f);
         } else {
             const u32 s = f.s;                           // 1..63, p = 2^(64(L-1)+s) - c
             const u64 mask = (1ull << s) - 1;
-            u64 hi[L + 1];
+            u32 hi[N + 2];
 #pragma unroll
             for (int i = 0; i <= L; i++) {
-                u64 lo_part = (L - 1 + i < W) ? (x[L - 1 + i] >> s) : 0;
-                u64 hi_part = (L + i < W) ? (x[L + i] << (64 - s)) : 0;
-                hi[i] = lo_part | hi_part;
+                u64 lo_part = (2 * (L - 1 + i) < W) ? (get64(x, L - 1 + i) >> s) : 0;
+                u64 hi_part = (2 * (L + i) < W) ? (get64(x, L + i) << (64 - s)) : 0;
+                set64(hi, i, lo_part | hi_part);
             }
-            copy_n<L>(r1, x);
-            r1[L - 1] &= mask;
-            r1[L] = 0;
-            mac_1<L, L + 1>(r1, hi, c);
-            if constexpr (2 * L - 1 < W) r1[L] += hi[L] * c;
-            u64 top = (r1[L - 1] >> s) | (r1[L] << (64 - s));
-            r1[L - 1] &= mask;
-            u64 uu[L];
-            zero_n<L>(uu);
-            uu[0] = top * c;
-            add_n<L>(r, r1, uu);
+            copy_n<N>(r1, x);
+            set64(r1, L - 1, get64(r1, L - 1) & mask);
+            r1[N] = r1[N + 1] = 0;
+            mac_small<HM, N + 2>(r1, hi, c);
+            const u64 top = (get64(r1, L - 1) >> s) | (get64(r1, L) << (64 - s));
+            set64(r1, L - 1, get64(r1, L - 1) & mask);
+            const u64 u = top * c;
+            u32 uu[N];
+            zero_n<N>(uu);
+            uu[0] = (u32)u;
+            uu[1] = (u32)(u >> 32);
+            add_n<N>(r, r1, uu);
             csub(r, 0, f);
         }
     }
 
-    // L+1 Montgomery rounds on T (2L+2 limbs): round I clears limb I
+    // ---- generic: Montgomery REDC with guard limb: returns x / R' mod p, canonical -----------
+    // Precondition: x < p * R'  (R' = 2^(64(L+1))).  One round per 64-bit limb.
     template <int I>
-    static FF_HD void redc_rounds(u64* T, const FieldParams& f) {
+    static FF_HD void redc_rounds(u32* T, const FieldParams& f) {
         if constexpr (I <= L) {
-            u64 m = T[I] * f.pinv;
-            mac_1<L, 2 * L + 2 - I>(T + I, f.p, m);
+            const u64 m = get64(T, I) * f.pinv;
+            u32 m32[2] = {(u32)m, (u32)(m >> 32)};
+            u32 P[N + 2];
+            mul_fresh<N, 2>(P, as32(f.p), m32);
+            acc_add<N + 2, 2 * N + 4 - 2 * I>(T + 2 * I, P);
             redc_rounds<I + 1>(T, f);
         }
     }
 
-    // ---- generic: Montgomery REDC with guard limb: returns x / R' mod p, canonical -----
-    // Precondition: x < p * R'  (R' = 2^(64(L+1))).
     template <int W>
-    static FF_HD void redc(u64* r, const u64* x, const FieldParams& f) {
-        static_assert(W >= 1 && W <= 2 * L + 1, "unsupported width");
-        u64 T[2 * L + 2];
+    static FF_HD void redc(u32* r, const u32* x, const FieldParams& f) {
+        static_assert(W >= 1 && W <= 2 * N + 2, "unsupported width");
+        u32 T[2 * N + 4];
 #pragma unroll
-        for (int i = 0; i < 2 * L + 2; i++) T[i] = i < W ? x[i] : 0;
+        for (int i = 0; i < 2 * N + 4; i++) T[i] = i < W ? x[i] : 0;
         redc_rounds<0>(T, f);
-        // result = T[L+1 .. 2L+2) < 2p
-        copy_n<L>(r, T + L + 1);
-        csub(r, T[2 * L + 1], f);
+        copy_n<N>(r, T + N + 2);          // result = T[N+2 .. 2N+4) < 2p
+        csub(r, T[2 * N + 2], f);
     }
 
-    // acc (WACC limbs) += a * tab        (tab: L limbs, table form)
-    static FF_HD void mac(u64* acc, const u64* a, const u64* tab) { mac_n<L, L, WACC>(acc, a, tab); }
+    // acc (WACC limbs) += a * tab        (tab: N limbs, table form)
+    static FF_HD void mac(u32* acc, const u32* a, const u32* tab) {
+        u32 P[2 * N];
+        mul_fresh<N, N>(P, a, tab);
+        acc_add<2 * N, WACC>(acc, P);
+    }
+
+    // acc (WSM limbs) += a * v   for a plain 64-bit constant v (pseudo-Mersenne fields)
+    static FF_HD void mac_const(u32* acc, const u32* a, u64 v) {
+        mac_small<N, WSM>(acc, a, (u32)v);
+        const u32 vh = (u32)(v >> 32);
+        if (vh) mac_small<N, WSM - 1>(acc + 1, a, vh);   // table entries are warp-uniform
+    }
 
     // r = lazily accumulated sum, reduced.  GENERIC: the table-form factor R' is divided out.
-    static FF_HD void finish(u64* r, const u64* acc, const FieldParams& f) {
+    static FF_HD void finish(u32* r, const u32* acc, const FieldParams& f) {
         if constexpr (KIND == KIND_GENERIC) redc<WACC>(r, acc, f);
         else pm_reduce<WACC>(r, acc, f);
     }
 
     // "domain" multiplication: PM: plain modular product.  GENERIC: Montgomery product ab/R'.
-    static FF_HD void dmul(u64* r, const u64* a, const u64* b, const FieldParams& f) {
-        u64 x[2 * L];
-        zero_n<2 * L>(x);
-        mac_n<L, L, 2 * L>(x, a, b);
-        if constexpr (KIND == KIND_GENERIC) redc<2 * L>(r, x, f);
-        else pm_reduce<2 * L>(r, x, f);
+    static FF_HD void dmul(u32* r, const u32* a, const u32* b, const FieldParams& f) {
+        u32 x[2 * N];
+        mul_fresh<N, N>(x, a, b);
+        if constexpr (KIND == KIND_GENERIC) redc<2 * N>(r, x, f);
+        else pm_reduce<2 * N>(r, x, f);
     }
 
-    static FF_HD void to_dom(u64* r, const u64* a, const FieldParams& f) {
-        if constexpr (KIND == KIND_GENERIC) dmul(r, a, f.r2, f);
-        else copy_n<L>(r, a);
+    static FF_HD void to_dom(u32* r, const u32* a, const FieldParams& f) {
+        if constexpr (KIND == KIND_GENERIC) dmul(r, a, as32(f.r2), f);
+        else copy_n<N>(r, a);
     }
 
-    static FF_HD void from_dom(u64* r, const u64* a, const FieldParams& f) {
-        if constexpr (KIND == KIND_GENERIC) redc<L>(r, a, f);
-        else copy_n<L>(r, a);
+    static FF_HD void from_dom(u32* r, const u32* a, const FieldParams& f) {
+        if constexpr (KIND == KIND_GENERIC) redc<N>(r, a, f);
+        else copy_n<N>(r, a);
     }
 
-    static FF_HD void dom_one(u64* r, const FieldParams& f) {
-        if constexpr (KIND == KIND_GENERIC) copy_n<L>(r, f.r1);
+    static FF_HD void dom_one(u32* r, const FieldParams& f) {
+        if constexpr (KIND == KIND_GENERIC) copy_n<N>(r, as32(f.r1));
         else {
-            zero_n<L>(r);
+            zero_n<N>(r);
             r[0] = 1;
         }
     }
 
     // canonical * canonical -> canonical
-    static FF_HD void mul(u64* r, const u64* a, const u64* b, const FieldParams& f) {
+    static FF_HD void mul(u32* r, const u32* a, const u32* b, const FieldParams& f) {
         if constexpr (KIND == KIND_GENERIC) {
-            u64 t[L];
-            dmul(t, a, b, f);        // ab / R'
-            dmul(r, t, f.r2, f);     // ab
+            u32 t[N];
+            dmul(t, a, b, f);                // ab / R'
+            dmul(r, t, as32(f.r2), f);       // ab
         } else {
             dmul(r, a, b, f);
         }
     }
 
-    // true reduction of an arbitrary (L+1)-limb value
-    static FF_HD void reduce_small(u64* r, const u64* x, const FieldParams& f) {
+    // true reduction of an (L+1)-limb value x < 2^64 p  (WSM 32-bit limbs)
+    static FF_HD void reduce_small(u32* r, const u32* x, const FieldParams& f) {
         if constexpr (KIND == KIND_GENERIC) {
-            u64 t[L];
-            redc<L + 1>(t, x, f);    // x / R'
-            dmul(r, t, f.r2, f);     // x
+            u32 t[N];
+            redc<WSM>(t, x, f);              // x / R'
+            dmul(r, t, as32(f.r2), f);       // x
         } else {
-            pm_reduce<L + 1>(r, x, f);
+            pm_reduce<WSM>(r, x, f);
         }
     }
 
-    // r = a^e in the domain; e = little-endian limbs, ebits = bit length of e (>= 0)
-    static FF_HD void dpow(u64* r, const u64* a, const u64* e, int ebits, const FieldParams& f) {
-        u64 acc[L];
+    // r = a^e in the domain; e = little-endian 64-bit limbs, ebits = bit length of e (>= 0).
+    // Branch-free in the exponent (per-thread exponents).
+    static FF_HD void dpow(u32* r, const u32* a, const u64* e, int ebits, const FieldParams& f) {
+        u32 acc[N];
         dom_one(acc, f);
         for (int i = ebits - 1; i >= 0; i--) {
-            u64 sq[L];
+            u32 sq[N], mu[N];
             dmul(sq, acc, acc, f);
-            u64 mu[L];
             dmul(mu, sq, a, f);
-            bool bit = (e[i >> 6] >> (i & 63)) & 1;   // per-thread exponent: stay branch-free
-            copy_n<L>(acc, sq);
-            select_n<L>(acc, mu, bit);
+            bool bit = (e[i >> 6] >> (i & 63)) & 1;
+            copy_n<N>(acc, sq);
+            select_n<N>(acc, mu, bit);
         }
-        copy_n<L>(r, acc);
+        copy_n<N>(r, acc);
     }
 
     // same, for an exponent that is identical for every thread (public: p-2, (p+1)/4, ...):
     // the branch on the exponent bit is warp-uniform, so zero bits cost one squaring only.
-    static FF_HD void dpow_uniform(u64* r, const u64* a, const u64* e, int ebits, const FieldParams& f) {
-        u64 acc[L];
+    static FF_HD void dpow_uniform(u32* r, const u32* a, const u64* e, int ebits, const FieldParams& f) {
+        u32 acc[N];
         dom_one(acc, f);
         for (int i = ebits - 1; i >= 0; i--) {
             dmul(acc, acc, acc, f);
             if ((e[i >> 6] >> (i & 63)) & 1) dmul(acc, acc, a, f);
         }
-        copy_n<L>(r, acc);
+        copy_n<N>(r, acc);
     }
 };

@@ -14,12 +14,12 @@ static inline int bit_length(const u64* x, int n) {
 template <int LL>
 static inline void montgomery_constants(FieldParams& fp) {
     typedef Fp<LL, KIND_GENERIC> F;
-    u64 x[LL] = {0};
+    u32 x[2 * LL] = {0};
     x[0] = 1;   // 1 mod p (p >= 3)
     for (int i = 0; i < 64 * (LL + 1); i++) F::add(x, x, x, fp);   // R' = 2^(64(L+1)) mod p by doubling
-    for (int i = 0; i < LL; i++) fp.r1[i] = x[i];
+    for (int i = 0; i < LL; i++) fp.r1[i] = get64(x, i);
     for (int i = 0; i < 64 * (LL + 1); i++) F::add(x, x, x, fp);   // R'^2 mod p
-    for (int i = 0; i < LL; i++) fp.r2[i] = x[i];
+    for (int i = 0; i < LL; i++) fp.r2[i] = get64(x, i);
 }
 
 // modulus: nlimbs (already stripped of leading zero limbs, 1..4) limbs of an odd p >= 3

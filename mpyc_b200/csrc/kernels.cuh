@@ -32,41 +32,40 @@ struct ExpParams {
 // memory helpers
 // ---------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void ldg_v2(u64& x, u64& y, const u64* p) {
-    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p));
+__device__ __forceinline__ void ldg_v4(u32* v, const u64* p) {   // 16 bytes = two 64-bit limbs
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
 }
-__device__ __forceinline__ u64 ldg_1(const u64* p) {
-    u64 x;
-    asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(x) : "l"(p));
-    return x;
+__device__ __forceinline__ void ldg_v2(u32* v, const u64* p) {   // one 64-bit limb
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(p));
 }
-__device__ __forceinline__ void stg_v2(u64* p, u64 x, u64 y) {
-    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+__device__ __forceinline__ void stg_v4(u64* p, const u32* v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
-__device__ __forceinline__ void stg_1(u64* p, u64 x) {
-    asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
+__device__ __forceinline__ void stg_v2(u64* p, const u32* v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
 }
 
-// load / store NL limbs (NL even when VEC) starting at p
+// load / store NL 64-bit limbs (NL even when VEC) starting at p, as 2*NL 32-bit registers
 template <int NL, bool VEC>
-__device__ __forceinline__ void load_limbs(u64* v, const u64* p) {
+__device__ __forceinline__ void load_limbs(u32* v, const u64* p) {
     if constexpr (VEC) {
         static_assert(NL % 2 == 0, "vector path moves limb pairs");
 #pragma unroll
-        for (int q = 0; q < NL / 2; q++) ldg_v2(v[2 * q], v[2 * q + 1], p + 2 * q);
+        for (int q = 0; q < NL / 2; q++) ldg_v4(v + 4 * q, p + 2 * q);
     } else {
 #pragma unroll
-        for (int q = 0; q < NL; q++) v[q] = ldg_1(p + q);
+        for (int q = 0; q < NL; q++) ldg_v2(v + 2 * q, p + q);
     }
 }
 template <int NL, bool VEC>
-__device__ __forceinline__ void store_limbs(u64* p, const u64* v) {
+__device__ __forceinline__ void store_limbs(u64* p, const u32* v) {
     if constexpr (VEC) {
 #pragma unroll
-        for (int q = 0; q < NL / 2; q++) stg_v2(p + 2 * q, v[2 * q], v[2 * q + 1]);
+        for (int q = 0; q < NL / 2; q++) stg_v4(p + 2 * q, v + 4 * q);
     } else {
 #pragma unroll
-        for (int q = 0; q < NL; q++) stg_1(p + q, v[q]);
+        for (int q = 0; q < NL; q++) stg_v2(p + q, v + 2 * q);
     }
 }
 
@@ -118,7 +117,7 @@ __device__ __forceinline__ void tma_stage_table(void* smem_dst, const void* gmem
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_NEG = 3 };
 
 template <int L, int KIND, int OP>
-__device__ __forceinline__ void apply_op(u64* r, const u64* a, const u64* b, const FieldParams& f) {
+__device__ __forceinline__ void apply_op(u32* r, const u32* a, const u32* b, const FieldParams& f) {
     if constexpr (OP == OP_ADD) Fp<L, KIND>::add(r, a, b, f);
     else if constexpr (OP == OP_SUB) Fp<L, KIND>::sub(r, a, b, f);
     else if constexpr (OP == OP_MUL) Fp<L, KIND>::mul(r, a, b, f);
@@ -128,9 +127,10 @@ __device__ __forceinline__ void apply_op(u64* r, const u64* a, const u64* b, con
 // SCALAR: b is one broadcast element (canonical) in sc; NEG ignores b.
 // U items are processed together: all loads are issued before the first multiply.
 template <int L, int KIND, int OP, bool SCALAR, int E, bool VEC, int U>
-__device__ __forceinline__ void binop_items(const FieldParams& f, const u64* a, const u64* b, const u64* sc,
+__device__ __forceinline__ void binop_items(const FieldParams& f, const u64* a, const u64* b, const u32* sc,
                                             u64* out, size_t item0, size_t item_step) {
-    u64 x[U][E * L], y[U][E * L];
+    constexpr int N = 2 * L;
+    u32 x[U][E * N], y[U][E * N];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const size_t off = (item0 + u * item_step) * (size_t)(E * L);
@@ -139,11 +139,11 @@ __device__ __forceinline__ void binop_items(const FieldParams& f, const u64* a, 
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        u64 r[E * L];
+        u32 r[E * N];
 #pragma unroll
         for (int e = 0; e < E; e++) {
-            if constexpr (SCALAR) apply_op<L, KIND, OP>(r + e * L, x[u] + e * L, sc, f);
-            else apply_op<L, KIND, OP>(r + e * L, x[u] + e * L, y[u] + e * L, f);
+            if constexpr (SCALAR) apply_op<L, KIND, OP>(r + e * N, x[u] + e * N, sc, f);
+            else apply_op<L, KIND, OP>(r + e * N, x[u] + e * N, y[u] + e * N, f);
         }
         store_limbs<E * L, VEC>(out + (item0 + u * item_step) * (size_t)(E * L), r);
     }
@@ -158,9 +158,9 @@ k_binop(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, Sca
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
-    u64 sc[L];
+    u32 sc[2 * L];
 #pragma unroll
-    for (int i = 0; i < L; i++) sc[i] = scal.v[i];
+    for (int i = 0; i < 2 * L; i++) sc[i] = as32(scal.v)[i];
     size_t it = tid;
     for (; it + (U - 1) * nth < n_items; it += U * nth)
         binop_items<L, KIND, OP, SCALAR, E, VEC, U>(f, a, b, sc, out, it, nth);
@@ -182,9 +182,10 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
       int* zero_flag, size_t n) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
-        u64 x[L], r[L];
+        constexpr int N = 2 * L;
+        u32 x[N], r[N];
         load_limbs<L, false>(x, a + h * L);
-        if (zero_flag != nullptr && is_zero_n<L>(x)) *zero_flag = 1;
+        if (zero_flag != nullptr && is_zero_n<N>(x)) *zero_flag = 1;
         Fp<L, KIND>::to_dom(x, x, f);
         Fp<L, KIND>::dpow_uniform(r, x, ex.e, ex.ebits, f);
         Fp<L, KIND>::from_dom(r, r, f);
@@ -192,12 +193,12 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
             store_limbs<L, false>(out + h * L, r);
         } else {
             // legendre(a, p) == -1  <=>  a^((p-1)/2) == p - 1
-            u64 pm1[L];
-            copy_n<L>(pm1, f.p);
+            u32 pm1[N];
+            copy_n<N>(pm1, as32(f.p));
             pm1[0] -= 1;   // p odd
-            u64 d = 0;
+            u32 d = 0;
 #pragma unroll
-            for (int i = 0; i < L; i++) d |= r[i] ^ pm1[i];
+            for (int i = 0; i < N; i++) d |= r[i] ^ pm1[i];
             out_u8[h] = d != 0;
         }
     }
@@ -210,11 +211,16 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 //   full : table entry is a full field element in table form; acc (2L+1 limbs), one reduction
 // ---------------------------------------------------------------------------------------
 
+// items in flight per thread (tuned on B200: split is fastest without unrolling, recombine with
+// 4 items for 1-limb and 2 items for 2-limb fields); override with -D for experiments
 #ifndef MPYC_SPLIT_U
-#define MPYC_SPLIT_U 2
+#define MPYC_SPLIT_U 1
 #endif
-#ifndef MPYC_REC_U
-#define MPYC_REC_U 2
+#ifndef MPYC_REC_U1
+#define MPYC_REC_U1 4
+#endif
+#ifndef MPYC_REC_U2
+#define MPYC_REC_U2 2
 #endif
 
 // U items (item u at limb offset limb_off + u*limb_step) are processed together: every load is
@@ -224,7 +230,9 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
                                             size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
                                             size_t limb_off, size_t limb_step) {
     static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
-    u64 M[U][TP1][E * L];
+    constexpr int N = 2 * L;
+    typedef Fp<L, KIND> F;
+    u32 M[U][TP1][E * N];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const size_t off = limb_off + u * limb_step;
@@ -235,24 +243,24 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
     for (int i = 0; i < m; i++) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            u64 r[E * L];
+            u32 r[E * N];
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 if constexpr (FULL) {
-                    u64 acc[2 * L + 1];
-                    zero_n<2 * L + 1>(acc);
+                    u32 acc[F::WACC];
+                    zero_n<F::WACC>(acc);
 #pragma unroll
                     for (int j = 0; j < TP1; j++)
-                        Fp<L, KIND>::mac(acc, M[u][j] + e * L, tab + (size_t)(i * TP1 + j) * L);
-                    Fp<L, KIND>::finish(r + e * L, acc, f);
+                        F::mac(acc, M[u][j] + e * N, as32(tab + (size_t)(i * TP1 + j) * L));
+                    F::finish(r + e * N, acc, f);
                 } else {
-                    u64 acc[L + 1];
-                    copy_n<L>(acc, M[u][0] + e * L);
-                    acc[L] = 0;
+                    u32 acc[F::WSM];
+                    copy_n<N>(acc, M[u][0] + e * N);
+                    acc[N] = acc[N + 1] = 0;
 #pragma unroll
-                    for (int j = 1; j < TP1; j++) mac_1<L, L + 1>(acc, M[u][j] + e * L, tab[i * TP1 + j]);
-                    if constexpr (TP1 > 1) Fp<L, KIND>::template pm_reduce<L + 1>(r + e * L, acc, f);
-                    else copy_n<L>(r + e * L, acc);
+                    for (int j = 1; j < TP1; j++) F::mac_const(acc, M[u][j] + e * N, tab[i * TP1 + j]);
+                    if constexpr (TP1 > 1) F::template pm_reduce<F::WSM>(r + e * N, acc, f);
+                    else copy_n<N>(r + e * N, acc);
                 }
             }
             store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off + u * limb_step, r);
@@ -294,20 +302,21 @@ k_split_dyn(FieldParams f, const u64* __restrict__ secrets, const u64* __restric
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
         for (int i = 0; i < m; i++) {
-            u64 acc[2 * L + 1];
-            zero_n<2 * L + 1>(acc);
+            typedef Fp<L, KIND> F;
+            u32 acc[F::WACC];
+            zero_n<F::WACC>(acc);
             for (int j = 0; j < tp1; j++) {
-                u64 x[L], w[L];
+                u32 x[2 * L], w[2 * L];
                 const u64* src = j == 0 ? secrets + h * L : coeffs + (size_t)(j - 1) * cstride + h * L;
 #pragma unroll
                 for (int l = 0; l < L; l++) {
-                    x[l] = src[l];
-                    w[l] = gtab[(size_t)(i * tp1 + j) * L + l];
+                    set64(x, l, src[l]);
+                    set64(w, l, gtab[(size_t)(i * tp1 + j) * L + l]);
                 }
-                Fp<L, KIND>::mac(acc, x, w);
+                F::mac(acc, x, w);
             }
-            u64 r[L];
-            Fp<L, KIND>::finish(r, acc, f);
+            u32 r[2 * L];
+            F::finish(r, acc, f);
             store_limbs<L, false>(shares + (size_t)i * sstride + h * L, r);
         }
     }
@@ -322,14 +331,16 @@ __device__ __forceinline__ void recombine_items(const FieldParams& f, const RowP
                                                 const u64* tab, u64* out, size_t ostride, size_t limb_off,
                                                 size_t limb_step) {
     constexpr int RB = (U * E * L <= 4) ? 4 : 2;   // rows loaded per batch (loads issued before the multiplies)
+    constexpr int N = 2 * L;
+    typedef Fp<L, KIND> F;
     for (int r = 0; r < width; r++) {
-        u64 acc[U][E][2 * L + 1];
+        u32 acc[U][E][F::WACC];
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
-            for (int e = 0; e < E; e++) zero_n<2 * L + 1>(acc[u][e]);
+            for (int e = 0; e < E; e++) zero_n<F::WACC>(acc[u][e]);
         for (int i0 = 0; i0 < k; i0 += RB) {
-            u64 x[RB][U][E * L];
+            u32 x[RB][U][E * N];
 #pragma unroll
             for (int b = 0; b < RB; b++)
                 if (i0 + b < k) {
@@ -340,18 +351,19 @@ __device__ __forceinline__ void recombine_items(const FieldParams& f, const RowP
 #pragma unroll
             for (int b = 0; b < RB; b++)
                 if (i0 + b < k) {
-                    const u64* lam = tab + (size_t)(r * k + i0 + b) * L;
+                    u32 lam[N];
+                    copy_n<N>(lam, as32(tab + (size_t)(r * k + i0 + b) * L));
 #pragma unroll
                     for (int u = 0; u < U; u++)
 #pragma unroll
-                        for (int e = 0; e < E; e++) Fp<L, KIND>::mac(acc[u][e], x[b][u] + e * L, lam);
+                        for (int e = 0; e < E; e++) F::mac(acc[u][e], x[b][u] + e * N, lam);
                 }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            u64 res[E * L];
+            u32 res[E * N];
 #pragma unroll
-            for (int e = 0; e < E; e++) Fp<L, KIND>::finish(res + e * L, acc[u][e], f);
+            for (int e = 0; e < E; e++) F::finish(res + e * N, acc[u][e], f);
             store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);
         }
     }
@@ -365,7 +377,7 @@ k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
     constexpr int E = VEC ? VecItem<L>::E : 1;
-    constexpr int U = (L <= 2) ? MPYC_REC_U : 1;
+    constexpr int U = (L == 1) ? MPYC_REC_U1 : (L == 2 ? MPYC_REC_U2 : 1);
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
@@ -400,17 +412,19 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
     const int nl = (chunk_bytes + 7) >> 3;   // limbs per chunk
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
-        u64 outer[2 * L + 1];
-        zero_n<2 * L + 1>(outer);
+        typedef Fp<L, KIND> F;
+        constexpr int N = 2 * L;
+        u32 outer[F::WACC];
+        zero_n<F::WACC>(outer);
         for (int S = 0; S < nsub; S++) {
-            u64 inner[2 * L + 1];
-            zero_n<2 * L + 1>(inner);
+            u32 inner[F::WACC];
+            zero_n<F::WACC>(inner);
             for (int j = 0; j < d; j++) {
                 const unsigned char* src = bytes + (size_t)S * subset_stride + (h * d + j) * (size_t)chunk_bytes;
                 // value = little-endian integer of chunk_bytes bytes, reduced limb by limb from the top:
                 // v <- (v * 2^64 + limb) mod p   ((L+1)-limb value < 2^64 p)
-                u64 v[L];
-                zero_n<L>(v);
+                u32 v[N];
+                zero_n<N>(v);
                 for (int w = nl - 1; w >= 0; w--) {
                     u64 limb = 0;
                     int lo = w * 8, hi = min(lo + 8, chunk_bytes);
@@ -420,23 +434,23 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
                         if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
 #pragma unroll
                         for (int l = 0; l < L; l++)
-                            if (l == w) v[l] = limb;
+                            if (l == w) set64(v, l, limb);
                     } else {
-                        u64 x[L + 1];
-                        x[0] = limb;
+                        u32 x[N + 2];
+                        set64(x, 0, limb);
 #pragma unroll
-                        for (int l = 0; l < L; l++) x[l + 1] = v[l];
-                        Fp<L, KIND>::reduce_small(v, x, f);
+                        for (int l = 0; l < N; l++) x[l + 2] = v[l];
+                        F::reduce_small(v, x, f);
                     }
                 }
-                Fp<L, KIND>::mac(inner, v, wts + (size_t)j * L);
+                F::mac(inner, v, as32(wts + (size_t)j * L));
             }
-            u64 y[L];
-            Fp<L, KIND>::finish(y, inner, f);
-            Fp<L, KIND>::mac(outer, y, coef + (size_t)S * L);
+            u32 y[N];
+            F::finish(y, inner, f);
+            F::mac(outer, y, as32(coef + (size_t)S * L));
         }
-        u64 r[L];
-        Fp<L, KIND>::finish(r, outer, f);
+        u32 r[N];
+        F::finish(r, outer, f);
         store_limbs<L, false>(out + h * L, r);
     }
 }
@@ -457,7 +471,8 @@ __global__ void __launch_bounds__(MPYC_THREADS)
 k_fill_random(FieldParams f, u64* __restrict__ out, size_t n, u64 base) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
-        u64 x[L + 1], r[L];
+        u64 x[L + 1];
+        u32 r[2 * L];
 #pragma unroll
         for (int w = 0; w <= L; w++) x[w] = splitmix64_dev(base + h * (L + 1) + w);
         // keep bits(p)+64 bits so that the value is < 2^64 p (precondition of reduce_small)
@@ -470,7 +485,10 @@ k_fill_random(FieldParams f, u64* __restrict__ out, size_t n, u64 base) {
                 else if ((u32)w == top) x[w] = sh ? (x[w] & ((1ull << sh) - 1)) : 0;
             }
         }
-        Fp<L, KIND>::reduce_small(r, x, f);
+        u32 x32[2 * L + 2];
+#pragma unroll
+        for (int w = 0; w <= L; w++) set64(x32, w, x[w]);
+        Fp<L, KIND>::reduce_small(r, x32, f);
         store_limbs<L, false>(out + h * L, r);
     }
 }

@@ -17,25 +17,26 @@
 #include <sstream>
 #include "../../mpyc_b200/csrc/field_setup.h"
 
-static void parse_hex(const std::string& s, u64* out, int n) {
+// n = number of 32-bit limbs
+static void parse_hex(const std::string& s, u32* out, int n) {
     for (int i = 0; i < n; i++) out[i] = 0;
     int pos = 0;
     for (int i = (int)s.size() - 1; i >= 0; i--, pos++) {
         char c = s[i];
-        u64 v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
-        if (pos / 16 < n) out[pos / 16] |= v << (4 * (pos % 16));
+        u32 v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        if (pos / 8 < n) out[pos / 8] |= v << (4 * (pos % 8));
     }
 }
-static std::string to_hex(const u64* x, int n) {
+static std::string to_hex(const u32* x, int n) {
     char buf[32];
     std::string s;
     bool started = false;
     for (int i = n - 1; i >= 0; i--) {
         if (!started) {
             if (x[i] == 0 && i > 0) continue;
-            snprintf(buf, sizeof buf, "%llx", x[i]);
+            snprintf(buf, sizeof buf, "%x", x[i]);
             started = true;
-        } else snprintf(buf, sizeof buf, "%016llx", x[i]);
+        } else snprintf(buf, sizeof buf, "%08x", x[i]);
         s += buf;
     }
     return s;
@@ -46,69 +47,72 @@ static FieldParams fp;
 template <int L, int K>
 static std::string run(const std::string& cmd, std::istringstream& in) {
     typedef Fp<L, K> F;
+    constexpr int N = 2 * L;
     std::string t;
-    u64 a[L], b[L], r[L];
+    u32 a[N], b[N], r[N];
     if (cmd == "mul" || cmd == "add" || cmd == "sub") {
-        in >> t; parse_hex(t, a, L);
-        in >> t; parse_hex(t, b, L);
+        in >> t; parse_hex(t, a, N);
+        in >> t; parse_hex(t, b, N);
         if (cmd == "mul") F::mul(r, a, b, fp);
         else if (cmd == "add") F::add(r, a, b, fp);
         else F::sub(r, a, b, fp);
-        return to_hex(r, L);
+        return to_hex(r, N);
     }
     if (cmd == "neg") {
-        in >> t; parse_hex(t, a, L);
+        in >> t; parse_hex(t, a, N);
         F::neg(r, a, fp);
-        return to_hex(r, L);
+        return to_hex(r, N);
     }
     if (cmd == "lazy") {
         int cnt; in >> cnt;
-        u64 acc[2 * L + 1];
-        zero_n<2 * L + 1>(acc);
+        u32 acc[F::WACC];
+        zero_n<F::WACC>(acc);
         for (int i = 0; i < cnt; i++) {
-            in >> t; parse_hex(t, a, L);
-            in >> t; parse_hex(t, b, L);
-            u64 tb[L];
+            in >> t; parse_hex(t, a, N);
+            in >> t; parse_hex(t, b, N);
+            u32 tb[N];
             F::to_dom(tb, b, fp);
             F::mac(acc, a, tb);
         }
         F::finish(r, acc, fp);
-        return to_hex(r, L);
+        return to_hex(r, N);
     }
     if (cmd == "small") {
         if (K == KIND_GENERIC) return "n/a";
         int cnt; in >> cnt;
-        u64 acc[L + 1];
-        in >> t; parse_hex(t, acc, L);
-        acc[L] = 0;
+        u32 acc[F::WSM];
+        in >> t; parse_hex(t, acc, N);
+        acc[N] = acc[N + 1] = 0;
         for (int i = 0; i < cnt; i++) {
-            u64 v;
-            in >> t; parse_hex(t, a, L);
-            in >> t; parse_hex(t, &v, 1);
-            mac_1<L, L + 1>(acc, a, v);
+            u32 v[2];
+            in >> t; parse_hex(t, a, N);
+            in >> t; parse_hex(t, v, 2);
+            F::mac_const(acc, a, (u64)v[0] | ((u64)v[1] << 32));
         }
-        if constexpr (K != KIND_GENERIC) F::template pm_reduce<L + 1>(r, acc, fp);
-        return to_hex(r, L);
+        if constexpr (K != KIND_GENERIC) F::template pm_reduce<F::WSM>(r, acc, fp);
+        return to_hex(r, N);
     }
     if (cmd == "redsmall") {
-        u64 x[L + 1];
-        in >> t; parse_hex(t, x, L + 1);
+        u32 x[N + 2];
+        in >> t; parse_hex(t, x, N + 2);
         F::reduce_small(r, x, fp);
-        return to_hex(r, L);
+        return to_hex(r, N);
     }
     if (cmd == "pow") {
+        u32 e32[16];
         u64 e[8];
-        in >> t; parse_hex(t, a, L);
-        in >> t; parse_hex(t, e, 8);
-        u64 x[L];
+        in >> t; parse_hex(t, a, N);
+        in >> t; parse_hex(t, e32, 16);
+        for (int i = 0; i < 8; i++) e[i] = get64(e32, i);
+        u32 x[N];
         F::to_dom(x, a, fp);
         F::dpow_uniform(x, x, e, bit_length(e, 8), fp);
         F::from_dom(r, x, fp);
-        std::string r1 = to_hex(r, L);
+        std::string r1 = to_hex(r, N);
         F::to_dom(x, a, fp);
         F::dpow(x, x, e, bit_length(e, 8), fp);
         F::from_dom(r, x, fp);
-        return r1 == to_hex(r, L) ? r1 : std::string("MISMATCH");
+        return r1 == to_hex(r, N) ? r1 : (std::string("MISMATCH:") + r1 + "/" + to_hex(r, N));
     }
     return "?";
 }
@@ -130,11 +134,13 @@ int main() {
         in >> cmd;
         if (cmd.empty()) continue;
         if (cmd == "field") {
-            u64 p[4];
-            in >> t; parse_hex(t, p, 4);
+            u32 p32[8];
+            in >> t; parse_hex(t, p32, 8);
+            uint64_t p[4];
+            for (int i = 0; i < 4; i++) p[i] = get64(p32, i);
             int n = 4;
             while (n > 1 && p[n - 1] == 0) n--;
-            field_params_init((const uint64_t*)p, n, &fp);
+            field_params_init(p, n, &fp);
             printf("%u %u %u\n", fp.kind, fp.L, fp.k);
             continue;
         }
