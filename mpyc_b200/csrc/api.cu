@@ -586,11 +586,29 @@ MPYC_API int mpyc_b200_shamir_split(const mpyc_b200_field* f, const void* d_secr
 }
 
 MPYC_API int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secrets, void* d_shares,
-                                               size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
-                                               uint64_t nonce, void* stream) {
-    (void)d_secrets; (void)d_shares; (void)share_stride; (void)n; (void)t; (void)m; (void)key32; (void)nonce; (void)stream;
-    if (!f) return fail(MPYC_B200_EINVAL, "field is null");
-    return fail(MPYC_B200_EUNSUPPORTED, "shamir_split_generate: not built in this revision");
+                                             size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
+                                             uint64_t nonce, void* stream) {
+    if (!f || !key32) return fail(MPYC_B200_EINVAL, "shamir_split_generate: null argument");
+    if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
+    REQUIRE_PRIME(f, "shamir_split_generate");
+    if (t > 4) return fail(MPYC_B200_EUNSUPPORTED, "shamir_split_generate: t <= 4 (use explicit coefficients beyond)");
+    if (n == 0) return MPYC_B200_OK;
+    if (!d_secrets || !d_shares || share_stride < n) return fail(MPYC_B200_EINVAL, "shamir_split_generate: bad buffers");
+    DevTable tab;
+    int rc = split_table(f, t, m, &tab);
+    if (rc) return rc;
+    if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "shamir_split: (m, t) table exceeds shared memory");
+    ChaChaKey key;
+    memcpy(key.k, key32, 32);
+    key.nonce[0] = (u32)nonce;
+    key.nonce[1] = (u32)(nonce >> 32) & 0x7FFFFFFFu;   // top bit separates the tail keystream
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::split_gen(f->fp, tab.full, key, (const u64*)d_secrets, (u64*)d_shares,
+                                                   share_stride * LL, n, t, m, tab.d, tab.bytes, st),
+                             "shamir_split_generate launch");
+    });
 }
 
 // ---------------------------------------------------------------------------------------

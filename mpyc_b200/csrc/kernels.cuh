@@ -223,15 +223,44 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 #define MPYC_REC_U2 2
 #endif
 
+// shares of one item (E elements) from its t+1 polynomial coefficient rows held in registers
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
+__device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], u64* shares,
+                                              size_t sstride, int m, const u64* tab, size_t limb_off) {
+    static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
+    constexpr int N = 2 * L;
+    typedef Fp<L, KIND> F;
+    for (int i = 0; i < m; i++) {
+        u32 r[E * N];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if constexpr (FULL) {
+                u32 acc[F::WACC];
+                zero_n<F::WACC>(acc);
+#pragma unroll
+                for (int j = 0; j < TP1; j++) F::mac(acc, M[j] + e * N, as32(tab + (size_t)(i * TP1 + j) * L));
+                F::finish(r + e * N, acc, f);
+            } else {
+                u32 acc[F::WSM];
+                copy_n<N>(acc, M[0] + e * N);
+                acc[N] = acc[N + 1] = 0;
+#pragma unroll
+                for (int j = 1; j < TP1; j++) F::mac_const(acc, M[j] + e * N, tab[i * TP1 + j]);
+                if constexpr (TP1 > 1) F::template pm_reduce<F::WSM>(r + e * N, acc, f);
+                else copy_n<N>(r + e * N, acc);
+            }
+        }
+        store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off, r);
+    }
+}
+
 // U items (item u at limb offset limb_off + u*limb_step) are processed together: every load is
 // issued before the first multiply so that U*(t+1) 16-byte requests per thread are in flight.
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, int U>
 __device__ __forceinline__ void split_items(const FieldParams& f, const u64* secrets, const u64* coeffs,
                                             size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
                                             size_t limb_off, size_t limb_step) {
-    static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
     constexpr int N = 2 * L;
-    typedef Fp<L, KIND> F;
     u32 M[U][TP1][E * N];
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -240,32 +269,9 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
 #pragma unroll
         for (int j = 1; j < TP1; j++) load_limbs<E * L, VEC>(M[u][j], coeffs + (size_t)(j - 1) * cstride + off);
     }
-    for (int i = 0; i < m; i++) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            u32 r[E * N];
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-                if constexpr (FULL) {
-                    u32 acc[F::WACC];
-                    zero_n<F::WACC>(acc);
-#pragma unroll
-                    for (int j = 0; j < TP1; j++)
-                        F::mac(acc, M[u][j] + e * N, as32(tab + (size_t)(i * TP1 + j) * L));
-                    F::finish(r + e * N, acc, f);
-                } else {
-                    u32 acc[F::WSM];
-                    copy_n<N>(acc, M[u][0] + e * N);
-                    acc[N] = acc[N + 1] = 0;
-#pragma unroll
-                    for (int j = 1; j < TP1; j++) F::mac_const(acc, M[u][j] + e * N, tab[i * TP1 + j]);
-                    if constexpr (TP1 > 1) F::template pm_reduce<F::WSM>(r + e * N, acc, f);
-                    else copy_n<N>(r + e * N, acc);
-                }
-            }
-            store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off + u * limb_step, r);
-        }
-    }
+    for (int u = 0; u < U; u++)
+        split_compute<L, KIND, TP1, FULL, E, VEC>(f, M[u], shares, sstride, m, tab, limb_off + u * limb_step);
 }
 
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
@@ -291,6 +297,107 @@ k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ 
         for (size_t h = n_items * E + tid; h < n; h += nth)
             split_items<L, KIND, TP1, FULL, 1, false, 1>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
                                                          h * (size_t)L, 0);
+    }
+}
+
+// ---- generate mode: coefficients come from a ChaCha20 keystream and never touch memory ----------
+// (the role of secrets.randbelow in thresha.py:58-60; 64 bits wider than p, then reduced: bias < 2^-64)
+
+struct ChaChaKey {
+    u32 k[8];
+    u32 nonce[2];
+};
+
+#ifndef MPYC_CHACHA_ROUNDS
+#define MPYC_CHACHA_ROUNDS 20
+#endif
+
+__device__ __forceinline__ void chacha_qr(u32& a, u32& b, u32& c, u32& d) {
+    a += b; d ^= a; d = __funnelshift_l(d, d, 16);
+    c += d; b ^= c; b = __funnelshift_l(b, b, 12);
+    a += b; d ^= a; d = __funnelshift_l(d, d, 8);
+    c += d; b ^= c; b = __funnelshift_l(b, b, 7);
+}
+
+__device__ __forceinline__ void chacha_block(u32* out, const ChaChaKey& key, u64 counter) {
+    u32 x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
+                 key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6], key.k[7],
+                 (u32)counter, (u32)(counter >> 32), key.nonce[0], key.nonce[1]};
+    u32 w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = x[i];
+#pragma unroll
+    for (int r = 0; r < MPYC_CHACHA_ROUNDS; r += 2) {
+        chacha_qr(w[0], w[4], w[8], w[12]);
+        chacha_qr(w[1], w[5], w[9], w[13]);
+        chacha_qr(w[2], w[6], w[10], w[14]);
+        chacha_qr(w[3], w[7], w[11], w[15]);
+        chacha_qr(w[0], w[5], w[10], w[15]);
+        chacha_qr(w[1], w[6], w[11], w[12]);
+        chacha_qr(w[2], w[7], w[8], w[13]);
+        chacha_qr(w[3], w[4], w[9], w[14]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = w[i] + x[i];
+}
+
+// coefficient slots per 16-word block: each coefficient takes N+2 words (rounded up to a power of two)
+template <int L>
+struct GenLayout {
+    static constexpr int SLOT = (2 * L + 2 <= 4) ? 4 : (2 * L + 2 <= 8 ? 8 : 16);
+    static constexpr int PER_BLOCK = 16 / SLOT;
+};
+
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
+__device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaChaKey& key, u64 counter0,
+                                               const u64* secrets, u64* shares, size_t sstride, int m,
+                                               const u64* tab, size_t limb_off) {
+    constexpr int N = 2 * L;
+    constexpr int NC = (TP1 - 1) * E;   // coefficients of this item
+    u32 M[TP1][E * N];
+    load_limbs<E * L, VEC>(M[0], secrets + limb_off);
+    u32 blk[16];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        if (c % GenLayout<L>::PER_BLOCK == 0) chacha_block(blk, key, counter0 + c / GenLayout<L>::PER_BLOCK);
+        u32 x[N + 2];
+#pragma unroll
+        for (int w = 0; w < N + 2; w++) x[w] = blk[(c % GenLayout<L>::PER_BLOCK) * GenLayout<L>::SLOT + w];
+        // keep bits(p)+64 bits so that x < 2^64 p (precondition of reduce_small)
+        const u32 keep = f.k + 64;
+#pragma unroll
+        for (int w = 0; w < N + 2; w++) {
+            const u32 lo = 32u * w;
+            if (lo >= keep) x[w] = 0;
+            else if (lo + 32 > keep) x[w] &= (1u << (keep - lo)) - 1;
+        }
+        const int j = 1 + c / E, e = c % E;
+        Fp<L, KIND>::reduce_small(M[j] + e * N, x, f);
+    }
+    split_compute<L, KIND, TP1, FULL, E, VEC>(f, M, shares, sstride, m, tab, limb_off);
+}
+
+template <int L, int KIND, int TP1, bool FULL, bool VEC>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, u64* __restrict__ shares, size_t sstride,
+            size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
+    extern __shared__ __align__(16) u64 stab[];
+    __shared__ __align__(8) u64 mbar;
+    tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    constexpr int BPI = ((TP1 - 1) * E + GenLayout<L>::PER_BLOCK - 1) / GenLayout<L>::PER_BLOCK;   // blocks per item
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
+    for (size_t it = tid; it < n_items; it += nth)
+        split_gen_item<L, KIND, TP1, FULL, E, VEC>(f, key, (u64)it * BPI, secrets, shares, sstride, m, stab,
+                                                   it * (size_t)(E * L));
+    if constexpr (E > 1) {
+        ChaChaKey tail = key;
+        tail.nonce[1] ^= 0x80000000u;   // disjoint keystream for the scalar tail
+        for (size_t h = n_items * E + tid; h < n; h += nth)
+            split_gen_item<L, KIND, TP1, FULL, 1, false>(f, tail, (u64)h * BPI, secrets, shares, sstride, m, stab,
+                                                         h * (size_t)L);
     }
 }
 

@@ -166,6 +166,61 @@ cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secret
 #undef GO
 }
 
+// ---- split, generate mode (t <= 4) -----------------------------------------------------------------
+
+template <int L, int KIND, bool FULL, bool VEC>
+static cudaError_t split_gen_k(const FieldParams& fp, const ChaChaKey& key, const u64* secrets, u64* shares,
+                               size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    size_t items = (n + E - 1) / E;
+#define GEN_CASE(T)                                                                                                 \
+    case T:                                                                                                         \
+        return launch_kernel(k_split_gen<L, KIND, T, FULL, VEC>, items, tab_bytes, st, fp, key, secrets, shares,    \
+                             sstride, n, m, gtab, tab_bytes)
+    switch (t + 1) {
+        GEN_CASE(1);
+        GEN_CASE(2);
+        GEN_CASE(3);
+        GEN_CASE(4);
+        GEN_CASE(5);
+        default: break;
+    }
+#undef GEN_CASE
+    return cudaErrorNotSupported;
+}
+
+template <int L>
+cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets, u64* shares,
+                                 size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+    const bool vec = aligned16(secrets) && aligned16(shares) && ((sstride * L) % 2 == 0);
+    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
+#define GEN_GO(V)                                                                                                  \
+    do {                                                                                                           \
+        if (full) {                                                                                                \
+            switch (fp.kind) {                                                                                     \
+                case KIND_GENERIC: return split_gen_k<L, KIND_GENERIC, true, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+                case KIND_PM_ALIGNED: return split_gen_k<L, KIND_PM_ALIGNED, true, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+                case KIND_PM_SHIFT: return split_gen_k<L, KIND_PM_SHIFT, true, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+            }                                                                                                      \
+            return cudaErrorInvalidValue;                                                                          \
+        }                                                                                                          \
+        if (fp.kind == KIND_PM_ALIGNED)                                                                            \
+            return split_gen_k<L, KIND_PM_ALIGNED, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+        if (fp.kind == KIND_PM_SHIFT)                                                                              \
+            return split_gen_k<L, KIND_PM_SHIFT, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+        return cudaErrorInvalidValue;                                                                              \
+    } while (0)
+    if constexpr (L % 2 == 0) {
+        GEN_GO(true);
+    } else if constexpr (L == 1) {
+        if (vec) GEN_GO(true);
+        GEN_GO(false);
+    } else {
+        GEN_GO(false);   // L == 3: scalar-limb path (keeps the binary small)
+    }
+#undef GEN_GO
+}
+
 // ---- recombine ------------------------------------------------------------------------------
 
 template <int L>

@@ -272,3 +272,22 @@ def shamir_recombine(ctx, xs, rows, x_rs=0, out=None):
                                          _cabi.i64_array([int(x) for x in pts]), len(pts), out.ptr, out.stride, n,
                                          _stream_ptr()))
     return out.row(0) if single else out
+
+
+def shamir_split_generate(ctx, secrets: DeviceArray, t, m, key=None, nonce=0, out=None):
+    """Share generation with coefficients drawn INSIDE the kernel from a ChaCha20 keystream (never written
+    to memory).  key: 32 bytes of fresh CSPRNG output (default: os.urandom(32)); nonce: 63-bit call counter.
+    The role of secrets.randbelow in mpyc/thresha.py:58-60; not bit-reproducible against anything unless the
+    key is fixed (tests do that)."""
+    import os
+    key = os.urandom(32) if key is None else bytes(key)
+    if len(key) != 32:
+        raise ValueError('key must be 32 bytes')
+    n = secrets.n
+    secrets._check_contiguous()
+    if out is None:
+        out = DeviceMatrix.empty(ctx, m, n, secrets.t.device)
+    kbuf = (ctypes.c_uint8 * 32).from_buffer_copy(key)
+    check(lib.mpyc_b200_shamir_split_generate(ctx.handle, secrets.ptr, out.ptr, out.stride, n, t, m, kbuf,
+                                              int(nonce) & (2**63 - 1), _stream_ptr()))
+    return out

@@ -319,3 +319,89 @@ def test_error_behaviour():
     with pytest.raises(mpyc_b200.UnsupportedFieldError):
         mpyc_b200.context_for(2)
     assert mpyc_b200.launch_count() > 0
+
+
+# ---- generate mode (coefficients from a ChaCha20 keystream inside the kernel) ---------------------------
+
+def _chacha20_block(key, counter, nonce0, nonce1):
+    """Reference ChaCha20 block function (RFC 8439 section 2.3 arithmetic; 64-bit counter layout)."""
+    def rotl(v, c):
+        return ((v << c) & 0xffffffff) | (v >> (32 - c))
+
+    def qr(x, a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & 0xffffffff; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & 0xffffffff; x[b] = rotl(x[b] ^ x[c], 7)
+    init = [0x61707865, 0x3320646e, 0x79622d32, 0x6b206574] + [int.from_bytes(key[4 * i:4 * i + 4], 'little') for i in range(8)] \
+        + [counter & 0xffffffff, counter >> 32, nonce0, nonce1]
+    x = list(init)
+    for _ in range(10):
+        qr(x, 0, 4, 8, 12); qr(x, 1, 5, 9, 13); qr(x, 2, 6, 10, 14); qr(x, 3, 7, 11, 15)
+        qr(x, 0, 5, 10, 15); qr(x, 1, 6, 11, 12); qr(x, 2, 7, 8, 13); qr(x, 3, 4, 9, 14)
+    return [(a + b) & 0xffffffff for a, b in zip(x, init)]
+
+
+def test_chacha_reference_block_matches_rfc8439():
+    key = bytes(range(32))
+    # RFC 8439 2.3.2: counter = 1, nonce = 00:00:00:09:00:00:00:4a:00:00:00:00
+    out = _chacha20_block(key, 1 | (0x09000000 << 32), 0x4a000000, 0)
+    assert out[:4] == [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3]
+    assert out[12:] == [0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
+
+
+@pytest.mark.parametrize('p', [P64, P61, P128, P69, P256, P64G, GEN['128'], 2**192 - 237], ids=lambda p: f'p{p.bit_length()}_{p & 0xffff:x}')
+def test_generate_mode_uses_chacha20_keystream(p):
+    """Known-answer: with t=1 the coefficient of X is share_2 - share_1; it must equal the ChaCha20
+    keystream words (64 bits wider than p) reduced mod p, for the documented counter layout."""
+    ctx = mpyc_b200.context_for(p)
+    L = ctx.nlimbs
+    n = 37
+    key = bytes((7 * i + 3) & 0xFF for i in range(32))
+    nonce = 0x1234567_89ABCDEF
+    s = (orc.edge_block(p) + orc.synth_elements(p, n, 3))[:n]
+    S = DeviceArray.from_ints(ctx, s)
+    sh = dev.shamir_split_generate(ctx, S, 1, 3, key=key, nonce=nonce).to_ints()
+    coef = [(int(b) - int(a)) % p for a, b in zip(sh[0], sh[1])]
+    words = 2 * L + 2
+    slot = 4 if words <= 4 else (8 if words <= 8 else 16)
+    per_block = 16 // slot
+    E = 2 if (L == 1) else 1          # vector items of 1-limb fields hold two elements (L == 3: scalar path)
+    bpi = (E + per_block - 1) // per_block
+    keep = (1 << (p.bit_length() + 64)) - 1
+    n_items = n // E
+    for h in range(n):
+        if h < n_items * E:
+            it, c = divmod(h, E)
+            blk = _chacha20_block(key, it * bpi + c // per_block, nonce & 0xffffffff, (nonce >> 32) & 0x7fffffff)
+            off = (c % per_block) * slot
+        else:   # scalar tail: disjoint keystream (top nonce bit set), one element per item
+            blk = _chacha20_block(key, h * ((1 + per_block - 1) // per_block), nonce & 0xffffffff, ((nonce >> 32) & 0x7fffffff) | 0x80000000)
+            off = 0
+        x = sum(w << (32 * i) for i, w in enumerate(blk[off:off + words]))
+        assert coef[h] == (x & keep) % p, h
+    # shares are a valid degree-1 sharing of the secrets
+    F = orc.field_of(p)
+    assert orc.recombine(F, [2, 3], [[int(v) for v in sh[1]], [int(v) for v in sh[2]]]) == s
+
+
+@pytest.mark.parametrize('p,m,t,n', [(P64, 3, 1, 1_000_003), (P128, 5, 2, 500_000), (P256, 7, 3, 100_001), (P64G, 5, 2, 200_000), (P69, 9, 4, 50_001)])
+def test_generate_mode_properties(p, m, t, n):
+    ctx = mpyc_b200.context_for(p)
+    S = DeviceArray.random(ctx, n, seed=5, stream_id=9)
+    key = bytes(range(32))
+    sh = dev.shamir_split_generate(ctx, S, t, m, key=key, nonce=1)
+    for xs in ([1 + i for i in range(t + 1)], [m - i for i in range(t + 1)]):
+        assert dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs]).count_mismatch(S) == 0
+    sh_same = dev.shamir_split_generate(ctx, S, t, m, key=key, nonce=1)
+    sh_other = dev.shamir_split_generate(ctx, S, t, m, key=key, nonce=2)
+    sh_fresh = dev.shamir_split_generate(ctx, S, t, m)      # OS randomness
+    assert all(sh.row(i).count_mismatch(sh_same.row(i)) == 0 for i in range(m))
+    assert sh.row(0).count_mismatch(sh_other.row(0)) > n - 10
+    assert sh.row(0).count_mismatch(sh_fresh.row(0)) > n - 10
+    # fewer than t+1 shares do not determine the secrets: recombining t shares gives something else
+    if t >= 1:
+        xs = list(range(1, t + 1))
+        assert dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs]).count_mismatch(S) > n - 10
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):
+        dev.shamir_split_generate(ctx, S, 5, 11)

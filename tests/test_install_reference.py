@@ -1,0 +1,75 @@
+"""install() against the REAL reference (only where /root/reference exists, i.e. the build container):
+attribute swap, pass-through for fields the engine does not cover, host-only helpers equal to the
+reference's, and no silent CPU computation for covered fields."""
+import os
+import sys
+
+import pytest
+
+REF = os.environ.get('MPYC_REFERENCE', '/root/reference')
+if not os.path.isdir(os.path.join(REF, 'mpyc')):
+    pytest.skip('reference checkout not present', allow_module_level=True)
+
+
+@pytest.fixture(scope='module')
+def mpyc_thresha():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    argv, sys.argv = sys.argv, [sys.argv[0], '--no-log']
+    try:
+        from mpyc import thresha, finfields, gfpx
+    finally:
+        sys.argv = argv
+    yield thresha, finfields, gfpx
+    sys.path.remove(REF)
+
+
+def test_install_swaps_and_restores(mpyc_thresha):
+    thresha, finfields, gfpx = mpyc_thresha
+    from mpyc_b200 import install as inst
+    orig = {n: getattr(thresha, n) for n in inst._NAMES}
+    names = inst.install(thresha)
+    assert set(names) == set(inst._NAMES)
+    assert all(getattr(getattr(thresha, n), '__mpyc_b200__', False) for n in names)
+    inst.uninstall()
+    assert all(getattr(thresha, n) is orig[n] for n in names)
+
+
+def test_host_helpers_equal_reference_and_uncovered_fields_pass_through(mpyc_thresha):
+    thresha, finfields, gfpx = mpyc_thresha
+    from mpyc_b200 import install as inst
+    ref_rv, ref_fsi = thresha._recombination_vector, thresha._f_S_i
+    fields = [finfields.GF(p) for p in (19, 101, 2**61 - 1, 2**64 - 189, 2**69 - 93, 2**128 - 173, 2**256 - 189,
+                                         9409569905028393239)]
+    f256 = finfields.GF(gfpx.GFpX(2)(283))
+    from itertools import combinations
+    cases_rv = [(F, xs, x_r) for F in fields + [f256]
+                for xs in ((1,), (1, 2, 3), (2, 3, 5), (1, 2, 3, 4, 5, 6, 7), tuple(range(1, 18))) for x_r in (0, 1, 18)
+                if not (F.order == 19 and (len(xs) > 16 or x_r == 18))]
+    cases_fs = [(F, m, i, S) for F in fields + [f256] for m, t in ((3, 1), (5, 2), (7, 3))
+                for S in combinations(range(m), m - t) for i in S]
+    want_rv = [ref_rv(F, xs, x_r) for F, xs, x_r in cases_rv]      # the unmodified reference, before install()
+    want_fs = [ref_fsi(F, m, i, S) for F, m, i, S in cases_fs]
+    inst.install(thresha)
+    try:
+        for (F, xs, x_r), want in zip(cases_rv, want_rv):
+            assert thresha._recombination_vector(F, xs, x_r) == want
+        for (F, m, i, S), want in zip(cases_fs, want_fs):
+            got = thresha._f_S_i(F, m, i, S)
+            if F is f256:
+                assert got == want
+            else:
+                assert got % F.modulus == want % F.modulus
+        # fields the engine does not cover run on the reference's own code, unchanged
+        f2, f27 = finfields.GF(2), finfields.GF(gfpx.GFpX(3)(46))
+        for F in (f2, f27):
+            a = [F(0), F(1), F(1)]
+            sh = thresha.random_split(F, a, 1, 3) if F is f27 else thresha.random_split(F, a, 0, 1)
+            assert a == thresha.recombine(F, [(j + 1, sh[j]) for j in range(len(sh))])   # order as in tests/test_thresha.py:21
+        # covered field, no GPU here: the call must fail loudly, never compute on the CPU
+        import torch
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError):
+                thresha.random_split(fields[2], [1, 2, 3], 1, 3)
+    finally:
+        inst.uninstall()
