@@ -129,30 +129,56 @@ def cpu_baseline(w, n=20000, target_s=12.0):
                       f'on {n} elements x {reps} reps, 1 process', 'value_without_rng': pairs2 / dt2}
 
 
+_REF = {}
+
+
+def _ref_init(p, m, t, k, n):
+    """Pool initializer: every worker builds its inputs once (outside the timed steps)."""
+    import numpy as np
+    from oracle import shamir_oracle as orc
+    _REF.update(p=p, m=m, t=t, k=k, n=n, s=np.array(orc.synth_elements(p, n, 20260923 + os.getpid() % 1000), dtype=object))
+
+
+def _ref_step(_):
+    """One worker's share of a step: draw coefficients as the reference does, split, recombine t+1 shares."""
+    import secrets
+    from oracle import shamir_oracle as orc
+    r = _REF
+    C = orc.np_draw_coefficients(r['p'], r['t'], r['n'], secrets.randbelow)
+    sh = orc.np_split(r['p'], r['s'], C, r['m'])
+    out = orc.np_recombine(r['p'], tuple(range(1, r['k'] + 1)), sh[:r['k']])
+    assert out[0] == r['s'][0]
+    return r['n']
+
+
 def run_reference_arm(a, w):
+    """CPU arm: the oracle port of thresha.np_random_split + np_recombine (NumPy object arrays, per-element
+    secrets.randbelow -- the reference's own code path) on all host cores, one independent process per core.
+    The reference is pure Python and cannot travel to the GPU box, hence kind = 'port'."""
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = 4000
-    times = []
-    with mp.get_context('fork').Pool(cores) as pool:
+    n = 20000
+    done = []
+    with mp.get_context('fork').Pool(cores, initializer=_ref_init, initargs=(w['p'], w['m'], w['t'], w['k'], n)) as pool:
+        pool.map(_ref_step, range(cores))          # make sure every worker is up before timing
         for step in range(a.warmup + a.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_pairs, [(w['p'], w['m'], w['t'], w['k'], n, 1, True)] * cores)
+            res = pool.map(_ref_step, range(cores), chunksize=1)
             dt = time.perf_counter() - t0
             if step >= a.warmup:
-                times.append((sum(r[0] for r in res), dt))
-    pairs = sum(x for x, _ in times)
-    dt = sum(y for _, y in times)
+                done.append((sum(res), dt))
+    pairs = sum(x for x, _ in done)
+    dt = sum(y for _, y in done)
     val = pairs / dt
+    sample = f'{cores} independent processes x {n} pairs per step (oracle port of thresha.np_random_split+np_recombine incl. secrets.randbelow)'
     line = {'metric': METRIC, 'impl': 'reference', 'value': val, 'unit': 'pairs/s', 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': 1e3 * dt / max(a.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'python-int (exact)', 'data': 'synthetic',
             'config': {'workload': w['name'], 'sample_per_step': f'{n} pairs x {cores} processes'},
-            'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{cores} independent processes x {n} pairs per step (oracle port of thresha.np_random_split+np_recombine)'},
+            'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -235,6 +261,10 @@ def run_gpu_arm(a, w):
     if world > 1:
         dist.barrier()
     launches = mpyc_b200.launch_count() - launches0
+    if world > 1:   # whole-job count
+        tl = torch.tensor([launches], device='cuda', dtype=torch.int64)
+        dist.all_reduce(tl)
+        launches = int(tl.item())
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     split_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(a.steps)) / a.steps

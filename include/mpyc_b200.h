@@ -102,6 +102,12 @@ int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int inverse, vo
 int mpyc_b200_ff_is_sqr(const mpyc_b200_field* f, const void* d_a, uint8_t* d_out_u8, size_t n,
                         void* stream);
 
+/* FiniteFieldArray.__matmul__ (mpyc/finfields.py:1126-1146; np_matmul's local step, runtime.py:2531):
+ * C[r x c] = A[r x k] @ B[k x c] mod p, all row-major and contiguous.  Exact big-int semantics: the k
+ * products are accumulated unreduced and reduced once, like `(a @ b) % p`. */
+int mpyc_b200_ff_matmul(const mpyc_b200_field* f, const void* d_a, const void* d_b, void* d_c,
+                        size_t r, size_t k, size_t c, void* stream);
+
 /* ---- Shamir share generation ---------------------------------------------------------------
  * thresha.np_random_split (mpyc/thresha.py:47-64) with the coefficient matrix C given explicitly:
  *   shares[i][h] = sum_{j=0..t} (i+1)^j * M[j][h] mod p,   M[0] = secrets, M[j] = coeffs row j-1

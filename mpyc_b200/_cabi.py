@@ -58,6 +58,7 @@ _SIGNATURES = {
     'mpyc_b200_ff_inv': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_ff_sqrt': (c_int, [_field_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_ff_is_sqr': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_matmul': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     'mpyc_b200_shamir_split': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,
                                        c_int, c_int, c_void_p]),
     'mpyc_b200_shamir_split_generate': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,

@@ -545,6 +545,22 @@ MPYC_API int mpyc_b200_ff_is_sqr(const mpyc_b200_field* f, const void* d_a, uint
     return pow_impl(f, d_a, e, 4, 1, false, nullptr, d_out_u8, n, st);
 }
 
+MPYC_API int mpyc_b200_ff_matmul(const mpyc_b200_field* f, const void* d_a, const void* d_b, void* d_c, size_t r,
+                                 size_t k, size_t c, void* stream) {
+    if (!f) return fail(MPYC_B200_EINVAL, "ff_matmul: field is null");
+    if (r == 0 || c == 0) return MPYC_B200_OK;
+    if (!d_c || (k && (!d_a || !d_b))) return fail(MPYC_B200_EINVAL, "ff_matmul: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->kind == MPYC_B200_KIND_GF256)
+        return launch_status(gf256_matmul(f->gf_poly, (const unsigned char*)d_a, (const unsigned char*)d_b,
+                                          (unsigned char*)d_c, r, k, c, st), "gf256 matmul");
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::matmul(f->fp, (const u64*)d_a, (const u64*)d_b, (u64*)d_c, r, k, c, st),
+                             "ff_matmul launch");
+    });
+}
+
 // ---------------------------------------------------------------------------------------
 // Shamir split
 // ---------------------------------------------------------------------------------------

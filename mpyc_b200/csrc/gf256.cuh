@@ -195,6 +195,19 @@ k_gf_mismatch(const unsigned char* __restrict__ a, const unsigned char* __restri
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
+// ---- matmul: C[r x c] = A[r x k] @ B[k x c] over GF(2^8), one thread per output element -----------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_matmul(unsigned poly, const unsigned char* __restrict__ A, const unsigned char* __restrict__ B,
+            unsigned char* __restrict__ C, size_t r, size_t k, size_t c) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < r * c; o += nth) {
+        const size_t i = o / c, j = o % c;
+        unsigned acc = 0;
+        for (size_t l = 0; l < k; l++) acc ^= gf_mul1(A[i * k + l], B[l * c + j], poly);
+        C[o] = (unsigned char)acc;
+    }
+}
+
 // ---- host wrappers ---------------------------------------------------------------------------------
 
 #define GF_LAUNCH(kernel, items, st, ...)                                                   \
@@ -267,4 +280,8 @@ static inline cudaError_t gf256_fill(unsigned long long base, unsigned char* out
 static inline cudaError_t gf256_mismatch(const unsigned char* a, const unsigned char* b, size_t n, unsigned long long* count,
                                          cudaStream_t st) {
     GF_LAUNCH(k_gf_mismatch, n, st, a, b, n, count);
+}
+static inline cudaError_t gf256_matmul(unsigned poly, const unsigned char* A, const unsigned char* B, unsigned char* C,
+                                       size_t r, size_t k, size_t c, cudaStream_t st) {
+    GF_LAUNCH(k_gf_matmul, r * c, st, poly, A, B, C, r, k, c);
 }

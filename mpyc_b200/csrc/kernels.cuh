@@ -563,6 +563,89 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 }
 
 // ---------------------------------------------------------------------------------------
+// K1c: modular matrix product C[r x c] = A[r x k] @ B[k x c] mod p (finfields.py:1126-1146; the
+// np_matmul inner step, runtime.py:2531).  Integer work on the IMAD pipe -- no tensor cores for
+// >= 64-bit moduli.  One thread owns one output column for TM consecutive rows: B[l][j] is read
+// coalesced once per row tile, the A tile is staged in shared memory and broadcast; the k products
+// of a dot product are accumulated lazily and reduced once (every 2^20 terms for huge k).
+// GENERIC fields: A is converted to table form while it is staged, so REDC divides R' back out.
+// ---------------------------------------------------------------------------------------
+
+#define MPYC_MM_KT 64   // k-chunk of the A tile held in shared memory
+
+template <int L, int KIND, int TM>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_matmul(FieldParams f, const u64* __restrict__ A, const u64* __restrict__ B, u64* __restrict__ C, size_t r, size_t k,
+         size_t c) {
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    __shared__ u32 sA[TM][MPYC_MM_KT][N];
+    const size_t col_tiles = (c + MPYC_THREADS - 1) / MPYC_THREADS;
+    const size_t row_tiles = (r + TM - 1) / TM;
+    for (size_t tile = blockIdx.x; tile < col_tiles * row_tiles; tile += gridDim.x) {
+        const size_t i0 = (tile / col_tiles) * TM;
+        const size_t j = (tile % col_tiles) * MPYC_THREADS + threadIdx.x;
+        u32 acc[TM][F::WACC];
+        u32 partial[TM][N];
+#pragma unroll
+        for (int a = 0; a < TM; a++) {
+            zero_n<F::WACC>(acc[a]);
+            zero_n<N>(partial[a]);
+        }
+        u32 lazy = 0;
+        for (size_t l0 = 0; l0 < k; l0 += MPYC_MM_KT) {
+            const int kt = (int)min((size_t)MPYC_MM_KT, k - l0);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < TM * kt; idx += MPYC_THREADS) {
+                const int a = idx / kt, l = idx % kt;
+                u32 x[N];
+                if (i0 + a < r) load_limbs<L, false>(x, A + ((i0 + a) * k + l0 + l) * L);
+                else zero_n<N>(x);
+                F::to_dom(x, x, f);
+#pragma unroll
+                for (int w = 0; w < N; w++) sA[a][l][w] = x[w];
+            }
+            __syncthreads();
+            if (j < c) {
+                for (int l = 0; l < kt; l++) {
+                    u32 b[N];
+                    load_limbs<L, false>(b, B + ((l0 + l) * c + j) * L);
+#pragma unroll
+                    for (int a = 0; a < TM; a++) {
+                        u32 av[N];
+#pragma unroll
+                        for (int w = 0; w < N; w++) av[w] = sA[a][l][w];
+                        F::mac(acc[a], b, av);
+                    }
+                }
+            }
+            lazy += kt;
+            if (lazy + MPYC_MM_KT > FF_MAX_LAZY_TERMS) {   // fold the lazy sums before they can overflow
+#pragma unroll
+                for (int a = 0; a < TM; a++) {
+                    u32 t[N];
+                    F::finish(t, acc[a], f);
+                    F::add(partial[a], partial[a], t, f);
+                    zero_n<F::WACC>(acc[a]);
+                }
+                lazy = 0;
+            }
+        }
+        if (j < c) {
+#pragma unroll
+            for (int a = 0; a < TM; a++) {
+                if (i0 + a < r) {
+                    u32 t[N];
+                    F::finish(t, acc[a], f);
+                    F::add(t, t, partial[a], f);
+                    store_limbs<L, false>(C + ((i0 + a) * c + j) * L, t);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // utilities
 // ---------------------------------------------------------------------------------------
 

@@ -28,6 +28,8 @@ struct Launch {
     static cudaError_t prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                             int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                             cudaStream_t st);
+    static cudaError_t matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,
+                              cudaStream_t st);
     static cudaError_t fill_random(const FieldParams& fp, u64* out, size_t n, u64 base, cudaStream_t st);
 };
 

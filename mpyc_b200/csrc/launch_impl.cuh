@@ -265,3 +265,21 @@ cudaError_t Launch<L>::fill_random(const FieldParams& fp, u64* out, size_t n, u6
 #undef M
     return cudaErrorInvalidValue;
 }
+
+template <int L>
+cudaError_t Launch<L>::matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,
+                              cudaStream_t st) {
+    const size_t col_tiles = (c + MPYC_THREADS - 1) / MPYC_THREADS;
+    // TM rows per thread: 4 when there are enough rows, else 1 (vector-matrix products)
+    if (r >= 4) {
+        const size_t tiles = col_tiles * ((r + 3) / 4);
+#define M(K) return launch_kernel(k_matmul<L, K, 4>, tiles * MPYC_THREADS, 0, st, fp, A, B, C, r, k, c)
+        KIND_SWITCH(fp.kind, M)
+#undef M
+    }
+    const size_t tiles = col_tiles * r;
+#define M(K) return launch_kernel(k_matmul<L, K, 1>, tiles * MPYC_THREADS, 0, st, fp, A, B, C, r, k, c)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}

@@ -291,3 +291,15 @@ def shamir_split_generate(ctx, secrets: DeviceArray, t, m, key=None, nonce=0, ou
     check(lib.mpyc_b200_shamir_split_generate(ctx.handle, secrets.ptr, out.ptr, out.stride, n, t, m, kbuf,
                                               int(nonce) & (2**63 - 1), _stream_ptr()))
     return out
+
+
+def matmul(ctx, A, B, r, k, c):
+    """C = A @ B mod p for row-major DeviceArrays A (r*k elements) and B (k*c elements): DeviceArray of r*c
+    elements (FiniteFieldArray.__matmul__, mpyc/finfields.py:1126-1146)."""
+    if A.n != r * k or B.n != k * c:
+        raise ValueError('matmul: shapes do not match the buffers')
+    A._check_contiguous()
+    B._check_contiguous()
+    out = DeviceArray.empty(ctx, r * c, A.t.device)
+    check(lib.mpyc_b200_ff_matmul(ctx.handle, A.ptr, B.ptr, out.ptr, r, k, c, _stream_ptr()))
+    return out

@@ -405,3 +405,47 @@ def test_generate_mode_properties(p, m, t, n):
         assert dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs]).count_mismatch(S) > n - 10
     with pytest.raises(mpyc_b200.UnsupportedFieldError):
         dev.shamir_split_generate(ctx, S, 5, 11)
+
+
+# ---- modular matmul (finfields.py:1126-1146) -----------------------------------------------------------
+
+@pytest.mark.parametrize('case', FF['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_{c['p'][-4:]}")
+def test_golden_matmul(case):
+    p = int(case['p'], 16)
+    ctx = mpyc_b200.context_for(p)
+    a, b = unhex(case['a']), unhex(case['b'])
+    A, B = DeviceArray.from_ints(ctx, a[:12]), DeviceArray.from_ints(ctx, b[:20])
+    got = dev.matmul(ctx, A, B, 3, 4, 5).to_ints().tolist()
+    want = unhex(case['matmul_3x4_4x5'])
+    assert got == [v for row in want for v in row]
+
+
+@pytest.mark.parametrize('p', [P61, P64, P64G, P69, P128, GEN['128'], 2**192 - 237, P256, GEN['256'], 101], ids=lambda p: f'p{p.bit_length()}_{p & 0xffff:x}')
+@pytest.mark.parametrize('shape', [(1, 1, 1), (1, 3136, 300), (5, 70, 257), (9, 64, 3), (2, 129, 600), (4, 0, 3)])
+def test_matmul_vs_oracle(p, shape):
+    r, k, c = shape
+    ctx = mpyc_b200.context_for(p)
+    a = (orc.edge_block(p) * (r * k // 8 + 1))[:r * k // 2] + orc.synth_elements(p, r * k - r * k // 2, 21)
+    b = orc.synth_elements(p, k * c - min(k * c, 8), 22) + orc.edge_block(p)[:min(k * c, 8)]
+    A = DeviceArray.from_ints(ctx, a) if a else DeviceArray.empty(ctx, 0)
+    B = DeviceArray.from_ints(ctx, b) if b else DeviceArray.empty(ctx, 0)
+    got = dev.matmul(ctx, A, B, r, k, c).to_ints().tolist()
+    Am = [a[i * k:(i + 1) * k] for i in range(r)]
+    Bm = [b[l * c:(l + 1) * c] for l in range(k)]
+    want = [[sum(Am[i][l] * Bm[l][j] for l in range(k)) % p for j in range(c)] for i in range(r)]
+    assert got == [v for row in want for v in row]
+
+
+def test_gf256_matmul():
+    f = G256['modulus']
+    ctx = mpyc_b200.context_for(f, binary=True)
+    tab = np.frombuffer(bytes.fromhex(G256['mul_table_hex']), dtype=np.uint8).reshape(256, 256)
+    rng = np.random.default_rng(3)
+    r, k, c = 4, 16, 33
+    a = rng.integers(0, 256, size=(r, k), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(k, c), dtype=np.uint8)
+    want = np.zeros((r, c), dtype=np.uint8)
+    for l in range(k):
+        want ^= tab[a[:, l][:, None], b[l][None, :]]
+    got = dev.matmul(ctx, DeviceArray.from_limbs(ctx, a.reshape(-1)), DeviceArray.from_limbs(ctx, b.reshape(-1)), r, k, c)
+    assert np.array_equal(got.to_limbs().reshape(r, c), want)
