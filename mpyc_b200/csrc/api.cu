@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -654,6 +655,40 @@ static int recombine_table(const mpyc_b200_field* cf, const int64_t* xs, int k, 
         full = true;
         int rc = compute_lambda(f->fp, xs, k, x_rs, width, host);
         if (rc) return rc;
+        // signed-magnitude form: |lambda| < 2^58 for every entry (e.g. x-coordinates 1..k at 0:
+        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (pseudo-Mersenne fields, k <= 32)
+        if (f->fp.kind != KIND_GENERIC && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
+            const int L = (int)f->fp.L;
+            std::vector<u64> sm((size_t)width * k * 2);
+            bool ok = true;
+            for (size_t e = 0; e < (size_t)width * k && ok; e++) {
+                const u64* lam = &host[e * L];
+                bool small_pos = lam[0] < (1ull << 58);
+                for (int l = 1; l < L; l++) small_pos = small_pos && lam[l] == 0;
+                if (small_pos) {
+                    sm[2 * e] = lam[0];
+                    sm[2 * e + 1] = 0;
+                    continue;
+                }
+                u64 neg[4];   // p - lambda
+                unsigned __int128 bw = 0;
+                for (int l = 0; l < L; l++) {
+                    unsigned __int128 d = (unsigned __int128)f->fp.p[l] - lam[l] - (u64)bw;
+                    neg[l] = (u64)d;
+                    bw = (d >> 64) & 1;
+                }
+                bool small_neg = neg[0] < (1ull << 58);
+                for (int l = 1; l < L; l++) small_neg = small_neg && neg[l] == 0;
+                if (!small_neg) ok = false;
+                sm[2 * e] = neg[0];
+                sm[2 * e + 1] = 1;
+            }
+            if (ok) {
+                host.swap(sm);
+                full = false;
+                return MPYC_B200_OK;
+            }
+        }
         to_table_form(f->fp, host);
         return MPYC_B200_OK;
     });
@@ -686,7 +721,7 @@ MPYC_API int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* co
     for (int i = 0; i < k; i++) rows.p[i] = (const u64*)d_share_rows[i];
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        return launch_status(Launch<LL>::recombine(f->fp, rows, k, width, tab.d, tab.bytes, (u64*)d_out, out_stride * LL, n, st),
+        return launch_status(Launch<LL>::recombine(f->fp, !tab.full, rows, k, width, tab.d, tab.bytes, (u64*)d_out, out_stride * LL, n, st),
                              "shamir_recombine launch");
     });
 }

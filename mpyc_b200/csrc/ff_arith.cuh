@@ -277,7 +277,24 @@ struct Fp {
         // number of 32-bit limbs of the part above the fold point that can be non-zero
         constexpr int HM = (W == N + 2) ? 2 : (W == 2 * N ? N : N + 1);
         u32 r1[N + 2];
-        if constexpr (KIND == KIND_PM_ALIGNED) {
+        if constexpr (KIND == KIND_PM_ALIGNED && W == N + 2 && L >= 2) {
+            // (L+1)-limb sum of 64-bit-constant products: the limb above the fold point times c is
+            // < 2^80 and fits the element width, so one pass suffices: r = lo + top*c (+ c on carry).
+            const u64 t0 = (u64)x[N] * c, t1 = (u64)x[N + 1] * c;
+            const u64 a = t0 + (t1 << 32);
+            u32 uu[N];
+            zero_n<N>(uu);
+            uu[0] = (u32)a;
+            uu[1] = (u32)(a >> 32);
+            uu[2] = (u32)(t1 >> 32) + (a < t0 ? 1u : 0u);
+            u32 cy = add_n<N>(r, x, uu);
+            if (cy) {                                    // 2^(64L) = c (mod p); cannot carry again.  Rare.
+                zero_n<N>(uu);
+                uu[0] = c;
+                add_n<N>(r, r, uu);
+            }
+            csub(r, 0, f);
+        } else if constexpr (KIND == KIND_PM_ALIGNED) {
             copy_n<N>(r1, x);
             r1[N] = r1[N + 1] = 0;
             mac_small<HM, N + 2>(r1, x + N, c);

@@ -476,6 +476,89 @@ __device__ __forceinline__ void recombine_items(const FieldParams& f, const RowP
     }
 }
 
+// Small-coefficient form (pseudo-Mersenne fields): when every lambda has a signed representative of
+// magnitude < 2^58 -- always the case for x-coordinates 1..k at 0, where lambda_i = (-1)^(i-1) C(k,i),
+// e.g. the 2t+1 = m shares of a resharing (runtime.py:672-680) -- the k full-width products become
+// multiplications by 64-bit constants.  tab[2*(r*k+i)] = |lambda|, tab[2*(r*k+i)+1] = sign.
+template <int L, int KIND, int E, bool VEC, int U>
+__device__ __forceinline__ void recombine_items_small(const FieldParams& f, const RowPtrs& rows, int k, int width,
+                                                      const u64* tab, u64* out, size_t ostride, size_t limb_off,
+                                                      size_t limb_step) {
+    static_assert(KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
+    constexpr int RB = (U * E * L <= 4) ? 4 : 2;
+    constexpr int N = 2 * L;
+    typedef Fp<L, KIND> F;
+    for (int r = 0; r < width; r++) {
+        u32 pos[U][E][F::WSM], neg[U][E][F::WSM];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                zero_n<F::WSM>(pos[u][e]);
+                zero_n<F::WSM>(neg[u][e]);
+            }
+        for (int i0 = 0; i0 < k; i0 += RB) {
+            u32 x[RB][U][E * N];
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (i0 + b < k) {
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        load_limbs<E * L, VEC>(x[b][u], rows.p[i0 + b] + limb_off + u * limb_step);
+                }
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (i0 + b < k) {
+                    const u64 mag = tab[2 * (r * k + i0 + b)];
+                    const bool minus = tab[2 * (r * k + i0 + b) + 1] != 0;   // warp-uniform
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            if (minus) F::mac_const(neg[u][e], x[b][u] + e * N, mag);
+                            else F::mac_const(pos[u][e], x[b][u] + e * N, mag);
+                        }
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            u32 res[E * N];
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                u32 rp[N], rn[N];
+                F::template pm_reduce<F::WSM>(rp, pos[u][e], f);
+                F::template pm_reduce<F::WSM>(rn, neg[u][e], f);
+                F::sub(res + e * N, rp, rn, f);
+            }
+            store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);
+        }
+    }
+}
+
+template <int L, int KIND, bool VEC>
+__global__ void __launch_bounds__(MPYC_THREADS)
+k_recombine_small(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,
+                  u64* __restrict__ out, size_t ostride, size_t n) {
+    extern __shared__ __align__(16) u64 stab[];
+    __shared__ __align__(8) u64 mbar;
+    tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    constexpr int E = VEC ? VecItem<L>::E : 1;
+    constexpr int U = (L <= 2) ? 2 : 1;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
+    size_t it = tid;
+    for (; it + (U - 1) * nth < n_items; it += U * nth)
+        recombine_items_small<L, KIND, E, VEC, U>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L),
+                                                  nth * (size_t)(E * L));
+    for (; it < n_items; it += nth)
+        recombine_items_small<L, KIND, E, VEC, 1>(f, rows, k, width, stab, out, ostride, it * (size_t)(E * L), 0);
+    if constexpr (E > 1) {
+        for (size_t h = n_items * E + tid; h < n; h += nth)
+            recombine_items_small<L, KIND, 1, false, 1>(f, rows, k, width, stab, out, ostride, h * (size_t)L, 0);
+    }
+}
+
 template <int L, int KIND, bool VEC>
 __global__ void __launch_bounds__(MPYC_THREADS)
 k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,

@@ -224,13 +224,30 @@ cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaK
 // ---- recombine ------------------------------------------------------------------------------
 
 template <int L>
-cudaError_t Launch<L>::recombine(const FieldParams& fp, const RowPtrs& rows, int k, int width, const u64* gtab,
-                                 u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st) {
+cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width,
+                                 const u64* gtab, u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st) {
     bool vec = aligned16(out) && ((ostride * L) % 2 == 0);
     for (int i = 0; i < k; i++) vec = vec && aligned16(rows.p[i]);
     if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
     if (L == 3) vec = false;
     constexpr int EV = VecItem<L>::E;
+    if (small) {
+        if (fp.kind == KIND_GENERIC) return cudaErrorInvalidValue;
+#define SM(VECF, ITEMS)                                                                                                  \
+    do {                                                                                                                 \
+        if (fp.kind == KIND_PM_ALIGNED)                                                                                  \
+            return launch_kernel(k_recombine_small<L, KIND_PM_ALIGNED, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width,  \
+                                 gtab, tab_bytes, out, ostride, n);                                                      \
+        return launch_kernel(k_recombine_small<L, KIND_PM_SHIFT, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width, gtab,  \
+                             tab_bytes, out, ostride, n);                                                                \
+    } while (0)
+        if constexpr (L != 3) {
+            if (vec) SM(true, (n + EV - 1) / EV);
+        }
+        if constexpr (L % 2 == 1) SM(false, n);
+#undef SM
+        return cudaErrorInvalidValue;
+    }
     if constexpr (L != 3) {
         if (vec) {
 #define M(K) return launch_kernel(k_recombine<L, K, true>, (n + EV - 1) / EV, tab_bytes, st, fp, rows, k, width, gtab, tab_bytes, out, ostride, n)
