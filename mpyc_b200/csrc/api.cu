@@ -656,8 +656,9 @@ static int recombine_table(const mpyc_b200_field* cf, const int64_t* xs, int k, 
         int rc = compute_lambda(f->fp, xs, k, x_rs, width, host);
         if (rc) return rc;
         // signed-magnitude form: |lambda| < 2^58 for every entry (e.g. x-coordinates 1..k at 0:
-        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (pseudo-Mersenne fields, k <= 32)
-        if (f->fp.kind != KIND_GENERIC && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
+        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (pseudo-Mersenne fields of >= 2 limbs,
+        // k <= 32; for 1-limb fields the full product is as cheap, measured)
+        if (f->fp.kind != KIND_GENERIC && f->fp.L >= 2 && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
             const int L = (int)f->fp.L;
             std::vector<u64> sm((size_t)width * k * 2);
             bool ok = true;

@@ -46,13 +46,33 @@ __device__ __forceinline__ void stg_v2(u64* p, const u32* v) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v[0]), "r"(v[1]) : "memory");
 }
 
-// load / store NL 64-bit limbs (NL even when VEC) starting at p, as 2*NL 32-bit registers
+__device__ __forceinline__ void ldg_v8(u32* v, const u64* p) {   // 32 bytes = four 64-bit limbs (LDG.E.256)
+    asm("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(u64* p, const u32* v) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// load / store NL 64-bit limbs starting at p, as 2*NL 32-bit registers.  VEC: 256-bit accesses
+// (sm_100 LDG.E.256 / STG.E.256; p 32-byte aligned, NL a multiple of 4); else one limb at a time.
+#ifndef MPYC_VEC128
+#define MPYC_VEC128 0   // 1: split every 256-bit access into two 128-bit ones (experiments)
+#endif
 template <int NL, bool VEC>
 __device__ __forceinline__ void load_limbs(u32* v, const u64* p) {
     if constexpr (VEC) {
-        static_assert(NL % 2 == 0, "vector path moves limb pairs");
+        static_assert(NL % 4 == 0, "vector path moves 32-byte groups");
 #pragma unroll
-        for (int q = 0; q < NL / 2; q++) ldg_v4(v + 4 * q, p + 2 * q);
+        for (int q = 0; q < NL / 4; q++) {
+            if constexpr (MPYC_VEC128) {
+                ldg_v4(v + 8 * q, p + 4 * q);
+                ldg_v4(v + 8 * q + 4, p + 4 * q + 2);
+            } else {
+                ldg_v8(v + 8 * q, p + 4 * q);
+            }
+        }
     } else {
 #pragma unroll
         for (int q = 0; q < NL; q++) ldg_v2(v + 2 * q, p + q);
@@ -62,17 +82,24 @@ template <int NL, bool VEC>
 __device__ __forceinline__ void store_limbs(u64* p, const u32* v) {
     if constexpr (VEC) {
 #pragma unroll
-        for (int q = 0; q < NL / 2; q++) stg_v4(p + 2 * q, v + 4 * q);
+        for (int q = 0; q < NL / 4; q++) {
+            if constexpr (MPYC_VEC128) {
+                stg_v4(p + 4 * q, v + 8 * q);
+                stg_v4(p + 4 * q + 2, v + 8 * q + 4);
+            } else {
+                stg_v8(p + 4 * q, v + 8 * q);
+            }
+        }
     } else {
 #pragma unroll
         for (int q = 0; q < NL; q++) stg_v2(p + q, v + 2 * q);
     }
 }
 
-// elements per vector item: the smallest E with E*L even
+// elements per vector item: the smallest E with E*L a multiple of 4 limbs (32 bytes)
 template <int L>
 struct VecItem {
-    static constexpr int E = (L % 2 == 0) ? 1 : 2;
+    static constexpr int E = (L == 4) ? 1 : (L == 2 ? 2 : 4);
 };
 
 // ---------------------------------------------------------------------------------------
@@ -154,7 +181,10 @@ __global__ void __launch_bounds__(MPYC_THREADS)
 k_binop(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, ScalarParam scal,
         u64* __restrict__ out, size_t n) {
     constexpr int E = VEC ? VecItem<L>::E : 1;
-    constexpr int U = (L <= 2) ? 4 : 2;   // items in flight per thread
+#ifndef MPYC_BINOP_U
+#define MPYC_BINOP_U 1
+#endif
+    constexpr int U = MPYC_BINOP_U;   // items in flight per thread
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
@@ -217,10 +247,13 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 #define MPYC_SPLIT_U 1
 #endif
 #ifndef MPYC_REC_U1
-#define MPYC_REC_U1 4
+#define MPYC_REC_U1 2
 #endif
 #ifndef MPYC_REC_U2
-#define MPYC_REC_U2 2
+#define MPYC_REC_U2 1
+#endif
+#ifndef MPYC_RECS_U
+#define MPYC_RECS_U 1
 #endif
 
 // shares of one item (E elements) from its t+1 polynomial coefficient rows held in registers
@@ -543,7 +576,7 @@ k_recombine_small(FieldParams f, RowPtrs rows, int k, int width, const u64* __re
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
     constexpr int E = VEC ? VecItem<L>::E : 1;
-    constexpr int U = (L <= 2) ? 2 : 1;
+    constexpr int U = (L <= 2) ? MPYC_RECS_U : 1;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;

@@ -3,7 +3,7 @@
 #pragma once
 #include "launch.h"
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 template <class... KArgs, class... Args>
 static cudaError_t launch_kernel(void (*kernel)(KArgs...), size_t items, size_t smem, cudaStream_t st, Args... args) {
@@ -55,23 +55,17 @@ static cudaError_t binop_k(const FieldParams& fp, int op, const u64* a, const u6
 template <int L>
 cudaError_t Launch<L>::binop(const FieldParams& fp, int op, const u64* a, const u64* b, const u64* scal, u64* out,
                              size_t n, cudaStream_t st) {
-    bool vec = aligned16(a) && aligned16(out) && (scal || op == OP_NEG || aligned16(b));
-    if constexpr (L % 2 == 0) {
-        if (!vec) return cudaErrorMisalignedAddress;
-#define M(K) return binop_k<L, K, true>(fp, op, a, b, scal, out, n, st)
-        KIND_SWITCH(fp.kind, M)
-#undef M
-    } else {
+    const bool vec = L != 3 && aligned32(a) && aligned32(out) && (scal || op == OP_NEG || aligned32(b));
+    if constexpr (L != 3) {
         if (vec) {
 #define M(K) return binop_k<L, K, true>(fp, op, a, b, scal, out, n, st)
             KIND_SWITCH(fp.kind, M)
 #undef M
-        } else {
-#define M(K) return binop_k<L, K, false>(fp, op, a, b, scal, out, n, st)
-            KIND_SWITCH(fp.kind, M)
-#undef M
         }
     }
+#define M(K) return binop_k<L, K, false>(fp, op, a, b, scal, out, n, st)
+    KIND_SWITCH(fp.kind, M)
+#undef M
     return cudaErrorInvalidValue;
 }
 
@@ -140,9 +134,8 @@ template <int L>
 cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
                              u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st) {
-    const bool vec = aligned16(secrets) && aligned16(shares) && (t == 0 || aligned16(coeffs)) &&
-                     ((cstride * L) % 2 == 0) && ((sstride * L) % 2 == 0);
-    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
+    const bool vec = L != 3 && aligned32(secrets) && aligned32(shares) && (t == 0 || aligned32(coeffs)) &&
+                     (cstride % 4 == 0 || t <= 1) && (sstride % 4 == 0 || m <= 1);   // strides in limbs
     const int maxt = full ? 5 : 9;
     if (t + 1 > maxt) {
         if (!full) return cudaErrorInvalidValue;   // api.cu asks for full tables whenever t > 8
@@ -153,16 +146,12 @@ cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secret
 #define GO(VECF)                                                                                                   \
     return full ? split_kind<L, true, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st) \
                 : split_kind<L, false, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
-    if constexpr (L % 2 == 0) {
-        GO(true);
-    } else if constexpr (L == 1) {
+    if constexpr (L != 3) {
         if (vec) {
             GO(true);
         }
-        GO(false);
-    } else {   // L == 3: 24-byte elements use the scalar-limb path only (keeps the binary small)
-        GO(false);
     }
+    GO(false);
 #undef GO
 }
 
@@ -192,8 +181,7 @@ static cudaError_t split_gen_k(const FieldParams& fp, const ChaChaKey& key, cons
 template <int L>
 cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets, u64* shares,
                                  size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
-    const bool vec = aligned16(secrets) && aligned16(shares) && ((sstride * L) % 2 == 0);
-    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
+    const bool vec = L != 3 && aligned32(secrets) && aligned32(shares) && (sstride % 4 == 0 || m <= 1);
 #define GEN_GO(V)                                                                                                  \
     do {                                                                                                           \
         if (full) {                                                                                                \
@@ -210,14 +198,10 @@ cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaK
             return split_gen_k<L, KIND_PM_SHIFT, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
         return cudaErrorInvalidValue;                                                                              \
     } while (0)
-    if constexpr (L % 2 == 0) {
-        GEN_GO(true);
-    } else if constexpr (L == 1) {
+    if constexpr (L != 3) {
         if (vec) GEN_GO(true);
-        GEN_GO(false);
-    } else {
-        GEN_GO(false);   // L == 3: scalar-limb path (keeps the binary small)
     }
+    GEN_GO(false);
 #undef GEN_GO
 }
 
@@ -226,10 +210,8 @@ cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaK
 template <int L>
 cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width,
                                  const u64* gtab, u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st) {
-    bool vec = aligned16(out) && ((ostride * L) % 2 == 0);
-    for (int i = 0; i < k; i++) vec = vec && aligned16(rows.p[i]);
-    if (L % 2 == 0 && !vec) return cudaErrorMisalignedAddress;
-    if (L == 3) vec = false;
+    bool vec = L != 3 && aligned32(out) && (ostride % 4 == 0 || width <= 1);   // stride in limbs
+    for (int i = 0; i < k; i++) vec = vec && aligned32(rows.p[i]);
     constexpr int EV = VecItem<L>::E;
     if (small) {
         if (fp.kind == KIND_GENERIC) return cudaErrorInvalidValue;
@@ -244,9 +226,8 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
         if constexpr (L != 3) {
             if (vec) SM(true, (n + EV - 1) / EV);
         }
-        if constexpr (L % 2 == 1) SM(false, n);
+        SM(false, n);
 #undef SM
-        return cudaErrorInvalidValue;
     }
     if constexpr (L != 3) {
         if (vec) {
@@ -255,11 +236,9 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
 #undef M
         }
     }
-    if constexpr (L % 2 == 1) {
 #define M(K) return launch_kernel(k_recombine<L, K, false>, n, tab_bytes, st, fp, rows, k, width, gtab, tab_bytes, out, ostride, n)
-        KIND_SWITCH(fp.kind, M)
+    KIND_SWITCH(fp.kind, M)
 #undef M
-    }
     return cudaErrorInvalidValue;
 }
 

@@ -25,13 +25,15 @@ def _require_cuda():
 
 
 def _alloc(ctx, rows, n, device):
-    """Uninitialised limb storage: int64 (rows, n, L) or uint8 (rows, n); row stride padded to 16 bytes."""
+    """Uninitialised limb storage: int64 (rows, n, L) or uint8 (rows, n); row stride padded to 32 bytes
+    so that every row start allows 256-bit vector accesses."""
     _require_cuda()
     if ctx.binary:
-        stride = (n + 15) // 16 * 16
+        stride = (n + 31) // 32 * 32
         return torch.empty((rows, stride), dtype=torch.uint8, device=device)[:, :n]
     L = ctx.nlimbs
-    stride = n + (n & 1) if L % 2 else n
+    q = {1: 4, 2: 2, 3: 4, 4: 1}[L]
+    stride = (n + q - 1) // q * q
     return torch.empty((rows, stride, L), dtype=torch.int64, device=device)[:, :n]
 
 

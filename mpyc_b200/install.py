@@ -42,12 +42,50 @@ def _wrap(name, ours, theirs, strict):
     return call
 
 
-def install(thresha_module=None, strict=False, device=0):
-    """Patch `mpyc.thresha` (or the module passed in).  Returns the list of patched names."""
+def _install_finfields(finfields_module, min_size):
+    """PrimeFieldArray._reciprocal/_pow/_sqrt/_is_sqr -> batched kernels for covered primes and arrays of
+    at least `min_size` elements (below that the per-call overhead of a launch outweighs the gain)."""
+    from mpyc_b200 import finfields as ours
+    cls = finfields_module.PrimeFieldArray
+    orig = {name: cls.__dict__[name] for name in ('_reciprocal', '_pow', '_sqrt', '_is_sqr')}
+    _saved_ff.update({'cls': cls, **orig})
+
+    def use_gpu(klass, a):
+        import numpy as np
+        return np.size(a) >= min_size and klass.field.modulus % 2 == 1 and klass.field.modulus.bit_length() <= 256
+
+    def _reciprocal(klass, a):
+        return ours.reciprocal(klass, a) if use_gpu(klass, a) else orig['_reciprocal'].__func__(klass, a)
+
+    def _pow(klass, a, b):
+        theirs = lambda x, y: orig['_pow'].__func__(klass, x, y)   # noqa: E731
+        return ours.power(klass, a, b, _fallback=theirs) if use_gpu(klass, a) else theirs(a, b)
+
+    def _sqrt(klass, a, INV=False):
+        theirs = lambda x, INV=False: orig['_sqrt'].__func__(klass, x, INV=INV)   # noqa: E731
+        return ours.sqrt(klass, a, INV=INV, _fallback=theirs) if use_gpu(klass, a) else theirs(a, INV=INV)
+
+    def _is_sqr(klass, a):
+        return ours.is_sqr(klass, a) if use_gpu(klass, a) else orig['_is_sqr'].__func__(klass, a)
+
+    cls._reciprocal = classmethod(_reciprocal)
+    cls._pow = classmethod(_pow)
+    cls._sqrt = classmethod(_sqrt)
+    cls._is_sqr = classmethod(_is_sqr)
+
+
+_saved_ff = {}
+
+
+def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256):
+    """Patch `mpyc.thresha` (or the module passed in); with finfields_module also the batched
+    inverse/pow/sqrt/is_sqr of PrimeFieldArray.  Returns the list of patched names."""
     if thresha_module is None:
         import mpyc.thresha as thresha_module
     if _saved:
         uninstall()
+    if finfields_module is not None:
+        _install_finfields(finfields_module, finfields_min_size)
     engine.device = device
     for name in _NAMES:
         theirs = getattr(thresha_module, name)
@@ -65,3 +103,8 @@ def uninstall():
     for name, (module, theirs) in list(_saved.items()):
         setattr(module, name, theirs)
     _saved.clear()
+    if _saved_ff:
+        cls = _saved_ff.pop('cls')
+        for name, member in _saved_ff.items():
+            setattr(cls, name, member)
+        _saved_ff.clear()

@@ -366,7 +366,7 @@ def test_generate_mode_uses_chacha20_keystream(p):
     words = 2 * L + 2
     slot = 4 if words <= 4 else (8 if words <= 8 else 16)
     per_block = 16 // slot
-    E = 2 if (L == 1) else 1          # vector items of 1-limb fields hold two elements (L == 3: scalar path)
+    E = {1: 4, 2: 2, 3: 1, 4: 1}[L]   # elements per 32-byte vector item (L == 3: scalar path)
     bpi = (E + per_block - 1) // per_block
     keep = (1 << (p.bit_length() + 64)) - 1
     n_items = n // E
@@ -449,3 +449,27 @@ def test_gf256_matmul():
         want ^= tab[a[:, l][:, None], b[l][None, :]]
     got = dev.matmul(ctx, DeviceArray.from_limbs(ctx, a.reshape(-1)), DeviceArray.from_limbs(ctx, b.reshape(-1)), r, k, c)
     assert np.array_equal(got.to_limbs().reshape(r, c), want)
+
+
+def test_finfields_batched_hooks():
+    """mpyc_b200.finfields: value-array in / value-array out replacements of PrimeFieldArray's classmethods."""
+    from mpyc_b200 import finfields as ff
+    for p in (P61, P128, P256, P64G):
+        F = fakefield.make_prime_field(p)
+        cls = F.array
+        a = np.array(orc.synth_elements(p, 600, 31), dtype=object).reshape(20, 30)
+        nz = np.where(a == 0, 1, a)
+        assert ff.reciprocal(cls, nz).tolist() == np.array(orc.ff_inv(p, nz.reshape(-1).tolist()), dtype=object).reshape(20, 30).tolist()
+        assert ff.power(cls, a, 7).reshape(-1).tolist() == orc.ff_pow(p, a.reshape(-1).tolist(), 7)
+        assert ff.power(cls, nz, -2).reshape(-1).tolist() == orc.ff_pow(p, nz.reshape(-1).tolist(), -2)
+        assert ff.is_sqr(cls, a).reshape(-1).tolist() == orc.ff_is_sqr(p, a.reshape(-1).tolist())
+        if p & 3 == 3:
+            assert ff.sqrt(cls, a).reshape(-1).tolist() == orc.ff_sqrt(p, a.reshape(-1).tolist())
+            assert ff.sqrt(cls, nz, INV=True).reshape(-1).tolist() == orc.ff_sqrt(p, nz.reshape(-1).tolist(), INV=True)
+        with pytest.raises(ZeroDivisionError):
+            ff.reciprocal(cls, np.array([3, 0, 5], dtype=object))
+        A, B = a[:4, :6], a[:6, :5]
+        want = orc.ff_matmul(p, A.tolist(), B.tolist())
+        assert ff.matmul(cls, A, B).tolist() == want
+        assert ff.matmul(cls, A[0], B).tolist() == want[0]
+        assert ff.matmul(cls, A, B[:, 0]).tolist() == [row[0] for row in want]

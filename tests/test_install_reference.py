@@ -73,3 +73,26 @@ def test_host_helpers_equal_reference_and_uncovered_fields_pass_through(mpyc_thr
                 thresha.random_split(fields[2], [1, 2, 3], 1, 3)
     finally:
         inst.uninstall()
+
+
+def test_finfields_hooks_installed_and_small_arrays_untouched(mpyc_thresha):
+    """PrimeFieldArray's batched hot spots are swapped in; arrays below the size threshold (and per-element
+    exponents) still run the reference's own code, so this part can be checked without a GPU."""
+    thresha, finfields, gfpx = mpyc_thresha
+    import numpy as np
+    from mpyc_b200 import install as inst
+    F = finfields.GF(2**61 - 1)
+    a = F.array(np.array([1, 2, 3, 12345], dtype=object))
+    want_inv, want_sqr = a.reciprocal().value.tolist(), a.is_sqr().tolist()
+    orig = finfields.PrimeFieldArray.__dict__['_reciprocal']
+    inst.install(thresha, finfields_module=finfields, finfields_min_size=100)
+    try:
+        assert finfields.PrimeFieldArray.__dict__['_reciprocal'] is not orig
+        assert a.reciprocal().value.tolist() == want_inv          # 4 elements < 100: reference path
+        assert a.is_sqr().tolist() == want_sqr
+        assert (a ** np.array([1, 2, 3, 4], dtype=object)).value.tolist() == [1, 4, 27, pow(12345, 4, 2**61 - 1)]
+        with pytest.raises(ZeroDivisionError):
+            F.array(np.array([0, 1], dtype=object)).reciprocal()
+    finally:
+        inst.uninstall()
+    assert finfields.PrimeFieldArray.__dict__['_reciprocal'] is orig
