@@ -188,6 +188,34 @@ def run_reference_arm(a, w):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
 
+def dropin_rate(w, device, n=200_000):
+    """The rate an unmodified MPyC caller sees: mpyc_b200.thresha.np_random_split + np_recombine on NumPy
+    object arrays of Python ints (conversion to limbs, CSPRNG draw, PCIe and kernels all inside)."""
+    import numpy as np
+    from mpyc_b200 import thresha
+    from oracle import shamir_oracle as orc
+    p, m, t, k = w['p'], w['m'], w['t'], w['k']
+
+    class Arr:
+        def __init__(self, value, check=True):
+            self.value = value
+
+    class Field:
+        modulus = order = characteristic = p
+        ext_deg = 1
+        array = Arr
+    thresha.device = device
+    s = np.array(orc.synth_elements(p, n, 1), dtype=object)
+    thresha.np_random_split(Field, s[:1000], t, m)                     # warm-up (tables, workspace)
+    t0 = time.perf_counter()
+    sh = thresha.np_random_split(Field, s, t, m)
+    out = thresha.np_recombine(Field, [(i + 1, sh[i]) for i in range(k)])
+    dt = time.perf_counter() - t0
+    assert out.value.tolist() == s.tolist()
+    return {'value': n / dt, 'unit': 'pairs/s', 'n': n,
+            'path': 'mpyc_b200.thresha.np_random_split + np_recombine on dtype=object arrays (what runtime.py calls)'}
+
+
 def run_gpu_arm(a, w):
     import torch
     import torch.distributed as dist
@@ -343,6 +371,9 @@ def run_gpu_arm(a, w):
             dist.destroy_process_group()
         return
     cpu = None if (a.no_cpu or is_mul or world > 1) else cpu_baseline(w)
+    dropin = None
+    if not (a.no_e2e or is_mul or world > 1):
+        dropin = dropin_rate(w, local)
     line = {'metric': METRIC if not is_mul else 'GF(p) modmul elem/sec', 'value': value,
             'unit': 'pairs/s' if not is_mul else 'elem/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -351,7 +382,8 @@ def run_gpu_arm(a, w):
                        'parallelism': f'element axis sharded over {world} GPU(s), no data-path collective',
                        'l2_policy': 'inputs (>= 1.6 GB) far larger than the 126 MB L2; no flush needed',
                        'coefficients': 'resident in HBM (parity mode)'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_dropin': dropin,
+            'gpu_launches': int(launches), 'clocks': clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
