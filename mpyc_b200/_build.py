@@ -32,6 +32,22 @@ def _digest():
     return h.hexdigest()
 
 
+CODEC_SRC = os.path.join(CSRC, 'pycodec.c')
+CODEC_LIB = os.path.join(HERE, '_pycodec.so')
+
+
+def build_codec(force=False):
+    """The small CPython extension that packs/unpacks Python ints (gcc, no CUDA involved)."""
+    import sysconfig
+    if not force and os.path.exists(CODEC_LIB) and os.path.getmtime(CODEC_LIB) >= os.path.getmtime(CODEC_SRC):
+        return CODEC_LIB
+    inc = sysconfig.get_paths()['include']
+    r = subprocess.run(['gcc', '-O2', '-shared', '-fPIC', '-I' + inc, CODEC_SRC, '-o', CODEC_LIB], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError('gcc failed for pycodec.c:\n' + r.stderr[-4000:])
+    return CODEC_LIB
+
+
 def build(force=False, verbose=False, defines=(), lib=None):
     """Compile (if sources changed) and return the path of the shared library.
     defines/lib: build a tuning variant (-D flags) under another file name (kernel experiments)."""
@@ -44,6 +60,7 @@ def build(force=False, verbose=False, defines=(), lib=None):
         finally:
             OBJ, LIB = saved
     os.makedirs(OBJ, exist_ok=True)
+    build_codec(force=False)
     stamp = os.path.join(OBJ, 'digest.txt')
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:

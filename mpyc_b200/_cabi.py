@@ -33,7 +33,7 @@ def _load():
     try:
         builder.build()
     except RuntimeError:
-        if not os.path.exists(LIB_PATH):
+        if not (os.path.exists(LIB_PATH) and os.path.exists(os.path.join(_HERE, '_pycodec.so'))):
             raise
     return ctypes.CDLL(os.path.join(_HERE, _VARIANT) if _VARIANT else LIB_PATH)
 

@@ -8,6 +8,8 @@ The fixed-width little-endian byte string of FiniteFieldElement.to_bytes/from_by
 """
 import numpy as np
 
+from mpyc_b200 import _pycodec   # C extension built in-tree by mpyc_b200._build (csrc/pycodec.c)
+
 
 def ints_to_limbs(values, ctx, reduce=True):
     """values: iterable / object ndarray of Python ints (any sign/size if reduce) -> uint64 (n, nlimbs),
@@ -17,17 +19,11 @@ def ints_to_limbs(values, ctx, reduce=True):
         if any(v < 0 or v > 255 for v in flat):
             raise ValueError('GF(2^8) values must be reduced polynomials (0..255)')
         return np.array(flat, dtype=np.uint8)
-    arr = np.asarray(values, dtype=object).reshape(-1)
-    n, L, p = arr.shape[0], ctx.nlimbs, ctx.modulus
-    if n == 0:
-        return np.zeros((0, L), dtype=np.uint64)
-    if reduce:
-        arr = arr % p
-    if L == 1:
-        return arr.astype(np.uint64).reshape(n, 1)
-    nb = 8 * L
-    buf = b''.join([int(v).to_bytes(nb, 'little') for v in arr])
-    return np.frombuffer(buf, dtype='<u8').reshape(n, L).copy()
+    L, p = ctx.nlimbs, ctx.modulus
+    if isinstance(values, np.ndarray):
+        values = values.reshape(-1).tolist()
+    buf = _pycodec.pack(values, 8 * L, p)        # reduces out-of-range values mod p
+    return np.frombuffer(buf, dtype='<u8').reshape(-1, L)
 
 
 def limbs_to_ints(limbs, ctx):
@@ -39,15 +35,8 @@ def limbs_to_ints(limbs, ctx):
     limbs = np.ascontiguousarray(limbs, dtype=np.uint64)
     n, L = limbs.shape
     out = np.empty(n, dtype=object)
-    if n == 0:
-        return out
-    if L == 1:
-        out[:] = limbs[:, 0].tolist()
-        return out
-    data = limbs.tobytes()
-    nb = 8 * L
-    from_bytes = int.from_bytes
-    out[:] = [from_bytes(data[i:i + nb], 'little') for i in range(0, n * nb, nb)]
+    if n:
+        out[:] = _pycodec.unpack(limbs, 8 * L)
     return out
 
 

@@ -17,9 +17,9 @@ Randomness.  The reference draws coefficients with secrets.randbelow per element
 (thresha.py:37,58-60).  `coefficient_source`, when set to a callable (order, count) -> ints, is
 used instead -- the parity tests inject deterministic streams this way, in the reference's own
 consumption order (np: (t, n) row-major; list: element-major, Horner order).  When None (default)
-the coefficients come from the OS CSPRNG in bulk (os.urandom, 64 bits wider than the modulus) and
-are reduced on the device, or -- for device-resident data -- are generated inside the kernel
-(mpyc_b200_shamir_split_generate).
+the coefficients are generated inside the kernel from a ChaCha20 stream keyed with 32 fresh bytes of
+OS randomness per call (mpyc_b200_shamir_split_generate; t <= 4), or drawn from os.urandom in bulk
+(64 bits wider than the modulus, then reduced) for GF(2^8) and t > 4.
 """
 import ctypes
 import os
@@ -91,15 +91,41 @@ def _split_limbs(ctx, sec, C, t, m):
     return shares
 
 
+_nonce = [int.from_bytes(os.urandom(7), 'little')]
+
+
+def _split_generate(ctx, sec, t, m):
+    """Default (CSPRNG) path for prime fields: secrets go to the GPU, the coefficients are generated INSIDE
+    the kernel from a ChaCha20 stream keyed with fresh OS randomness (mpyc_b200_shamir_split_generate) and
+    never exist in memory; shares come back as a limb array (m, n, L)."""
+    import torch
+    from mpyc_b200.device import DeviceArray, shamir_split_generate
+    if not torch.cuda.is_available():
+        raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
+    _nonce[0] = (_nonce[0] + 1) & (2**63 - 1)
+    dev = torch.device('cuda', device)
+    with torch.cuda.device(dev):
+        S = DeviceArray.from_limbs(ctx, sec, device=dev)
+        sh = shamir_split_generate(ctx, S, t, m, key=os.urandom(32), nonce=_nonce[0])
+        return sh.t.contiguous().cpu().numpy().view(np.uint64)
+
+
+def _use_generate(ctx, t, n):
+    return coefficient_source is None and not ctx.binary and 1 <= t <= 4 and n > 0
+
+
 def np_random_split(field, s, t, m):
     """Split each secret in s into m Shamir shares of degree t (0 <= t < m): object ndarray (m, n)."""
     ctx = context_of_field(field)
     s = _values_of(field, s)
     n = len(s)
     sec = codec.ints_to_limbs(s, ctx)
-    C = _draw(ctx, field.order, t * n)
-    C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
-    shares = _split_limbs(ctx, sec, C, t, m)
+    if _use_generate(ctx, t, n):
+        shares = _split_generate(ctx, sec, t, m)
+    else:
+        C = _draw(ctx, field.order, t * n)
+        C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
+        shares = _split_limbs(ctx, sec, C, t, m)
     out = np.empty((m, n), dtype=object)
     for i in range(m):
         out[i] = _wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))
@@ -113,11 +139,14 @@ def random_split(field, s, t, m):
     s = _values_of(field, s)
     n = len(s)
     sec = codec.ints_to_limbs(s, ctx)
-    c = _draw(ctx, field.order, t * n)
-    c = c.reshape((n, t) if ctx.binary else (n, t, ctx.nlimbs))
-    # element-major draws, first draw = highest power  ->  row j-1 = coefficient of X^j
-    C = np.ascontiguousarray(np.swapaxes(c, 0, 1)[::-1])
-    shares = _split_limbs(ctx, sec, C, t, m)
+    if _use_generate(ctx, t, n):
+        shares = _split_generate(ctx, sec, t, m)
+    else:
+        c = _draw(ctx, field.order, t * n)
+        c = c.reshape((n, t) if ctx.binary else (n, t, ctx.nlimbs))
+        # element-major draws, first draw = highest power  ->  row j-1 = coefficient of X^j
+        C = np.ascontiguousarray(np.swapaxes(c, 0, 1)[::-1])
+        shares = _split_limbs(ctx, sec, C, t, m)
     return [list(_wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))) for i in range(m)]
 
 
