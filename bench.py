@@ -33,6 +33,8 @@ WORKLOADS = {
     'ns64': dict(p=2**64 - 189, m=3, t=1, k=2, n=200_000_000, name='shamir split+recombine p=2^64-189 m=3 t=1 n=2e8/GPU (north_star 64-bit case)'),
     'c5': dict(p=2**256 - 189, m=7, t=3, k=7, n=20_000_000, name='shamir reshare p=2^256-189 m=7 t=3 recombine 2t+1 n=2e7/GPU (configs[4] shape)'),
     'modmul': dict(p=2**64 - 189, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul p=2^64-189 n=1e8/GPU (BASELINE configs[1])'),
+    'modmul_generic': dict(p=9409569905028393239, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul generic 64-bit prime 9409569905028393239 (Montgomery) n=1e8/GPU (BASELINE configs[1])'),
+    'c4': dict(p=283, binary=True, m=3, t=1, k=3, n=1 << 28, name='GF(2^8) reshare (np_aes field, modulus 283) m=3 t=1 recombine 2t+1, batched n=2^28 bytes/GPU + per-call latency at n=16 (BASELINE configs[3] shape)'),
 }
 METRIC = 'GF(p) Shamir share+recombine pairs/sec'
 
@@ -45,6 +47,22 @@ def peaks():
         except Exception:
             pass
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary of the same workload (profiles/), or (None, None)."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', f'r*_ncu_{kernel}_{workload}.txt')), reverse=True):
+        total, units = 0.0, {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}
+        for line in open(path):
+            mt = re.match(r'\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)', line)
+            if mt:
+                total += float(mt.group(2)) * units.get(mt.group(3), 1.0)
+        if total:
+            return total, os.path.relpath(path, ROOT)
+    return None, None
 
 
 class ClockSampler:
@@ -233,9 +251,11 @@ def run_gpu_arm(a, w):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     p, m, t, k, n = w['p'], w['m'], w['t'], w['k'], a.n or w['n']
-    ctx = mpyc_b200.context_for(p)
-    L = ctx.nlimbs
+    ctx = mpyc_b200.context_for(p, binary=bool(w.get('binary')))
+    L = max(ctx.nlimbs, 1)
     eb = ctx.elem_bytes
+    if w.get('binary'):
+        a.no_e2e = True   # host-buffer pipeline is exercised by the prime-field workloads
     is_mul = w['m'] == 0
     peak, peak_src = peaks()
 
@@ -318,8 +338,10 @@ def run_gpu_arm(a, w):
                               'frac': (split_bytes + rec_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
                               'bytes_per_pair': (split_bytes + rec_bytes) / n}}
     ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(a.workload, 'binop' if is_mul else 'split') if n == w['n'] else (None, None)
     roofline = {'bound': 'hbm', 'kernel': dom_name, 'achieved': ach, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                'frac': ach / peak, 'traffic': None, 'ms': dom_ms, 'algorithmic_bytes': dom_bytes, **sec}
+                'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'ms': dom_ms,
+                'algorithmic_bytes': dom_bytes, **sec}
 
     # ---- e2e: same path through the C ABI's host-buffer entry points, pinned host memory ----------------
     e2e = None
@@ -370,19 +392,40 @@ def run_gpu_arm(a, w):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None if (a.no_cpu or is_mul or world > 1) else cpu_baseline(w)
+    cpu = None if (a.no_cpu or is_mul or world > 1 or w.get('binary')) else cpu_baseline(w)
+    small_call = None
+    if w.get('binary'):
+        # np_aes.py shape: calls on n = 16 bytes; launch latency, not bandwidth, is what counts there
+        s16 = dev.DeviceArray.random(ctx, 16, seed=1, stream_id=1)
+        c16 = dev.DeviceMatrix.empty(ctx, t, 16)
+        c16.t[0].copy_(dev.DeviceArray.random(ctx, 16, seed=2, stream_id=2).t)
+        sh16 = dev.DeviceMatrix.empty(ctx, m, 16)
+        r16 = dev.DeviceMatrix.empty(ctx, 1, 16)
+        rows16 = [sh16.row(i) for i in range(k)]
+        for _ in range(20):
+            dev.shamir_split(ctx, s16, c16, t, m, out=sh16)
+            dev.shamir_recombine(ctx, list(range(1, k + 1)), rows16, 0, out=r16)
+        torch.cuda.synchronize()
+        reps = 2000
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dev.shamir_split(ctx, s16, c16, t, m, out=sh16)
+            dev.shamir_recombine(ctx, list(range(1, k + 1)), rows16, 0, out=r16)
+        torch.cuda.synchronize()
+        small_call = {'n': 16, 'us_per_split_plus_recombine': 1e6 * (time.perf_counter() - t0) / reps,
+                      'note': 'device-resident, two kernel launches per pair, host-side issue rate included'}
     dropin = None
-    if not (a.no_e2e or is_mul or world > 1):
+    if not (a.no_e2e or is_mul or world > 1 or w.get('binary')):
         dropin = dropin_rate(w, local)
     line = {'metric': METRIC if not is_mul else 'GF(p) modmul elem/sec', 'value': value,
             'unit': 'pairs/s' if not is_mul else 'elem/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': f'u64x{L} limbs (exact integer arithmetic mod p)', 'data': 'synthetic',
+            'dtype': ('u8 (GF(2^8) polynomial arithmetic)' if w.get('binary') else f'u64x{L} limbs (exact integer arithmetic mod p)'), 'data': 'synthetic',
             'config': {'workload': w['name'], 'p_bits': p.bit_length(), 'm': m, 't': t, 'recombine_k': k, 'n_per_gpu': n,
                        'parallelism': f'element axis sharded over {world} GPU(s), no data-path collective',
                        'l2_policy': 'inputs (>= 1.6 GB) far larger than the 126 MB L2; no flush needed',
                        'coefficients': 'resident in HBM (parity mode)'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_dropin': dropin,
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_dropin': dropin, 'small_call': small_call,
             'gpu_launches': int(launches), 'clocks': clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

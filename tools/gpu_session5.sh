@@ -1,6 +1,6 @@
 #!/bin/bash
 # full round-end style session: all gpu tests, smoke, all bench workloads (with e2e, cpu baseline), ncu captures
-mkdir -p gpurun_out
+rm -rf gpurun_out; mkdir -p gpurun_out
 (timeout 300 python __graft_entry__.py smoke) > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 (timeout 1200 python -m pytest tests -m gpu -q) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench_c3.json 2>gpurun_out/bench.err; echo "bench default rc=$?"
@@ -21,4 +21,9 @@ for w in c3 ns64 c5; do
   ncu --set full --clock-control none --import-source on -k regex:k_recombine -s 3 -c 1 -o gpurun_out/prof_rec_$w python bench.py --workload $w --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_rec_$w.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:k_binop -s 3 -c 1 -o gpurun_out/prof_binop_modmul python bench.py --workload modmul --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_binop.log 2>&1
+# keep the transfer small: raw-metric CSVs for every capture, the .ncu-rep only for the dominant kernel
+for f in gpurun_out/prof_*.ncu-rep; do ncu -i $f --page raw --csv > ${f%.ncu-rep}.csv 2>/dev/null; done
+for f in gpurun_out/prof_*.ncu-rep; do case $f in *prof_split_c3*) ;; *) rm -f $f;; esac; done
+rm -f gpurun_out/ncu_*.log
+du -sh gpurun_out
 tail -3 gpurun_out/bench.err
