@@ -17,6 +17,7 @@ int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem);
 
 #define GF_THREADS 256
 #define GF_MAX_TAB 2048
+#define GF_LADDER_T 4     // degrees up to this keep the x^b multiples of the coefficient words in registers
 
 struct GfTab {
     unsigned char v[GF_MAX_TAB];
@@ -68,6 +69,7 @@ __device__ __forceinline__ unsigned long long gf_mulc8(unsigned long long a, uns
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if ((c >> i) & 1u) acc ^= a;
+        if ((c >> (i + 1)) == 0) break;   // c is warp-uniform: no xtime beyond its top bit
         a = gf_xtime8(a, red);
     }
     return acc;
@@ -114,14 +116,47 @@ k_gf_split(unsigned poly, GfTab tab, const unsigned char* __restrict__ secrets, 
     const bool al = ((((uintptr_t)secrets | (uintptr_t)shares | (t ? (uintptr_t)coeffs : 0)) & 7u) == 0) &&
                     (cstride % 8 == 0 || t <= 1) && (sstride % 8 == 0 || m <= 1);
     const size_t nw = al ? n / 8 : 0;
-    for (size_t w = tid; w < nw; w += nth) {
-        for (int i = 0; i < m; i++) {
-            unsigned long long acc = ((const unsigned long long*)secrets)[w];
-            for (int j = 1; j <= t; j++) {
-                unsigned long long x = ((const unsigned long long*)(coeffs + (size_t)(j - 1) * cstride))[w];
-                acc ^= gf_mulc8(x, tab.v[i * (t + 1) + j], red);
+    if (t <= GF_LADDER_T) {
+        // x^b multiples of every coefficient word once (7 xtimes each), then each share only XORs the
+        // multiples selected by the bits of its (warp-uniform) Vandermonde entries
+        for (size_t w = tid; w < nw; w += nth) {
+            unsigned long long lad[GF_LADDER_T][8];
+            const unsigned long long s0 = ((const unsigned long long*)secrets)[w];
+#pragma unroll
+            for (int j = 0; j < GF_LADDER_T; j++) {
+                if (j < t) {
+                    unsigned long long x = ((const unsigned long long*)(coeffs + (size_t)j * cstride))[w];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        lad[j][b] = x;
+                        x = gf_xtime8(x, red);
+                    }
+                }
             }
-            ((unsigned long long*)(shares + (size_t)i * sstride))[w] = acc;
+            for (int i = 0; i < m; i++) {
+                unsigned long long acc = s0;
+#pragma unroll
+                for (int j = 0; j < GF_LADDER_T; j++) {
+                    if (j < t) {
+                        const unsigned c = tab.v[i * (t + 1) + j + 1];
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            if ((c >> b) & 1u) acc ^= lad[j][b];
+                    }
+                }
+                ((unsigned long long*)(shares + (size_t)i * sstride))[w] = acc;
+            }
+        }
+    } else {
+        for (size_t w = tid; w < nw; w += nth) {
+            for (int i = 0; i < m; i++) {
+                unsigned long long acc = ((const unsigned long long*)secrets)[w];
+                for (int j = 1; j <= t; j++) {
+                    unsigned long long x = ((const unsigned long long*)(coeffs + (size_t)(j - 1) * cstride))[w];
+                    acc ^= gf_mulc8(x, tab.v[i * (t + 1) + j], red);
+                }
+                ((unsigned long long*)(shares + (size_t)i * sstride))[w] = acc;
+            }
         }
     }
     for (size_t h = nw * 8 + tid; h < n; h += nth) {
@@ -143,11 +178,19 @@ k_gf_recombine(unsigned poly, GfTab lam, GfRows rows, int k, int width, unsigned
     for (int i = 0; i < k; i++) bits |= (uintptr_t)rows.p[i];
     const bool al = ((bits & 7u) == 0) && (ostride % 8 == 0 || width <= 1);
     const size_t nw = al ? n / 8 : 0;
-    for (size_t w = tid; w < nw; w += nth) {
-        for (int r = 0; r < width; r++) {
+    if (width == 1) {
+        for (size_t w = tid; w < nw; w += nth) {
             unsigned long long acc = 0;
-            for (int i = 0; i < k; i++) acc ^= gf_mulc8(((const unsigned long long*)rows.p[i])[w], lam.v[r * k + i], red);
-            ((unsigned long long*)(out + (size_t)r * ostride))[w] = acc;
+            for (int i = 0; i < k; i++) acc ^= gf_mulc8(((const unsigned long long*)rows.p[i])[w], lam.v[i], red);
+            ((unsigned long long*)out)[w] = acc;
+        }
+    } else {
+        for (size_t w = tid; w < nw; w += nth) {
+            for (int r = 0; r < width; r++) {
+                unsigned long long acc = 0;
+                for (int i = 0; i < k; i++) acc ^= gf_mulc8(((const unsigned long long*)rows.p[i])[w], lam.v[r * k + i], red);
+                ((unsigned long long*)(out + (size_t)r * ostride))[w] = acc;
+            }
         }
     }
     for (size_t h = nw * 8 + tid; h < n; h += nth) {
