@@ -34,6 +34,7 @@ WORKLOADS = {
     'c5': dict(p=2**256 - 189, m=7, t=3, k=7, n=20_000_000, name='shamir reshare p=2^256-189 m=7 t=3 recombine 2t+1 n=2e7/GPU (configs[4] shape)'),
     'modmul': dict(p=2**64 - 189, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul p=2^64-189 n=1e8/GPU (BASELINE configs[1])'),
     'modmul_generic': dict(p=9409569905028393239, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul generic 64-bit prime 9409569905028393239 (Montgomery) n=1e8/GPU (BASELINE configs[1])'),
+    'c3g': dict(p=0x800000000000000000000000000000fb, m=5, t=2, k=3, n=100_000_000, name='shamir split+recombine GENERIC 128-bit prime (Montgomery path) m=5 t=2 n=1e8/GPU'),
     'c4': dict(p=283, binary=True, m=3, t=1, k=3, n=1 << 28, name='GF(2^8) reshare (np_aes field, modulus 283) m=3 t=1 recombine 2t+1, batched n=2^28 bytes/GPU + per-call latency at n=16 (BASELINE configs[3] shape)'),
 }
 METRIC = 'GF(p) Shamir share+recombine pairs/sec'

@@ -117,8 +117,17 @@ k_gf_split(unsigned poly, GfTab tab, const unsigned char* __restrict__ secrets, 
                     (cstride % 8 == 0 || t <= 1) && (sstride % 8 == 0 || m <= 1);
     const size_t nw = al ? n / 8 : 0;
     if (t <= GF_LADDER_T) {
-        // x^b multiples of every coefficient word once (7 xtimes each), then each share only XORs the
-        // multiples selected by the bits of its (warp-uniform) Vandermonde entries
+        // x^b multiples of every coefficient word once (only up to the top bit any share needs for that
+        // column), then each share only XORs the multiples selected by the bits of its (warp-uniform)
+        // Vandermonde entries
+        int depth[GF_LADDER_T];
+#pragma unroll
+        for (int j = 0; j < GF_LADDER_T; j++) {
+            unsigned any = 0;
+            if (j < t)
+                for (int i = 0; i < m; i++) any |= tab.v[i * (t + 1) + j + 1];
+            depth[j] = 32 - __clz(any | 1u);
+        }
         for (size_t w = tid; w < nw; w += nth) {
             unsigned long long lad[GF_LADDER_T][8];
             const unsigned long long s0 = ((const unsigned long long*)secrets)[w];
@@ -129,7 +138,7 @@ k_gf_split(unsigned poly, GfTab tab, const unsigned char* __restrict__ secrets, 
 #pragma unroll
                     for (int b = 0; b < 8; b++) {
                         lad[j][b] = x;
-                        x = gf_xtime8(x, red);
+                        if (b + 1 < depth[j]) x = gf_xtime8(x, red);
                     }
                 }
             }
