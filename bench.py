@@ -210,9 +210,9 @@ def run_reference_arm(a, w):
 def dropin_rate(w, device, n=200_000):
     """The rate an unmodified MPyC caller sees: mpyc_b200.thresha.np_random_split + np_recombine on NumPy
     object arrays of Python ints (conversion to limbs, CSPRNG draw, PCIe and kernels all inside)."""
+    import random
     import numpy as np
     from mpyc_b200 import thresha
-    from oracle import shamir_oracle as orc
     p, m, t, k = w['p'], w['m'], w['t'], w['k']
 
     class Arr:
@@ -224,7 +224,8 @@ def dropin_rate(w, device, n=200_000):
         ext_deg = 1
         array = Arr
     thresha.device = device
-    s = np.array(orc.synth_elements(p, n, 1), dtype=object)
+    rnd = random.Random(20260923)
+    s = np.array([rnd.randrange(p) for _ in range(n)], dtype=object)
     thresha.np_random_split(Field, s[:1000], t, m)                     # warm-up (tables, workspace)
     t0 = time.perf_counter()
     sh = thresha.np_random_split(Field, s, t, m)

@@ -826,7 +826,8 @@ struct Workspace {
 Workspace g_ws[16];
 std::mutex g_ws_mu;
 
-int acquire_workspace(int device, size_t in_bytes, size_t out_bytes, Workspace** out) {
+// creates the per-device workspace (streams) on first use; the caller then locks w->mu and calls reserve()
+int acquire_workspace(int device, Workspace** out) {
     if (device < 0 || device >= 16) return fail(MPYC_B200_EINVAL, "device ordinal out of range");
     CU(cudaSetDevice(device));
     Workspace& w = g_ws[device];
@@ -837,6 +838,12 @@ int acquire_workspace(int device, size_t in_bytes, size_t out_bytes, Workspace**
             w.device = device;
         }
     }
+    *out = &w;
+    return MPYC_B200_OK;
+}
+
+// grow the staging buffers (call with w.mu held)
+int reserve(Workspace& w, size_t in_bytes, size_t out_bytes) {
     if (in_bytes > w.in_cap) {
         for (int s = 0; s < kSlots; s++) {
             if (w.d_in[s]) cudaFree(w.d_in[s]);
@@ -855,7 +862,6 @@ int acquire_workspace(int device, size_t in_bytes, size_t out_bytes, Workspace**
         for (int s = 0; s < kSlots; s++) CU(cudaMalloc(&w.d_out[s], out_bytes));
         w.out_cap = out_bytes;
     }
-    *out = &w;
     return MPYC_B200_OK;
 }
 
@@ -881,9 +887,11 @@ MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * (size_t)(t + 1 + m));
     Workspace* w;
-    int rc = acquire_workspace(device, ch * eb * (size_t)(t + 1), ch * eb * (size_t)m, &w);
+    int rc = acquire_workspace(device, &w);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(w->mu);
+    rc = reserve(*w, ch * eb * (size_t)(t + 1), ch * eb * (size_t)m);
+    if (rc) return rc;
     size_t c = 0;
     for (size_t off = 0; off < n; off += ch, c++) {
         const int s = (int)(c % kSlots);
@@ -915,9 +923,11 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * (size_t)(k + width));
     Workspace* w;
-    int rc = acquire_workspace(device, ch * eb * (size_t)k, ch * eb * (size_t)width, &w);
+    int rc = acquire_workspace(device, &w);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(w->mu);
+    rc = reserve(*w, ch * eb * (size_t)k, ch * eb * (size_t)width);
+    if (rc) return rc;
     size_t c = 0;
     for (size_t off = 0; off < n; off += ch, c++) {
         const int s = (int)(c % kSlots);
@@ -946,9 +956,11 @@ MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const voi
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * 3);
     Workspace* w;
-    int rc = acquire_workspace(device, ch * eb * 2, ch * eb, &w);
+    int rc = acquire_workspace(device, &w);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(w->mu);
+    rc = reserve(*w, ch * eb * 2, ch * eb);
+    if (rc) return rc;
     size_t c = 0;
     for (size_t off = 0; off < n; off += ch, c++) {
         const int s = (int)(c % kSlots);

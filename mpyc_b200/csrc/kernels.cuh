@@ -14,6 +14,13 @@
 
 #define MPYC_MAX_POINTS 64
 #define MPYC_THREADS 256
+// launch bounds: asking ptxas for >= 1 resident CTA lets it use the registers it wants (fewer moves,
+// measured +1..8 % on K2); -DMPYC_LB_PLAIN restores the default heuristic (experiments)
+#ifdef MPYC_LB_PLAIN
+#define MPYC_LB __launch_bounds__(MPYC_THREADS)
+#else
+#define MPYC_LB __launch_bounds__(MPYC_THREADS, 1)
+#endif
 
 struct RowPtrs {
     const u64* p[MPYC_MAX_POINTS];
@@ -177,7 +184,7 @@ __device__ __forceinline__ void binop_items(const FieldParams& f, const u64* a, 
 }
 
 template <int L, int KIND, int OP, bool SCALAR, bool VEC>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_binop(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, ScalarParam scal,
         u64* __restrict__ out, size_t n) {
     constexpr int E = VEC ? VecItem<L>::E : 1;
@@ -207,7 +214,7 @@ k_binop(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, Sca
 // ---------------------------------------------------------------------------------------
 
 template <int L, int KIND, int MODE>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ out, unsigned char* __restrict__ out_u8,
       int* zero_flag, size_t n) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -414,7 +421,7 @@ __device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaCh
 }
 
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, u64* __restrict__ shares, size_t sstride,
             size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
     extern __shared__ __align__(16) u64 stab[];
@@ -439,7 +446,7 @@ k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, u64* 
 
 // any t: streams the t+1 input rows per output row (re-reads hit L1/L2); full tables
 template <int L, int KIND>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_split_dyn(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
             u64* __restrict__ shares, size_t sstride, size_t n, int m, int tp1, const u64* __restrict__ gtab) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -572,7 +579,7 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
 }
 
 template <int L, int KIND, bool VEC>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_recombine_small(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,
                   u64* __restrict__ out, size_t ostride, size_t n) {
     extern __shared__ __align__(16) u64 stab[];
@@ -596,7 +603,7 @@ k_recombine_small(FieldParams f, RowPtrs rows, int k, int width, const u64* __re
 }
 
 template <int L, int KIND, bool VEC>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,
             u64* __restrict__ out, size_t ostride, size_t n) {
     extern __shared__ __align__(16) u64 stab[];
@@ -626,7 +633,7 @@ k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict
 // ---------------------------------------------------------------------------------------
 
 template <int L, int KIND>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
                int chunk_bytes, int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out,
                size_t n) {
@@ -693,7 +700,7 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 #define MPYC_MM_KT 64   // k-chunk of the A tile held in shared memory
 
 template <int L, int KIND, int TM>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_matmul(FieldParams f, const u64* __restrict__ A, const u64* __restrict__ B, u64* __restrict__ C, size_t r, size_t k,
          size_t c) {
     typedef Fp<L, KIND> F;
@@ -776,7 +783,7 @@ __device__ __forceinline__ u64 splitmix64_dev(u64 x) {
 }
 
 template <int L, int KIND>
-__global__ void __launch_bounds__(MPYC_THREADS, 1)
+__global__ void MPYC_LB
 k_fill_random(FieldParams f, u64* __restrict__ out, size_t n, u64 base) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
@@ -802,7 +809,7 @@ k_fill_random(FieldParams f, u64* __restrict__ out, size_t n, u64 base) {
     }
 }
 
-static __global__ void __launch_bounds__(MPYC_THREADS, 1)
+static __global__ void MPYC_LB
 k_count_mismatch(const u64* __restrict__ a, const u64* __restrict__ b, size_t n_elems, int L, unsigned long long* count) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     unsigned long long local = 0;

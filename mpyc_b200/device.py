@@ -162,15 +162,19 @@ class DeviceArray:
     def __truediv__(self, other):
         if isinstance(other, DeviceArray):
             return self * other.reciprocal()
-        if isinstance(other, (int, np.integer)):
+        if isinstance(other, (int, np.integer)) and not self.ctx.binary:
             return self * pow(int(other), -1, self.ctx.order)
         return NotImplemented
 
     def __lshift__(self, k):
+        if self.ctx.binary:
+            return NotImplemented   # polynomial shifts of GF(2^8) arrays are not part of the batched surface
         return self * pow(2, int(k), self.ctx.order)
 
     def __rshift__(self, k):
         """'>> k' multiplies by (2^k)^-1 mod p (finfields.py:1250-1259) -- not a bit shift."""
+        if self.ctx.binary:
+            return NotImplemented
         return self * pow(pow(2, int(k), self.ctx.order), -1, self.ctx.order)
 
     def sqrt(self, INV=False):
