@@ -265,7 +265,7 @@ def test_host_buffer_abi_large_chunked():
 
 # ---- size-independent properties at full benchmark sizes ---------------------------------------------
 
-@pytest.mark.parametrize('p,m,t,n', [(P64, 3, 1, 20_000_000), (P128, 5, 2, 10_000_000), (P256, 7, 3, 2_000_000),
+@pytest.mark.parametrize('p,m,t,n', [(P128, 5, 2, 100_000_000), (P64, 3, 1, 20_000_000), (P128, 5, 2, 10_000_000), (P256, 7, 3, 2_000_000),
                                       (P64G, 3, 1, 10_000_000), (GEN['128'], 5, 2, 4_000_000), (P61, 3, 1, 10_000_001)])
 def test_full_size_roundtrip_and_linearity(p, m, t, n):
     ctx = mpyc_b200.context_for(p)
@@ -277,7 +277,7 @@ def test_full_size_roundtrip_and_linearity(p, m, t, n):
         C.t[j].copy_(DeviceArray.random(ctx, n, seed=10 + j, stream_id=3).t)
         C2.t[j].copy_(DeviceArray.random(ctx, n, seed=20 + j, stream_id=4).t)
     sh = dev.shamir_split(ctx, S, C, t, m)
-    sh2 = dev.shamir_split(ctx, S2, C2, t, m)
+    sh2 = dev.shamir_split(ctx, S2, C2, t, m) if n < 50_000_000 else None
     # encode -> erase -> decode: any t+1 shares return the secrets
     for xs in ([1 + i for i in range(t + 1)], [m - i for i in range(t + 1)]):
         rec = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs])
@@ -285,26 +285,24 @@ def test_full_size_roundtrip_and_linearity(p, m, t, n):
     # all m shares (degree t < m) as well
     rec = dev.shamir_recombine(ctx, list(range(1, m + 1)), [sh.row(i) for i in range(m)])
     assert rec.count_mismatch(S) == 0
-    # linearity: shares of (S + S2) with coefficients (C + C2) are the sums of the shares
-    Ssum = S + S2
-    Csum = DeviceMatrix.empty(ctx, t, n)
-    for j in range(t):
-        Csum.t[j].copy_((C.row(j) + C2.row(j)).t)
-    shsum = dev.shamir_split(ctx, Ssum, Csum, t, m)
-    for i in range(m):
-        assert shsum.row(i).count_mismatch(sh.row(i) + sh2.row(i)) == 0
+    if sh2 is not None:   # (skipped at the BASELINE full size to bound memory: the checks around it remain)
+        # linearity: shares of (S + S2) with coefficients (C + C2) are the sums of the shares
+        Ssum = S + S2
+        Csum = DeviceMatrix.empty(ctx, t, n)
+        for j in range(t):
+            Csum.t[j].copy_((C.row(j) + C2.row(j)).t)
+        shsum = dev.shamir_split(ctx, Ssum, Csum, t, m)
+        for i in range(m):
+            assert shsum.row(i).count_mismatch(sh.row(i) + sh2.row(i)) == 0
     # recombining at a party's own point returns that party's share
     xs = list(range(1, t + 2))
     own = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs], [m])
     assert own.row(0).count_mismatch(sh.row(m - 1)) == 0
     # spot-check against the oracle at a few positions
-    idx = [0, 1, n // 3, n - 2, n - 1]
-    lim = S.to_limbs()[idx]
-    s_int = codec.limbs_to_ints(lim, ctx).tolist()
-    C_int = [codec.limbs_to_ints(C.row(j).to_limbs()[idx], ctx).tolist() for j in range(t)]
-    want = orc.split_np_order(orc.field_of(p), s_int, C_int, m)
-    got = [codec.limbs_to_ints(sh.row(i).to_limbs()[idx], ctx).tolist() for i in range(m)]
-    assert got == want
+    idx = torch.tensor([0, 1, n // 3, n - 2, n - 1], device=S.t.device)
+    pick = lambda arr: codec.limbs_to_ints(arr.t.index_select(0, idx).cpu().numpy().view(np.uint64), ctx).tolist()   # noqa: E731
+    want = orc.split_np_order(orc.field_of(p), pick(S), [pick(C.row(j)) for j in range(t)], m)
+    assert [pick(sh.row(i)) for i in range(m)] == want
 
 
 def test_error_behaviour():
