@@ -4,15 +4,16 @@ rm -rf gpurun_out; mkdir -p gpurun_out
 (timeout 300 python __graft_entry__.py smoke) > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 (timeout 1200 python -m pytest tests -m gpu -q) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py > gpurun_out/bench_c3.json 2>gpurun_out/bench.err; echo "bench default rc=$?"
-for w in ns64 c5 modmul; do
+for w in ns64 c5 modmul c4 modmul_generic c3g; do
   timeout 300 python bench.py --workload $w --steps 10 --no-cpu > gpurun_out/bench_$w.json 2>>gpurun_out/bench.err
 done
-for w in c3 ns64 c5 modmul; do
+for w in c3 ns64 c5 modmul c4 modmul_generic c3g; do
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/bench_$w.json')); r=d['roofline']
 rec=r.get('recombine',{'achieved':0,'frac':0}); st=r.get('step_total',{'frac':0})
-print('$w value %.3e %s %.0f GB/s (%.3f) rec %.0f GB/s (%.3f) step frac %.3f e2e %.3e dropin %s cpu %s' % (d['value'], r['kernel'], r['achieved'], r['frac'], rec['achieved'], rec['frac'], st['frac'], d['e2e']['value'], d.get('e2e_dropin'), d.get('cpu_baseline')))"
+e2e=(d.get('e2e') or {}).get('value',0); dr=(d.get('e2e_dropin') or {}).get('value',0); cpu=(d.get('cpu_baseline') or {}).get('value',0)
+print('$w value %.3e %s %.0f GB/s (%.3f) rec %.0f GB/s (%.3f) step frac %.3f e2e %.3e dropin %.3e cpu %.3e small %s' % (d['value'], r['kernel'], r['achieved'], r['frac'], rec['achieved'], rec['frac'], st['frac'], e2e, dr, cpu, d.get('small_call')))"
 done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>>gpurun_out/bench.err; cut -c1-200 gpurun_out/bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_c3.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launch_run.log 2>&1
