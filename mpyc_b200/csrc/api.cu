@@ -280,8 +280,8 @@ static int get_table(mpyc_b200_field* f, const std::string& key, DevTable* out, 
 
 // Vandermonde table for share generation: row i, column j = (i+1)^j
 static int build_split_table(const FieldParams& fp, int t, int m, std::vector<u64>& host, bool& full) {
-    // 64-bit-constant form when the field is pseudo-Mersenne and m^t < 2^59
-    bool small = fp.kind != KIND_GENERIC && t <= 8;
+    // 64-bit-constant form when m^t < 2^59 (t <= 8 keeps the (L+1)-limb sum below 2^(k+64))
+    bool small = t <= 8;
     if (small) {
         long double lim = 1;
         for (int j = 0; j < t; j++) lim *= m;
@@ -656,9 +656,9 @@ static int recombine_table(const mpyc_b200_field* cf, const int64_t* xs, int k, 
         int rc = compute_lambda(f->fp, xs, k, x_rs, width, host);
         if (rc) return rc;
         // signed-magnitude form: |lambda| < 2^58 for every entry (e.g. x-coordinates 1..k at 0:
-        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (pseudo-Mersenne fields of >= 2 limbs,
-        // k <= 32; for 1-limb fields the full product is as cheap, measured)
-        if (f->fp.kind != KIND_GENERIC && f->fp.L >= 2 && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
+        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (fields of >= 2 limbs, k <= 32; for 1-limb
+        // fields the full product is as cheap, measured)
+        if (f->fp.L >= 2 && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
             const int L = (int)f->fp.L;
             std::vector<u64> sm((size_t)width * k * 2);
             bool ok = true;

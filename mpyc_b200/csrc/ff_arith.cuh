@@ -11,11 +11,14 @@
 //     2^69-93, 2^128-173, 2^256-189): fold the high part down with a multiply by c.
 //       KIND_PM_ALIGNED  k == 64 L     (fold at a limb boundary)
 //       KIND_PM_SHIFT    k % 64 != 0   (fold at bit k with funnel shifts)
-//   * KIND_GENERIC: any odd p < 2^(64 L).  Montgomery reduction with ONE GUARD LIMB,
-//     R' = 2^(64 (L+1)), so that a lazily accumulated sum of up to 2^20 full products
-//     (< K p^2 < p R') reduces with a single REDC and one conditional subtraction.
-//     Constants ("table form") are pre-multiplied by R' on the host, data stays canonical:
-//     REDC(sum_i lambda_i R' * share_i) = sum_i lambda_i share_i mod p.
+//   * KIND_GENERIC: any odd p < 2^(64 L).
+//       - lazily accumulated sums of full products against per-call constants: Montgomery reduction
+//         with ONE GUARD LIMB, R' = 2^(64 (L+1)), so that up to 2^20 products (< K p^2 < p R') reduce
+//         with a single REDC and one conditional subtraction.  Constants ("table form") are
+//         pre-multiplied by R' on the host, data stays canonical:
+//         REDC(sum_i lambda_i R' * share_i) = sum_i lambda_i share_i mod p.
+//       - canonical * canonical and (L+1)-limb sums of 64-bit-constant products: Barrett reduction
+//         (quotient estimated from the top limbs with a precomputed reciprocal; at most 3 too small).
 //
 // Everything at the kernel boundary is a canonical residue in [0, p); Montgomery form never
 // leaves a kernel.  The arithmetic replaces the reference's Python-int `(a op b) % p` inside
@@ -48,6 +51,14 @@ struct FieldParams {
     u32 s;       // k % 64
     u32 L;       // 64-bit limbs
     u32 kind;
+    // GENERIC, Barrett reductions of canonical data (quotient estimate from the top bits, <= 3 too small):
+    u64 p2[5];   //   2p
+    u64 mus;     //   floor(2^(k+64) / p) - 2^64            (64-bit quotients: (L+1)-limb values)
+    u64 pn[4];   //   p << nsh: the modulus normalised to 64L bits
+    u64 pn2[5];  //   2 pn
+    u64 muf[4];  //   floor(2^(128L) / pn) - 2^(64L)        (full-width quotients: products)
+    u32 nsh;     //   64L - k
+    u32 pad_;
 };
 
 // 32-bit view of a little-endian u64 array (kernel parameters and tables are stored as u64)
@@ -195,6 +206,32 @@ FF_HD void mul_fresh(u32* r, const u32* a, const u32* b) {
     for (int i = 0; i < NA + NB + 2; i++) E[i] = O[i] = 0;
     mul_rows<NA, NB, 0>(E, O, a, b);
     add_n<NA + NB>(r, E, O);
+}
+
+// r[0..W) = a[0..NA) * b[0..NB) mod 2^(32 W): the partial products that land entirely at or above
+// column W are skipped, the one straddling it contributes its low half only.
+template <int NA, int NB, int W, int J>
+FF_HD void mul_lo_rows(u32* E, u32* O, const u32* a, const u32* b) {
+    if constexpr (J < NB && J < W) {
+        constexpr int FIT = W - 1 - J;                 // a[i], i < FIT: both halves of a[i]*b[J] lie below column W
+        constexpr int CNT = NA < FIT ? NA : FIT;
+        u32* X0 = (J % 2 == 0) ? E : O;                // accumulator of the even-i pairs of this row
+        u32* X1 = (J % 2 == 0) ? O : E;
+        if constexpr (CNT >= 1) mad_chain<CNT, ((CNT - 1) / 2) * 2 + 3, 0>(X0 + J, a, b[J]);
+        if constexpr (CNT >= 2) mad_chain<CNT, ((CNT - 2) / 2) * 2 + 1 + 3, 1>(X1 + J, a, b[J]);
+        if constexpr (CNT < NA) X0[W - 1] += a[CNT] * b[J];   // low half into the top column, carry irrelevant
+        mul_lo_rows<NA, NB, W, J + 1>(E, O, a, b);
+    }
+}
+
+template <int NA, int NB, int W>
+FF_HD void mul_lo(u32* r, const u32* a, const u32* b) {
+    static_assert(W <= NA + NB, "nothing to truncate");
+    u32 E[W + 3], O[W + 3];
+#pragma unroll
+    for (int i = 0; i < W + 3; i++) E[i] = O[i] = 0;
+    mul_lo_rows<NA, NB, W, 0>(E, O, a, b);
+    add_n<W>(r, E, O);
 }
 
 template <int N>
@@ -407,26 +444,70 @@ struct Fp {
         }
     }
 
-    // canonical * canonical -> canonical
-    static FF_HD void mul(u32* r, const u32* a, const u32* b, const FieldParams& f) {
-        if constexpr (KIND == KIND_GENERIC) {
-            u32 t[N];
-            dmul(t, a, b, f);                // ab / R'
-            dmul(r, t, as32(f.r2), f);       // ab
-        } else {
-            dmul(r, a, b, f);
+    // ---- generic: Barrett reductions of canonical data (no domain change) ---------------------
+    // d (N+1 limbs) in [0, 4m) -> [0, m) in r (N limbs); m2 = 2m (N+1 limbs)
+    static FF_HD void barrett_fix(u32* r, u32* d, const u32* m, const u32* m2) {
+        u32 t[N + 1];
+        u32 bw = sub_n<N + 1>(t, d, m2);
+        select_n<N + 1>(d, t, bw == 0);                 // now d < 2m
+        bw = sub_n<N>(t, d, m);
+        copy_n<N>(r, d);
+        select_n<N>(r, t, (d[N] != 0) | (bw == 0));
+    }
+
+    // x < 2^(k+64) in WSM limbs -> x mod p.  Quotient estimate q^ = x1 + floor(x1 * mus / 2^64) with
+    // x1 = floor(x / 2^k) < 2^64 and 2^64 + mus = floor(2^(k+64) / p):  q - 3 <= q^ <= q < 2^65.
+    static FF_HD void barrett_small(u32* r, const u32* x, const FieldParams& f) {
+        const u64 lo = get64(x, L - 1), hi = get64(x, L);
+        const u64 x1 = f.s ? ((lo >> f.s) | (hi << (64 - f.s))) : hi;
+        const u32 x32[2] = {(u32)x1, (u32)(x1 >> 32)};
+        u32 P[4], q[3];
+        mul_fresh<2, 2>(P, x32, as32(&f.mus));
+        q[2] = add_n<2>(q, x32, P + 2);
+        u32 T[N + 1], d[N + 1];
+        mul_lo<N, 3, N + 1>(T, as32(f.p), q);
+        sub_n<N + 1>(d, x, T);                          // x - q^ p in [0, 4p), exact mod 2^(32(N+1))
+        barrett_fix(r, d, as32(f.p), as32(f.p2));
+    }
+
+    // canonical a, b -> a b mod p.  The product is taken against b << nsh so that the modulus is the
+    // normalised pn = p << nsh (top bit of N limbs set): x' = a b 2^nsh < 2^(32N) pn, x1 = its high N
+    // limbs, q^ = x1 + floor(x1 * muf / 2^(32N)) with 2^(32N) + muf = floor(2^(64N) / pn);
+    // q' - 3 <= q^ <= q' = floor(x' / pn) < p.  r = (x' - q^ pn) mod pn, shifted back.
+    static FF_HD void barrett_mul(u32* r, const u32* a, const u32* b, const FieldParams& f) {
+        const u32 sh = f.nsh;                           // 0..63, warp-uniform
+        u32 bs[N];
+#pragma unroll
+        for (int i = L - 1; i >= 0; i--) {
+            const u64 cur = get64(b, i), below = i ? get64(b, i - 1) : 0;
+            set64(bs, i, sh ? ((cur << sh) | (below >> (64 - sh))) : cur);
+        }
+        u32 X[2 * N], H[2 * N], q[N];
+        mul_fresh<N, N>(X, a, bs);
+        mul_fresh<N, N>(H, X + N, as32(f.muf));
+        add_n<N>(q, X + N, H + N);
+        u32 T[N + 1], d[N + 1];
+        mul_lo<N, N, N + 1>(T, as32(f.pn), q);
+        sub_n<N + 1>(d, X, T);
+        u32 rs[N];
+        barrett_fix(rs, d, as32(f.pn), as32(f.pn2));
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            const u64 cur = get64(rs, i), above = i + 1 < L ? get64(rs, i + 1) : 0;
+            set64(r, i, sh ? ((cur >> sh) | (above << (64 - sh))) : cur);
         }
     }
 
-    // true reduction of an (L+1)-limb value x < 2^64 p  (WSM 32-bit limbs)
+    // canonical * canonical -> canonical
+    static FF_HD void mul(u32* r, const u32* a, const u32* b, const FieldParams& f) {
+        if constexpr (KIND == KIND_GENERIC) barrett_mul(r, a, b, f);
+        else dmul(r, a, b, f);
+    }
+
+    // true reduction of an (L+1)-limb value x < 2^(k+64)  (WSM 32-bit limbs)
     static FF_HD void reduce_small(u32* r, const u32* x, const FieldParams& f) {
-        if constexpr (KIND == KIND_GENERIC) {
-            u32 t[N];
-            redc<WSM>(t, x, f);              // x / R'
-            dmul(r, t, as32(f.r2), f);       // x
-        } else {
-            pm_reduce<WSM>(r, x, f);
-        }
+        if constexpr (KIND == KIND_GENERIC) barrett_small(r, x, f);
+        else pm_reduce<WSM>(r, x, f);
     }
 
     // r = a^e in the domain; e = little-endian 64-bit limbs, ebits = bit length of e (>= 0).

@@ -11,6 +11,49 @@ static inline int bit_length(const u64* x, int n) {
     return 0;
 }
 
+// q[0..5) = low 320 bits of floor(2^e / d), d = nd limbs (nd <= 4, d != 0): restoring division, bit by bit
+static inline void pow2_div(int e, const u64* d, int nd, u64* q) {
+    u64 rem[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; i++) q[i] = 0;
+    for (int bit = e; bit >= 0; bit--) {
+        for (int i = 4; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 63);   // rem < d <= 2^256: no overflow
+        rem[0] = (rem[0] << 1) | (bit == e ? 1u : 0u);
+        bool ge = true;   // rem >= d ?
+        for (int i = 4; i >= 0; i--) {
+            const u64 di = i < nd ? d[i] : 0;
+            if (rem[i] != di) {
+                ge = rem[i] > di;
+                break;
+            }
+        }
+        if (ge) {
+            u64 bw = 0;
+            for (int i = 0; i < 5; i++) {
+                const u64 di = i < nd ? d[i] : 0;
+                const u64 t = rem[i] - di - bw;
+                bw = (rem[i] < di + bw) || (bw && di == ~0ull);
+                rem[i] = t;
+            }
+            if (bit < 320) q[bit >> 6] |= 1ull << (bit & 63);
+        }
+    }
+}
+
+// Barrett constants of a GENERIC field (see FieldParams)
+static inline void barrett_constants(FieldParams& fp) {
+    const int L = (int)fp.L;
+    u64 q[5];
+    fp.nsh = 64u * L - fp.k;
+    for (int i = 0; i <= L; i++) fp.p2[i] = ((i < L ? fp.p[i] : 0) << 1) | (i ? fp.p[i - 1] >> 63 : 0);
+    pow2_div((int)fp.k + 64, fp.p, L, q);           // 2^64 <= quotient < 2^65
+    fp.mus = q[0];
+    for (int i = L - 1; i >= 0; i--)
+        fp.pn[i] = fp.nsh ? ((fp.p[i] << fp.nsh) | (i ? fp.p[i - 1] >> (64 - fp.nsh) : 0)) : fp.p[i];
+    for (int i = 0; i <= L; i++) fp.pn2[i] = ((i < L ? fp.pn[i] : 0) << 1) | (i ? fp.pn[i - 1] >> 63 : 0);
+    pow2_div(128 * L, fp.pn, L, q);                 // 2^(64L) <= quotient < 2^(64L+1)
+    for (int i = 0; i < L; i++) fp.muf[i] = q[i];
+}
+
 template <int LL>
 static inline void montgomery_constants(FieldParams& fp) {
     typedef Fp<LL, KIND_GENERIC> F;
@@ -47,6 +90,7 @@ static inline void field_params_init(const uint64_t* modulus, int nlimbs, FieldP
     u64 inv = fp.p[0];   // Newton iteration: p^-1 mod 2^64
     for (int i = 0; i < 6; i++) inv *= 2 - fp.p[0] * inv;
     fp.pinv = 0 - inv;
+    barrett_constants(fp);
     switch (L) {
         case 1: montgomery_constants<1>(fp); break;
         case 2: montgomery_constants<2>(fp); break;

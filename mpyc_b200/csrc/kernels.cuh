@@ -243,8 +243,9 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 
 // ---------------------------------------------------------------------------------------
 // K2: Shamir share generation.  M[0] = secrets, M[j] = coefficient row j-1.
-//   small: table entry (i, j) is the plain integer (i+1)^j < 2^59 (pseudo-Mersenne fields):
-//          acc (L+1 limbs) = M[0] + sum_j M[j] * v  -> one fold per share
+//   small: table entry (i, j) is the plain integer (i+1)^j < 2^59:
+//          acc (L+1 limbs) = M[0] + sum_j M[j] * v  -> one fold (pseudo-Mersenne) or one 64-bit-quotient
+//          Barrett step (generic fields) per share
 //   full : table entry is a full field element in table form; acc (2L+1 limbs), one reduction
 // ---------------------------------------------------------------------------------------
 
@@ -267,7 +268,6 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
 __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], u64* shares,
                                               size_t sstride, int m, const u64* tab, size_t limb_off) {
-    static_assert(FULL || KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
     for (int i = 0; i < m; i++) {
@@ -286,7 +286,7 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
                 acc[N] = acc[N + 1] = 0;
 #pragma unroll
                 for (int j = 1; j < TP1; j++) F::mac_const(acc, M[j] + e * N, tab[i * TP1 + j]);
-                if constexpr (TP1 > 1) F::template pm_reduce<F::WSM>(r + e * N, acc, f);
+                if constexpr (TP1 > 1) F::reduce_small(r + e * N, acc, f);
                 else copy_n<N>(r + e * N, acc);
             }
         }
@@ -519,7 +519,7 @@ __device__ __forceinline__ void recombine_items(const FieldParams& f, const RowP
     }
 }
 
-// Small-coefficient form (pseudo-Mersenne fields): when every lambda has a signed representative of
+// Small-coefficient form: when every lambda has a signed representative of
 // magnitude < 2^58 -- always the case for x-coordinates 1..k at 0, where lambda_i = (-1)^(i-1) C(k,i),
 // e.g. the 2t+1 = m shares of a resharing (runtime.py:672-680) -- the k full-width products become
 // multiplications by 64-bit constants.  tab[2*(r*k+i)] = |lambda|, tab[2*(r*k+i)+1] = sign.
@@ -527,7 +527,6 @@ template <int L, int KIND, int E, bool VEC, int U>
 __device__ __forceinline__ void recombine_items_small(const FieldParams& f, const RowPtrs& rows, int k, int width,
                                                       const u64* tab, u64* out, size_t ostride, size_t limb_off,
                                                       size_t limb_step) {
-    static_assert(KIND != KIND_GENERIC, "64-bit-constant tables need a pseudo-Mersenne field");
     constexpr int RB = (U * E * L <= 4) ? 4 : 2;
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
@@ -569,8 +568,8 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 u32 rp[N], rn[N];
-                F::template pm_reduce<F::WSM>(rp, pos[u][e], f);
-                F::template pm_reduce<F::WSM>(rn, neg[u][e], f);
+                F::reduce_small(rp, pos[u][e], f);
+                F::reduce_small(rn, neg[u][e], f);
                 F::sub(res + e * N, rp, rn, f);
             }
             store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);

@@ -23,7 +23,7 @@ struct Launch {
                              cudaStream_t st);
     static cudaError_t split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets, u64* shares,
                                  size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st);
-    // small: 64-bit signed-magnitude lambda table (pseudo-Mersenne fields only)
+    // small: 64-bit signed-magnitude lambda table
     static cudaError_t recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width, const u64* gtab,
                                  u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st);
     static cudaError_t prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,

@@ -120,12 +120,9 @@ static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u
         KIND_SWITCH(fp.kind, M)
 #undef M
     } else {
-        if (fp.kind == KIND_PM_ALIGNED)
-            return split_k<L, KIND_PM_ALIGNED, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab,
-                                                           tab_bytes, st);
-        if (fp.kind == KIND_PM_SHIFT)
-            return split_k<L, KIND_PM_SHIFT, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab,
-                                                         tab_bytes, st);
+#define M(K) return split_k<L, K, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
+        KIND_SWITCH(fp.kind, M)
+#undef M
     }
     return cudaErrorInvalidValue;
 }
@@ -192,10 +189,11 @@ cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaK
             }                                                                                                      \
             return cudaErrorInvalidValue;                                                                          \
         }                                                                                                          \
-        if (fp.kind == KIND_PM_ALIGNED)                                                                            \
-            return split_gen_k<L, KIND_PM_ALIGNED, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
-        if (fp.kind == KIND_PM_SHIFT)                                                                              \
-            return split_gen_k<L, KIND_PM_SHIFT, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+        switch (fp.kind) {                                                                                         \
+            case KIND_GENERIC: return split_gen_k<L, KIND_GENERIC, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+            case KIND_PM_ALIGNED: return split_gen_k<L, KIND_PM_ALIGNED, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+            case KIND_PM_SHIFT: return split_gen_k<L, KIND_PM_SHIFT, false, V>(fp, key, secrets, shares, sstride, n, t, m, gtab, tab_bytes, st); \
+        }                                                                                                          \
         return cudaErrorInvalidValue;                                                                              \
     } while (0)
     if constexpr (L != 3) {
@@ -214,13 +212,15 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
     for (int i = 0; i < k; i++) vec = vec && aligned32(rows.p[i]);
     constexpr int EV = VecItem<L>::E;
     if (small) {
-        if (fp.kind == KIND_GENERIC) return cudaErrorInvalidValue;
 #define SM(VECF, ITEMS)                                                                                                  \
     do {                                                                                                                 \
         if (fp.kind == KIND_PM_ALIGNED)                                                                                  \
             return launch_kernel(k_recombine_small<L, KIND_PM_ALIGNED, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width,  \
                                  gtab, tab_bytes, out, ostride, n);                                                      \
-        return launch_kernel(k_recombine_small<L, KIND_PM_SHIFT, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width, gtab,  \
+        if (fp.kind == KIND_PM_SHIFT)                                                                                    \
+            return launch_kernel(k_recombine_small<L, KIND_PM_SHIFT, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width,    \
+                                 gtab, tab_bytes, out, ostride, n);                                                      \
+        return launch_kernel(k_recombine_small<L, KIND_GENERIC, VECF>, ITEMS, tab_bytes, st, fp, rows, k, width, gtab,   \
                              tab_bytes, out, ostride, n);                                                                \
     } while (0)
         if constexpr (L != 3) {

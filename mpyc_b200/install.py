@@ -77,9 +77,11 @@ def _install_finfields(finfields_module, min_size):
 _saved_ff = {}
 
 
-def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256):
+def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256,
+            limb_wire=False):
     """Patch `mpyc.thresha` (or the module passed in); with finfields_module also the batched
-    inverse/pow/sqrt/is_sqr of PrimeFieldArray.  Returns the list of patched names."""
+    inverse/pow/sqrt/is_sqr of PrimeFieldArray.  limb_wire=True: shares travel between parties as limb
+    buffers (mpyc_b200.wire; every party must run mpyc_b200).  Returns the list of patched names."""
     if thresha_module is None:
         import mpyc.thresha as thresha_module
     if _saved:
@@ -87,6 +89,7 @@ def install(thresha_module=None, strict=False, device=0, finfields_module=None, 
     if finfields_module is not None:
         _install_finfields(finfields_module, finfields_min_size)
     engine.device = device
+    engine.limb_wire = bool(limb_wire)
     for name in _NAMES:
         theirs = getattr(thresha_module, name)
         _saved[name] = (thresha_module, theirs)
@@ -103,6 +106,7 @@ def uninstall():
     for name, (module, theirs) in list(_saved.items()):
         setattr(module, name, theirs)
     _saved.clear()
+    engine.limb_wire = False
     if _saved_ff:
         cls = _saved_ff.pop('cls')
         for name, member in _saved_ff.items():

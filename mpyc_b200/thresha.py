@@ -31,12 +31,15 @@ import numpy as np
 from mpyc_b200 import _cabi, codec
 from mpyc_b200._cabi import lib, check
 from mpyc_b200.field import context_of_field
+from mpyc_b200.wire import ShareRow, ShareRows
 
 __all__ = ['random_split', 'recombine', 'pseudorandom_share', 'pseudorandom_share_zero',
            'np_random_split', 'np_recombine', 'np_pseudorandom_share', 'np_pseudorandom_share_0', 'PRF']
 
 coefficient_source = None     # callable(order, count) -> sequence of ints, or None (CSPRNG)
 device = 0                    # CUDA device ordinal used by the host-buffer entry points
+limb_wire = False             # True: np_random_split returns limb-backed ShareRows (mpyc_b200.wire) that
+                              # pickle as fixed-width bytes and feed np_recombine without becoming ints
 
 
 def _ptr(a):
@@ -50,6 +53,8 @@ def _values_of(field, s):
         s = s.value
     if isinstance(s, np.ndarray):
         return s.reshape(-1)
+    if isinstance(s, ShareRow):
+        return s.__array__()
     s = list(s)
     if s and isinstance(s[0], field):
         s = [a.value for a in s]
@@ -126,6 +131,8 @@ def np_random_split(field, s, t, m):
         C = _draw(ctx, field.order, t * n)
         C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
         shares = _split_limbs(ctx, sec, C, t, m)
+    if limb_wire:
+        return ShareRows(ctx, shares, type(field.modulus) if ctx.binary else None)
     out = np.empty((m, n), dtype=object)
     for i in range(m):
         out[i] = _wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))
@@ -175,7 +182,8 @@ def np_recombine(field, points, x_rs=0):
     xs, shares = zip(*points)
     single = not isinstance(x_rs, list)
     pts = [x_rs] if single else x_rs
-    rows = [codec.ints_to_limbs(_values_of(field, sh), ctx) for sh in shares]
+    rows = [sh.limbs if isinstance(sh, ShareRow) and sh.ctx is ctx else codec.ints_to_limbs(_values_of(field, sh), ctx)
+            for sh in shares]
     out = _recombine_limbs(ctx, xs, rows, pts)
     n = rows[0].shape[0]
     vals = np.empty((len(pts), n), dtype=object)

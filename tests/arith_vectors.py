@@ -36,13 +36,13 @@ def commands(p, lazy_sizes=(1, 2, 3, 7, 17, 64, 1000)):
             terms = [(p - 1, p - 1) if mode == 'max' else (rnd.randrange(p), rnd.randrange(p)) for _ in range(K)]
             lines.append(f'lazy {K} ' + ' '.join(f'{a:x} {b:x}' for a, b in terms))
             want.append(sum(a * b for a, b in terms) % p)
-    if expected_kind(p):
-        for K in (0, 1, 2, 8):
-            for mode in ('max', 'rand'):
-                s = p - 1 if mode == 'max' else rnd.randrange(p)
-                terms = [(p - 1, (1 << 59) - 1) if mode == 'max' else (rnd.randrange(p), rnd.randrange(1 << 59)) for _ in range(K)]
-                lines.append(f'small {K} {s:x} ' + ' '.join(f'{a:x} {v:x}' for a, v in terms))
-                want.append((s + sum(a * v for a, v in terms)) % p)
+    for K in (0, 1, 2, 8):
+        for mode in ('max', 'rand', 'rand32'):
+            s = p - 1 if mode == 'max' else rnd.randrange(p)
+            vmax = 1 << (32 if mode == 'rand32' else 59)
+            terms = [(p - 1, (1 << 59) - 1) if mode == 'max' else (rnd.randrange(p), rnd.randrange(vmax)) for _ in range(K)]
+            lines.append(f'small {K} {s:x} ' + ' '.join(f'{a:x} {v:x}' for a, v in terms))
+            want.append((s + sum(a * v for a, v in terms)) % p)
     for x in [0, 1, p, p - 1, (1 << (k + 64)) - 1, (p << 64) - 1] + [rnd.randrange(1 << (k + 64)) for _ in range(16)]:
         lines.append(f'redsmall {x:x}')
         want.append(x % p)

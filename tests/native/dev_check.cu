@@ -41,13 +41,11 @@ __global__ void run(FieldParams fp, const Cmd* cmd, u32* out) {
         }
         F::finish(r, acc, fp);
     } else if (c.op == 5) {
-        if constexpr (K != KIND_GENERIC) {
-            u32 acc[F::WSM];
-            copy_n<N>(acc, c.x);
-            acc[N] = acc[N + 1] = 0;
-            for (int i = 0; i < c.cnt; i++) F::mac_const(acc, c.a[i], (u64)c.b[i][0] | ((u64)c.b[i][1] << 32));
-            F::template pm_reduce<F::WSM>(r, acc, fp);
-        }
+        u32 acc[F::WSM];
+        copy_n<N>(acc, c.x);
+        acc[N] = acc[N + 1] = 0;
+        for (int i = 0; i < c.cnt; i++) F::mac_const(acc, c.a[i], (u64)c.b[i][0] | ((u64)c.b[i][1] << 32));
+        F::reduce_small(r, acc, fp);
     } else if (c.op == 6) {
         F::reduce_small(r, c.x, fp);
     } else if (c.op == 7) {
@@ -148,7 +146,6 @@ int main() {
                 in >> t; parse_hex(t, c.a[i], N);
                 in >> t; parse_hex(t, c.b[i], 2);
             }
-            if (fp.kind == KIND_GENERIC) { printf("n/a\n"); continue; }
         } else if (cmd == "redsmall") {
             c.op = 6;
             in >> t; parse_hex(t, c.x, N + 2);

@@ -4,7 +4,7 @@
 //   field <p>                         -> prints "kind L k"
 //   mul|add|sub <a> <b> ; neg <a>
 //   lazy <K> a1 b1 ... aK bK          -> sum a_i*b_i mod p via mac (b in table form) + finish
-//   small <K> <s> a1 v1 ... aK vK     -> (s + sum a_i*v_i) mod p via mac_1 + pm_reduce<L+1> (PM fields)
+//   small <K> <s> a1 v1 ... aK vK     -> (s + sum a_i*v_i) mod p via mac_const + reduce_small
 //   redsmall <x>                      -> x mod p for x < 2^(k+64) via reduce_small
 //   pow <a> <e>
 // TEST INFRASTRUCTURE: not part of the shipped library.
@@ -78,7 +78,6 @@ static std::string run(const std::string& cmd, std::istringstream& in) {
         return to_hex(r, N);
     }
     if (cmd == "small") {
-        if (K == KIND_GENERIC) return "n/a";
         int cnt; in >> cnt;
         u32 acc[F::WSM];
         in >> t; parse_hex(t, acc, N);
@@ -89,7 +88,7 @@ static std::string run(const std::string& cmd, std::istringstream& in) {
             in >> t; parse_hex(t, v, 2);
             F::mac_const(acc, a, (u64)v[0] | ((u64)v[1] << 32));
         }
-        if constexpr (K != KIND_GENERIC) F::template pm_reduce<F::WSM>(r, acc, fp);
+        F::reduce_small(r, acc, fp);
         return to_hex(r, N);
     }
     if (cmd == "redsmall") {

@@ -75,3 +75,42 @@ def test_secure_multiplication_gf256():
         sc = [thresha.np_recombine(F, [(i + 1, dealt[i][j]) for i in range(2 * t + 1)]) for j in range(m)]
         opened = thresha.np_recombine(F, [(2, sc[1].value), (3, sc[2].value)])
         assert [int(v) for v in opened.value] == orc.bf_mul(283, a, b)
+
+
+@pytest.mark.parametrize('p,m,t', [(2**61 - 1, 3, 1), (2**69 - 93, 3, 1), (2**128 - 173, 5, 2), (2**256 - 189, 7, 3),
+                                   (9409569905028393239, 3, 1)])
+def test_secure_multiplication_over_the_limb_wire(p, m, t, monkeypatch):
+    """Same protocol with thresha.limb_wire: rows are ShareRow objects, every row that crosses to another
+    party goes through pickle.dumps / pickle.loads as in runtime.py:655-656,665,676, and np_recombine
+    consumes the unpickled limbs directly.  Results equal the object-array path bit for bit."""
+    import pickle
+    from mpyc_b200 import wire
+    F = fakefield.make_prime_field(p)
+    rnd = random.Random(p % 1000 + m + 1)
+    n = 301
+    a = [rnd.randrange(p) for _ in range(n)]
+    b = [rnd.randrange(p) for _ in range(n)]
+    seq = iter(rnd.randrange(p) for _ in range(10**7))
+    monkeypatch.setattr(thresha, 'coefficient_source', lambda order, count: [next(seq) for _ in range(count)])
+
+    def run(limb_wire):
+        nonlocal seq
+        seq = iter(random.Random(99).randrange(p) for _ in range(10**7))
+        monkeypatch.setattr(thresha, 'limb_wire', limb_wire)
+        ship = (lambda row: pickle.loads(pickle.dumps(row))) if limb_wire else (lambda row: row)
+        sa = [F.array(ship(r), check=False) for r in thresha.np_random_split(F, np.array(a, dtype=object), t, m)]
+        sb = [F.array(ship(r), check=False) for r in thresha.np_random_split(F, np.array(b, dtype=object), t, m)]
+        prod = [F.array(sa[i].value * sb[i].value) for i in range(m)]
+        k = 2 * t + 1
+        dealt = [thresha.np_random_split(F, prod[i].value, t, m) for i in range(k)]
+        if limb_wire:
+            assert all(isinstance(dealt[i][j], wire.ShareRow) for i in range(k) for j in range(m))
+        sc = [thresha.np_recombine(F, [(i + 1, dealt[i][j] if i == j else ship(dealt[i][j])) for i in range(k)])
+              for j in range(m)]
+        return [s.value.tolist() for s in sc]
+
+    plain, limbs = run(False), run(True)
+    assert plain == limbs
+    monkeypatch.setattr(thresha, 'limb_wire', False)
+    sc = [F.array(np.array(v, dtype=object), check=False) for v in limbs]
+    assert _open(F, sc, t, 0) == [x * y % p for x, y in zip(a, b)]
