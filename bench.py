@@ -232,8 +232,25 @@ def dropin_rate(w, device, n=200_000):
     out = thresha.np_recombine(Field, [(i + 1, sh[i]) for i in range(k)])
     dt = time.perf_counter() - t0
     assert out.value.tolist() == s.tolist()
+    # limb wire (mpyc_b200.wire): rows stay limb buffers; as in runtime.py:655-665 every row is pickled for its
+    # peer and the k received rows are unpickled before np_recombine -- pickling is INSIDE this timed region
+    import pickle
+    thresha.limb_wire = True
+    try:
+        t0 = time.perf_counter()
+        sh = thresha.np_random_split(Field, s, t, m)
+        sent = [pickle.dumps(row) for row in sh]
+        out = thresha.np_recombine(Field, [(i + 1, pickle.loads(sent[i])) for i in range(k)])
+        dt_lw = time.perf_counter() - t0
+    finally:
+        thresha.limb_wire = False
+    assert out.value.tolist() == s.tolist()
     return {'value': n / dt, 'unit': 'pairs/s', 'n': n,
-            'path': 'mpyc_b200.thresha.np_random_split + np_recombine on dtype=object arrays (what runtime.py calls)'}
+            'path': 'mpyc_b200.thresha.np_random_split + np_recombine on dtype=object arrays (what runtime.py calls)',
+            'limb_wire': {'value': n / dt_lw, 'unit': 'pairs/s',
+                          'path': 'same calls with install(limb_wire=True): ShareRow rows, pickle.dumps of all m rows and '
+                                  'pickle.loads of the k recombined ones inside the timed region',
+                          'wire_bytes_per_row': len(sent[0])}}
 
 
 def run_gpu_arm(a, w):

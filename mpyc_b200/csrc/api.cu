@@ -80,6 +80,13 @@ int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem) {
     return (int)std::min<size_t>(need, (size_t)w);
 }
 
+int mpyc_sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return 148;
+    return sms > 0 ? sms : 148;
+}
+
 // ---------------------------------------------------------------------------------------
 // field handle
 // ---------------------------------------------------------------------------------------
@@ -498,7 +505,24 @@ MPYC_API int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d
     u64 e[4];
     wide_copy(e, f->fp.p, 4);
     wide_sub_small(e, 4, 2);   // p - 2
-    return pow_impl(f, d_a, e, 4, 0, true, d_out, nullptr, n, st);
+    if (d_a == d_out || n == 0) return pow_impl(f, d_a, e, 4, 0, true, d_out, nullptr, n, st);   // in place: per-element Fermat
+    // Montgomery's trick: running products in d_out, one exponentiation per batch (k_inv_batch)
+    ExpParams ex;
+    memset(&ex, 0, sizeof ex);
+    for (int i = 0; i < 4; i++) ex.e[i] = e[i];
+    ex.ebits = bit_length(ex.e, 8);
+    ZeroFlag zf;
+    CU(cudaMalloc(&zf.d, sizeof(int)));
+    CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+    int rc = with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::inv_batch(f->fp, ex, (const u64*)d_a, (u64*)d_out, zf.d, n, st), "ff_inv launch");
+    });
+    if (rc != MPYC_B200_OK) return rc;
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, zf.d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return flag ? fail(MPYC_B200_EZERODIV, "inverse of zero") : MPYC_B200_OK;
 }
 
 MPYC_API int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int inverse, void* d_out, size_t n, void* stream) {

@@ -242,6 +242,74 @@ k_pow(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
+// K1b': batched inverse (PrimeFieldArray._reciprocal, finfields.py:1416-1422) with Montgomery's trick:
+// thread `tid` of T owns the B elements tid, tid+T, ..., tid+(B-1)T (coalesced across the warp), writes
+// their running products into `out`, inverts the last one with ONE Fermat exponentiation and walks back:
+//   inv(x_b) = inv(x_0..x_b) * (x_0..x_{b-1}),   inv(x_0..x_{b-1}) = inv(x_0..x_b) * x_b
+// i.e. 3 multiplications per element + 1/B of an exponentiation (~1.5 bits(p) multiplications) instead of
+// a whole one.  Zeros are skipped in the products (the result for them is 0) and reported through
+// zero_flag (the reference raises ZeroDivisionError, gmpy.py:192-213).  a and out must not alias.
+// ---------------------------------------------------------------------------------------
+
+template <int L>
+__device__ __forceinline__ void load_plain(u32* v, const u64* p) {   // coherent loads: `out` is re-read
+#pragma unroll
+    for (int q = 0; q < L; q++) {
+        const u64 w = p[q];
+        v[2 * q] = (u32)w;
+        v[2 * q + 1] = (u32)(w >> 32);
+    }
+}
+
+template <int L, int KIND>
+__global__ void MPYC_LB
+k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, int* zero_flag, size_t n, size_t T, int B) {
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < T; tid += nth) {
+        u32 acc[N], x[N];
+        zero_n<N>(acc);
+        acc[0] = 1;
+        int cnt = 0;
+        bool saw_zero = false;
+        for (int b = 0; b < B; b++) {
+            const size_t h = tid + (size_t)b * T;
+            if (h >= n) break;
+            load_limbs<L, false>(x, a + h * L);
+            if (is_zero_n<N>(x)) {
+                saw_zero = true;
+                x[0] = 1;
+            }
+            F::mul(acc, acc, x, f);
+            store_limbs<L, false>(out + h * L, acc);
+            cnt = b + 1;
+        }
+        if (saw_zero) *zero_flag = 1;
+        u32 inv[N];
+        F::to_dom(inv, acc, f);
+        F::dpow_uniform(inv, inv, ex.e, ex.ebits, f);
+        F::from_dom(inv, inv, f);
+        for (int b = cnt - 1; b >= 0; b--) {
+            const size_t h = tid + (size_t)b * T;
+            u32 prev[N], r[N];
+            load_limbs<L, false>(x, a + h * L);
+            const bool z = is_zero_n<N>(x);
+            if (z) x[0] = 1;
+            if (b > 0) {
+                load_plain<L>(prev, out + (h - T) * L);
+                F::mul(r, inv, prev, f);
+            } else {
+                copy_n<N>(r, inv);
+            }
+            F::mul(inv, inv, x, f);
+            if (z) zero_n<N>(r);
+            store_limbs<L, false>(out + h * L, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K2: Shamir share generation.  M[0] = secrets, M[j] = coefficient row j-1.
 //   small: table entry (i, j) is the plain integer (i+1)^j < 2^59:
 //          acc (L+1 limbs) = M[0] + sum_j M[j] * v  -> one fold (pseudo-Mersenne) or one 64-bit-quotient

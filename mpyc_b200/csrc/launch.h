@@ -18,6 +18,9 @@ struct Launch {
     // mode 0: out = a^e; mode 1: out8 = (a^e != p-1)
     static cudaError_t pow(const FieldParams& fp, const ExpParams& ex, int mode, const u64* a, u64* out,
                            unsigned char* out8, int* zero_flag, size_t n, cudaStream_t st);
+    // out[h] = a[h]^-1 (0 for a[h] == 0, reported in zero_flag); ex = p - 2; a and out must not alias
+    static cudaError_t inv_batch(const FieldParams& fp, const ExpParams& ex, const u64* a, u64* out, int* zero_flag,
+                                 size_t n, cudaStream_t st);
     static cudaError_t split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
                              u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st);

@@ -1,6 +1,7 @@
 // Definitions of Launch<L>: picks the kernel instantiation (reduction kind, vector/scalar memory
 // path, compile-time t+1) and launches it on a persistent grid.
 #pragma once
+#include <stdlib.h>
 #include "launch.h"
 
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
@@ -77,6 +78,26 @@ cudaError_t Launch<L>::pow(const FieldParams& fp, const ExpParams& ex, int mode,
 #define M(K)                                                                                              \
     if (mode == 0) return launch_kernel(k_pow<L, K, 0>, n, 0, st, fp, ex, a, out, out8, zero_flag, n);    \
     return launch_kernel(k_pow<L, K, 1>, n, 0, st, fp, ex, a, out, out8, zero_flag, n)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+int mpyc_sm_count();
+
+template <int L>
+cudaError_t Launch<L>::inv_batch(const FieldParams& fp, const ExpParams& ex, const u64* a, u64* out, int* zero_flag,
+                                 size_t n, cudaStream_t st) {
+    // batch length: as long as possible while every SM still gets >= 1024 threads; <= 32
+    int B = 1;
+    const size_t per_wave = (size_t)mpyc_sm_count() * 1024;
+    while (B < 32 && n / (2 * (size_t)B) >= per_wave) B *= 2;
+    if (const char* forced = getenv("MPYC_B200_INV_BATCH")) {   // tests: exercise long batches on small arrays
+        const int v = atoi(forced);
+        if (v >= 1 && v <= 1024) B = v;
+    }
+    const size_t T = (n + B - 1) / B;
+#define M(K) return launch_kernel(k_inv_batch<L, K>, T, 0, st, fp, ex, a, out, zero_flag, n, T, B)
     KIND_SWITCH(fp.kind, M)
 #undef M
     return cudaErrorInvalidValue;

@@ -471,3 +471,32 @@ def test_finfields_batched_hooks():
         assert ff.matmul(cls, A, B).tolist() == want
         assert ff.matmul(cls, A[0], B).tolist() == want[0]
         assert ff.matmul(cls, A, B[:, 0]).tolist() == [row[0] for row in want]
+
+
+@pytest.mark.parametrize('p', [2**61 - 1, 2**64 - 189, 2**69 - 93, 2**128 - 173, 2**192 - 237, 2**256 - 189,
+                               9409569905028393239, 0x800000000000000000000000000000fb, 101],
+                         ids=lambda p: f'p{p.bit_length()}')
+@pytest.mark.parametrize('batch', [1, 2, 7, 32])
+def test_batched_inverse_montgomery_trick(p, batch, monkeypatch):
+    """k_inv_batch (Montgomery's trick, one Fermat exponentiation per `batch` elements) equals the oracle's
+    per-element inverse for every batch length, ragged sizes, and reports zeros like gmpy2.invert."""
+    monkeypatch.setenv('MPYC_B200_INV_BATCH', str(batch))
+    ctx = mpyc_b200.context_for(p)
+    rnd = random.Random(p % 977 + batch)
+    for n in (1, 2, 31, 257, 1000):
+        a = [1, p - 1][:n] + [rnd.randrange(1, p) for _ in range(max(0, n - 2))]
+        assert DeviceArray.from_ints(ctx, a).reciprocal().to_ints().tolist() == orc.ff_inv(p, a)
+    z = [rnd.randrange(1, p) for _ in range(100)]
+    z[37] = 0
+    with pytest.raises(ZeroDivisionError):
+        DeviceArray.from_ints(ctx, z).reciprocal()
+
+
+def test_batched_inverse_large_property():
+    """n = 2^21 (the launcher picks batch 8 on a 148-SM part): a * a^-1 == 1 everywhere, checked on the device."""
+    for p in (2**128 - 173, 9409569905028393239):
+        ctx = mpyc_b200.context_for(p)
+        n = (1 << 21) + 5
+        A = DeviceArray.random(ctx, n, seed=5, stream_id=3)     # a zero among 2^21 random residues: probability ~0
+        limbs = (A * A.reciprocal()).to_limbs()
+        assert (limbs[:, 0] == 1).all() and (limbs[:, 1:] == 0).all()
