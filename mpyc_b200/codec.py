@@ -21,7 +21,7 @@ def ints_to_limbs(values, ctx, reduce=True):
         return np.array(flat, dtype=np.uint8)
     L, p = ctx.nlimbs, ctx.modulus
     if isinstance(values, np.ndarray):
-        values = values.reshape(-1).tolist()
+        values = values.reshape(-1).tolist()     # ~10-20 ns per element; PySequence_Fast needs a list/tuple
     buf = _pycodec.pack(values, 8 * L, p)        # reduces out-of-range values mod p
     return np.frombuffer(buf, dtype='<u8').reshape(-1, L)
 
@@ -34,9 +34,9 @@ def limbs_to_ints(limbs, ctx):
         return out
     limbs = np.ascontiguousarray(limbs, dtype=np.uint64)
     n, L = limbs.shape
-    out = np.empty(n, dtype=object)
+    out = np.empty(n, dtype=object)          # freshly allocated, C-contiguous, n object slots (all None)
     if n:
-        out[:] = _pycodec.unpack(limbs, 8 * L)
+        _pycodec.unpack_into(limbs, 8 * L, out.ctypes.data)
     return out
 
 

@@ -322,6 +322,9 @@ k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, in
 #ifndef MPYC_SPLIT_U
 #define MPYC_SPLIT_U 1
 #endif
+#ifndef MPYC_SPLIT_MU
+#define MPYC_SPLIT_MU 1
+#endif
 #ifndef MPYC_REC_U1
 #define MPYC_REC_U1 2
 #endif
@@ -338,6 +341,8 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
                                               size_t sstride, int m, const u64* tab, size_t limb_off) {
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
+    constexpr int MU = MPYC_SPLIT_MU;   // shares computed per trip of the party loop
+#pragma unroll MU
     for (int i = 0; i < m; i++) {
         u32 r[E * N];
 #pragma unroll
@@ -599,14 +604,11 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
     for (int r = 0; r < width; r++) {
-        u32 pos[U][E][F::WSM], neg[U][E][F::WSM];
+        u32 acc[U][E][F::WSM];
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                zero_n<F::WSM>(pos[u][e]);
-                zero_n<F::WSM>(neg[u][e]);
-            }
+            for (int e = 0; e < E; e++) zero_n<F::WSM>(acc[u][e]);
         for (int i0 = 0; i0 < k; i0 += RB) {
             u32 x[RB][U][E * N];
 #pragma unroll
@@ -625,8 +627,12 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
                     for (int u = 0; u < U; u++)
 #pragma unroll
                         for (int e = 0; e < E; e++) {
-                            if (minus) F::mac_const(neg[u][e], x[b][u] + e * N, mag);
-                            else F::mac_const(pos[u][e], x[b][u] + e * N, mag);
+                            // -|lambda| * share = |lambda| * (p - share): one accumulator, one reduction
+                            // (p - 0 = p is a fine representative of 0: the sum stays below k 2^58 p)
+                            u32 y[N];
+                            if (minus) sub_n<N>(y, as32(f.p), x[b][u] + e * N);
+                            else copy_n<N>(y, x[b][u] + e * N);
+                            F::mac_const(acc[u][e], y, mag);
                         }
                 }
         }
@@ -634,12 +640,7 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
         for (int u = 0; u < U; u++) {
             u32 res[E * N];
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                u32 rp[N], rn[N];
-                F::reduce_small(rp, pos[u][e], f);
-                F::reduce_small(rn, neg[u][e], f);
-                F::sub(res + e * N, rp, rn, f);
-            }
+            for (int e = 0; e < E; e++) F::reduce_small(res + e * N, acc[u][e], f);
             store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);
         }
     }
