@@ -177,6 +177,94 @@ k_gf_split(unsigned poly, GfTab tab, const unsigned char* __restrict__ secrets, 
     }
 }
 
+// ---- split, vector form: 16 bytes (two packed words) per thread and access, t <= GF_HORNER_T -------------
+// Horner in the point: share_i = s + x_i (c_1 + x_i (c_2 + ... x_i c_t)), x_i = i+1.  Multiplying by the
+// warp-uniform constant x_i needs only bitlen(x_i)-1 xtime steps (none for party 1, one for parties 2 and 3),
+// so the demo shape m=3, t=1 costs 2 xtime steps per 16 elements' worth of words and the kernel streams.
+#define GF_HORNER_T 4
+
+struct __align__(16) GfW2 {
+    unsigned long long a, b;
+};
+__device__ __forceinline__ GfW2 gf_ld16(const unsigned char* p) {
+    GfW2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.a), "=l"(v.b) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void gf_st16(unsigned char* p, GfW2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.a), "l"(v.b) : "memory");
+}
+// v * x for a warp-uniform constant x of nb significant bits (1 <= nb <= 8)
+__device__ __forceinline__ GfW2 gf_mulc16(GfW2 v, unsigned x, int nb, unsigned long long red) {
+    GfW2 acc = {0ull, 0ull};
+    for (int b = 0; b < nb; b++) {
+        if ((x >> b) & 1u) {
+            acc.a ^= v.a;
+            acc.b ^= v.b;
+        }
+        if (b + 1 < nb) {
+            v.a = gf_xtime8(v.a, red);
+            v.b = gf_xtime8(v.b, red);
+        }
+    }
+    return acc;
+}
+
+template <int T>
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_split_vec(unsigned poly, const unsigned char* __restrict__ secrets, const unsigned char* __restrict__ coeffs,
+               size_t cstride, unsigned char* __restrict__ shares, size_t sstride, size_t ngroups, int m) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const unsigned long long red = poly & 0xFFu;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += nth) {
+        const GfW2 s0 = gf_ld16(secrets + 16 * g);
+        GfW2 c[T > 0 ? T : 1];
+#pragma unroll
+        for (int j = 0; j < T; j++) c[j] = gf_ld16(coeffs + (size_t)j * cstride + 16 * g);
+        for (int i = 0; i < m; i++) {
+            const unsigned x = (unsigned)(i + 1);
+            const int nb = 32 - __clz(x);
+            GfW2 acc = s0;
+            if constexpr (T > 0) {
+                acc = c[T - 1];
+#pragma unroll
+                for (int j = T - 1; j >= 0; j--) {
+                    acc = gf_mulc16(acc, x, nb, red);
+                    const GfW2 nxt = j > 0 ? c[j - 1] : s0;
+                    acc.a ^= nxt.a;
+                    acc.b ^= nxt.b;
+                }
+            }
+            gf_st16(shares + (size_t)i * sstride + 16 * g, acc);
+        }
+    }
+}
+
+// ---- recombine, vector form (width 1): 16 bytes per thread and access ----------------------------------
+static __global__ void __launch_bounds__(GF_THREADS)
+k_gf_recombine_vec(unsigned poly, GfTab lam, GfRows rows, int k, unsigned char* __restrict__ out, size_t ngroups) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const unsigned long long red = poly & 0xFFu;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += nth) {
+        GfW2 acc = {0ull, 0ull};
+        for (int i0 = 0; i0 < k; i0 += 4) {
+            GfW2 v[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (i0 + b < k) v[b] = gf_ld16(rows.p[i0 + b] + 16 * g);
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (i0 + b < k) {
+                    const unsigned l = lam.v[i0 + b];
+                    const GfW2 t = gf_mulc16(v[b], l, 32 - __clz(l | 1u), red);
+                    acc.a ^= t.a;
+                    acc.b ^= t.b;
+                }
+        }
+        gf_st16(out + 16 * g, acc);
+    }
+}
+
 // ---- recombine: out[r][h] = sum_i lam[r*k+i] * rows[i][h] --------------------------------------------
 static __global__ void __launch_bounds__(GF_THREADS)
 k_gf_recombine(unsigned poly, GfTab lam, GfRows rows, int k, int width, unsigned char* __restrict__ out, size_t ostride,
@@ -292,6 +380,34 @@ static inline cudaError_t gf256_split(unsigned poly, const unsigned char* secret
             x = gf_mul1(x, (unsigned)(i + 1), poly);
         }
     }
+    // vector form for the bulk when every row is 16-byte aligned; the scalar kernel finishes the tail
+    const bool al16 = ((((uintptr_t)secrets | (uintptr_t)shares | (t ? (uintptr_t)coeffs : 0)) & 15u) == 0) &&
+                      (cstride % 16 == 0 || t <= 1) && (sstride % 16 == 0 || m <= 1);
+    if (al16 && t <= GF_HORNER_T && m <= 255 && n >= 16 && (n % 16 == 0 || n >= 4096)) {   // small ragged calls: one launch
+        const size_t groups = n / 16, done = groups * 16;
+        int grid = 0;
+        cudaError_t e = cudaSuccess;
+#define GF_SPLIT_VEC(T)                                                                                           \
+    case T:                                                                                                       \
+        grid = mpyc_grid_size((const void*)k_gf_split_vec<T>, groups, 0);                                         \
+        if (grid <= 0) return cudaErrorLaunchFailure;                                                             \
+        k_gf_split_vec<T><<<grid, GF_THREADS, 0, st>>>(poly, secrets, coeffs, cstride, shares, sstride, groups, m); \
+        break
+        switch (t) {
+            GF_SPLIT_VEC(0);
+            GF_SPLIT_VEC(1);
+            GF_SPLIT_VEC(2);
+            GF_SPLIT_VEC(3);
+            GF_SPLIT_VEC(4);
+        }
+#undef GF_SPLIT_VEC
+        g_mpyc_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        if (e != cudaSuccess || done == n) return e;
+        // tail (< 16 elements): byte path of the scalar kernel on the remaining columns
+        GF_LAUNCH(k_gf_split, 1, st, poly, tab, secrets + done, coeffs ? coeffs + done : coeffs, cstride, shares + done,
+                  sstride, n - done, t, m);
+    }
     GF_LAUNCH(k_gf_split, (n + 7) / 8, st, poly, tab, secrets, coeffs, cstride, shares, sstride, n, t, m);
 }
 // Lagrange coefficients over GF(2^8); returns 0 or MPYC_B200_EZERODIV (-3)
@@ -317,6 +433,19 @@ static inline cudaError_t gf256_recombine(unsigned poly, const unsigned char* co
     for (int i = 0; i < k * width; i++) tab.v[i] = lam[i];
     GfRows r;
     for (int i = 0; i < 64; i++) r.p[i] = i < k ? rows[i] : nullptr;
+    uintptr_t bits = (uintptr_t)out;
+    for (int i = 0; i < k; i++) bits |= (uintptr_t)rows[i];
+    if (width == 1 && (bits & 15u) == 0 && n >= 16 && (n % 16 == 0 || n >= 4096)) {
+        const size_t groups = n / 16, done = groups * 16;
+        int grid = mpyc_grid_size((const void*)k_gf_recombine_vec, groups, 0);
+        if (grid <= 0) return cudaErrorLaunchFailure;
+        k_gf_recombine_vec<<<grid, GF_THREADS, 0, st>>>(poly, tab, r, k, out, groups);
+        g_mpyc_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess || done == n) return e;
+        for (int i = 0; i < k; i++) r.p[i] += done;
+        GF_LAUNCH(k_gf_recombine, 1, st, poly, tab, r, k, width, out + done, ostride, n - done);
+    }
     GF_LAUNCH(k_gf_recombine, (n + 7) / 8, st, poly, tab, r, k, width, out, ostride, n);
 }
 static inline cudaError_t gf256_prss(unsigned poly, const unsigned char* bytes, size_t subset_stride, int nsub, int d,

@@ -500,3 +500,32 @@ def test_batched_inverse_large_property():
         A = DeviceArray.random(ctx, n, seed=5, stream_id=3)     # a zero among 2^21 random residues: probability ~0
         limbs = (A * A.reciprocal()).to_limbs()
         assert (limbs[:, 0] == 1).all() and (limbs[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize('m,t', [(3, 1), (1, 0), (5, 2), (7, 3), (9, 4), (13, 5), (255, 1)])
+@pytest.mark.parametrize('n', [16, 48, 1000, 4096, 4096 + 7, 100003])
+def test_gf256_vector_kernels_vs_oracle(m, t, n):
+    """GF(2^8) bulk path (k_gf_split_vec: Horner in the point, 16 bytes per access; k_gf_recombine_vec) equals
+    the oracle for every t the vector form covers (<= 4), the ladder/generic form (t = 5), ragged tails and
+    the largest party count the byte encoding of the points allows."""
+    if m == 255 and n > 5000:
+        pytest.skip('oracle too slow')
+    f = 283
+    ctx = mpyc_b200.context_for(f, binary=True)
+    Fo = orc.field_of(f, binary=True)
+    rnd = random.Random(n * 31 + m)
+    s = [rnd.randrange(256) for _ in range(n)]
+    C = [[rnd.randrange(256) for _ in range(n)] for _ in range(t)]
+    S = DeviceArray.from_limbs(ctx, np.array(s, dtype=np.uint8))
+    CM = DeviceMatrix.from_ints(ctx, C) if t else None
+    sh = dev.shamir_split(ctx, S, CM, t, m)
+    want = orc.split_np_order(Fo, s, C, m)
+    got = sh.to_ints()
+    assert [[int(v) for v in row] for row in got] == want
+    xs = list(range(m - t, m + 1))
+    rec = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs])
+    assert [int(v) for v in rec.to_ints()] == s
+    if m >= 2 * t + 1 and m < 255:
+        xs = list(range(1, 2 * t + 2))
+        rec = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs])
+        assert [int(v) for v in rec.to_ints()] == s

@@ -1,7 +1,12 @@
 """Times mpyc_b200_ff_inv: Montgomery-trick batches (out of place) vs one Fermat exponentiation per element
 (the in-place path) on device-resident arrays.  CUDA events, 3 warm-ups, best of 5."""
 import ctypes
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mpyc_b200
 from mpyc_b200 import _cabi
 from mpyc_b200.device import DeviceArray
