@@ -35,6 +35,7 @@ WORKLOADS = {
     'modmul': dict(p=2**64 - 189, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul p=2^64-189 n=1e8/GPU (BASELINE configs[1])'),
     'modmul_generic': dict(p=9409569905028393239, m=0, t=0, k=0, n=100_000_000, name='elementwise modmul generic 64-bit prime 9409569905028393239 (Montgomery) n=1e8/GPU (BASELINE configs[1])'),
     'c3g': dict(p=0x800000000000000000000000000000fb, m=5, t=2, k=3, n=100_000_000, name='shamir split+recombine GENERIC 128-bit prime (Montgomery path) m=5 t=2 n=1e8/GPU'),
+    'prss': dict(p=2**256 - 189, m=7, t=3, k=0, n=1 << 21, prss=True, name='PRSS np_pseudorandom_share p=2^256-189 m=7 t=3 (20 key subsets, 48-byte PRF chunks): combine kernel on n=2^21 resident bytes; e2e at np_cnnmnist call size n=213,248 (configs[4] shape)'),
     'c4': dict(p=283, binary=True, m=3, t=1, k=3, n=1 << 28, name='GF(2^8) reshare (np_aes field, modulus 283) m=3 t=1 recombine 2t+1, batched n=2^28 bytes/GPU + per-call latency at n=16 (BASELINE configs[3] shape)'),
 }
 METRIC = 'GF(p) Shamir share+recombine pairs/sec'
@@ -253,7 +254,137 @@ def dropin_rate(w, device, n=200_000):
                           'wire_bytes_per_row': len(sent[0])}}
 
 
+def run_prss_arm(a, w):
+    """PRSS (thresha.np_pseudorandom_share, mpyc/thresha.py:163-173) at the np_cnnmnist shape.  value: elements/s of the
+    combine kernel K4 on PRF bytes resident in HBM; e2e: the drop-in call on the host (SHAKE128 sponges on host threads,
+    pinned chunks, H2D, K4, D2H, ints) at the largest per-call size of the demo; cpu_baseline: the oracle port."""
+    import itertools
+    import numpy as np
+    import torch
+    import mpyc_b200
+    from mpyc_b200 import _cabi, thresha
+    from mpyc_b200._cabi import lib, check
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback for the product arm)')
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    p, m, t, n = w['p'], w['m'], w['t'], a.n or w['n']
+    ctx = mpyc_b200.context_for(p)
+    L, eb = ctx.nlimbs, ctx.elem_bytes
+    party = 1
+    subsets = [S for S in itertools.combinations(range(m), m - t) if party in S]
+    nsub, d = len(subsets), 1
+    prf = {S: thresha.PRF(bytes([(31 * a_ + 7) % 256 for a_ in S] + [0] * (16 - len(S))), p) for S in subsets}
+    chunk = next(iter(prf.values())).byte_length
+    stride = (n * d * chunk + 15) // 16 * 16
+    peak, peak_src = peaks()
+    # device-resident PRF bytes: random bytes stand in for the XOF output (the kernel's work does not depend on them)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(20260923 + rank)
+    d_bytes = torch.randint(0, 256, (nsub, stride), dtype=torch.uint8, device='cuda', generator=g)
+    d_out = torch.empty((n, L), dtype=torch.int64, device='cuda')
+    nl = L
+    coef = []
+    for S in subsets:
+        coef.extend(_cabi.int_to_limbs(int(thresha._f_S_i(_PrssField(p), m, party, S)), nl))
+    wl = _cabi.int_to_limbs(1, nl)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        check(lib.mpyc_b200_prss_combine(ctx.handle, ctypes.c_void_p(d_bytes.data_ptr()), stride, nsub, d, chunk, 0,
+                                         _cabi.u64_array(coef), _cabi.u64_array(wl), ctypes.c_void_p(d_out.data_ptr()), n, st))
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = mpyc_b200.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record()
+    for i in range(a.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    launches = mpyc_b200.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if world > 1:
+        tt = torch.tensor([total_ms], device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms = total_ms / a.steps
+    alg = n * (nsub * d * chunk + eb)
+    ach = alg / (ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'k_prss_tiles', 'achieved': ach, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': ncu_traffic('prss', 'prss')[0], 'ms': ms, 'algorithmic_bytes': alg,
+                'note': 'includes the per-call table upload (cudaMallocAsync + 1 KB H2D + stream sync) of mpyc_b200_prss_combine'}
+    # e2e through the drop-in call, host data in / ints out, at the demo's largest call size
+    ne = 213_248
+    F = _PrssField(p)
+    thresha.device = local
+    thresha.np_pseudorandom_share(F, m, party, prf, b'warm', 4096)
+    reps, t0 = 3, time.perf_counter()
+    for r in range(reps):
+        res = thresha.np_pseudorandom_share(F, m, party, prf, b'uci%d' % r, ne)
+    dt = (time.perf_counter() - t0) / reps
+    out_limbs = np.empty((ne, L), dtype=np.uint64)
+    keys = b''.join(f.key for f in prf.values())
+    t0 = time.perf_counter()
+    for r in range(reps):
+        check(lib.mpyc_b200_prss_host(ctx.handle, keys, 16, b'uci%d' % r, 4, nsub, d, chunk, 0, _cabi.u64_array(coef),
+                                      _cabi.u64_array(wl), ctypes.c_void_p(out_limbs.ctypes.data), ne, local, 0))
+    dt_abi = (time.perf_counter() - t0) / reps
+    e2e = {'value': world * ne / dt_abi, 'unit': 'shares/s', 'h2d_bytes_per_step': ne * nsub * d * chunk, 'd2h_bytes_per_step': ne * eb,
+           'n_per_step': ne, 'ms_per_step': dt_abi * 1e3,
+           'path': 'mpyc_b200_prss_host: SHAKE128 sponges on host threads -> pinned chunks -> H2D -> K4 -> D2H (host buffers in and out)',
+           'xof_bytes_per_step': ne * nsub * d * chunk, 'host_threads': min(nsub, os.cpu_count() or 1),
+           'dropin': {'value': ne / dt, 'unit': 'shares/s', 'path': 'mpyc_b200.thresha.np_pseudorandom_share (field.array of Python ints out)'}}
+    cpu = None
+    if rank == 0 and not a.no_cpu:
+        from oracle import shamir_oracle as orc
+        Fo = orc.field_of(p)
+        nc = 10_000
+        t0 = time.perf_counter()
+        got = orc.prss_share(Fo, m, party, {S: orc.prf_values(f.key, p, b'uci0', nc) for S, f in prf.items()}, nc)
+        dtc = time.perf_counter() - t0
+        assert got == res.value[:nc].tolist(), 'PRSS differs from the oracle'
+        cpu = {'value': nc / dtc, 'unit': 'shares/s', 'cores': 1, 'kind': 'port',
+               'sample': f'oracle port of np_pseudorandom_share (hashlib SHAKE128 + Python ints) on {nc} elements, 1 process'}
+    if rank == 0:
+        line = {'metric': 'PRSS pseudorandom shares/sec', 'value': world * n / (ms * 1e-3), 'unit': 'shares/s', 'n_gpus': world,
+                'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': f'u64x{L} limbs (exact integer arithmetic mod p)', 'data': 'synthetic',
+                'config': {'workload': w['name'], 'p_bits': p.bit_length(), 'm': m, 't': t, 'subsets': nsub, 'chunk_bytes': chunk, 'n_per_gpu': n,
+                           'l2_policy': 'PRF bytes (2 GB) far larger than the 126 MB L2; no flush needed'},
+                'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _PrssArr:
+    def __init__(self, value, check=True):
+        self.value = value
+
+
+def _PrssField(p):
+    class Field:
+        modulus = order = characteristic = p
+        ext_deg = 1
+        array = _PrssArr
+    return Field
+
+
 def run_gpu_arm(a, w):
+    if w.get('prss'):
+        return run_prss_arm(a, w)
     import torch
     import torch.distributed as dist
     import mpyc_b200

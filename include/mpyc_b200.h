@@ -151,6 +151,19 @@ int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes,
                            int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                            const uint64_t* h_weights, void* d_out, size_t n, void* stream);
 
+/* The same with the PRF evaluated inside the library (thresha.PRF.__call__, mpyc/thresha.py:240-266, and the
+ * callers thresha.py:163-217): subset S's stream is SHAKE128(key_S || uci) squeezed to n*d*chunk_bytes bytes.
+ * h_keys: nsub keys of key_bytes bytes each (PRF.key), h_uci: the unique call identifier bytes.  One sponge is
+ * sequential, so the nsub sponges run on up to max_threads host threads (0 = all hardware threads), squeezed
+ * chunk by chunk into pinned staging buffers and overlapped with the H2D copy and the combine kernel of the
+ * previous chunk.  h_out: host buffer of n elements (limb layout).  device = CUDA device ordinal. */
+int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                        size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                        const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads);
+/* SHAKE128 (FIPS 202) of `in`, squeezed to outlen bytes: hashlib.shake_128(in).digest(outlen), the XOF of
+ * thresha.PRF (mpyc/thresha.py:257).  Host only; no GPU involved. */
+int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen);
+
 /* ---- utilities -------------------------------------------------------------------------------
  * deterministic synthetic residues (tests, bench): element h = (L+1 SplitMix64 words of counter
  * seed + (stream_id << 56) + h*(L+1) + w, truncated to bits(p)+64 bits) mod p -- same recipe as

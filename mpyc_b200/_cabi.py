@@ -69,6 +69,9 @@ _SIGNATURES = {
                                            c_int, c_void_p, c_size_t, c_size_t, c_void_p]),
     'mpyc_b200_prss_combine': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, POINTER(c_uint64),
                                        POINTER(c_uint64), c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_prss_host': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int, c_int,
+                                    POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_int, c_int]),
+    'mpyc_b200_shake128': (c_int, [c_char_p, c_size_t, c_void_p, c_size_t]),
     'mpyc_b200_fill_random': (c_int, [_field_p, c_void_p, c_size_t, c_uint64, c_uint64, c_void_p]),
     'mpyc_b200_count_mismatch': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     'mpyc_b200_shamir_split_host': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,

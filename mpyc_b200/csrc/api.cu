@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -21,6 +22,7 @@
 #include "field_setup.h"
 #include "gf256.cuh"
 #include "launch.h"
+#include "shake128.h"
 
 #define MPYC_API extern "C" __attribute__((visibility("default")))
 
@@ -755,46 +757,72 @@ MPYC_API int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* co
 // PRSS linear step
 // ---------------------------------------------------------------------------------------
 
-MPYC_API int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes,
-                                      int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
-                                      const uint64_t* h_weights, void* d_out, size_t n, void* stream) {
-    if (!f || !h_coef || !h_weights || nsub < 1 || d < 1 || chunk_bytes < 1) return fail(MPYC_B200_EINVAL, "prss_combine: bad arguments");
-    if (n == 0) return MPYC_B200_OK;
-    if (!d_prf_bytes || !d_out) return fail(MPYC_B200_EINVAL, "prss_combine: null buffer");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (f->kind == MPYC_B200_KIND_GF256) {
-        if (chunk_bytes != 1 || (bound_bits != 0 && bound_bits != 8)) return fail(MPYC_B200_EINVAL, "prss_combine: GF(2^8) PRF chunks are one byte");
-        std::vector<unsigned char> tab((size_t)nsub + d);
-        for (int i = 0; i < nsub; i++) tab[i] = (unsigned char)h_coef[i];
-        for (int j = 0; j < d; j++) tab[nsub + j] = (unsigned char)h_weights[j];
-        return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.data(), (unsigned char*)d_out, n, st), "gf256 prss");
+namespace {
+
+// per-call PRSS constants on the device: [coef_S (nsub) | weight_j (d)] in table form (prime fields)
+struct PrssTable {
+    u64* d_tab = nullptr;
+    u32 bytes = 0;
+    std::vector<unsigned char> gf;     // GF(2^8): passed to the kernel by value
+    cudaStream_t st = nullptr;
+    ~PrssTable() {
+        if (d_tab) cudaFreeAsync(d_tab, st);
     }
-    if (chunk_bytes > 8 * (int)f->fp.L + 32) return fail(MPYC_B200_EINVAL, "prss_combine: chunk too wide for this field");
-    if (bound_bits < 0 || bound_bits >= (int)f->fp.k) return fail(MPYC_B200_EINVAL, "prss_combine: need 2^bound_bits <= p");
-    if (bound_bits > 0 && chunk_bytes != (bound_bits + 7) / 8) return fail(MPYC_B200_EINVAL, "prss_combine: chunk_bytes != ceil(bound_bits/8)");
-    if ((unsigned)nsub > FF_MAX_LAZY_TERMS || (unsigned)d > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "prss_combine: too many terms");
+};
+
+int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                 const uint64_t* h_weights, cudaStream_t st, PrssTable& tab) {
+    if (f->kind == MPYC_B200_KIND_GF256) {
+        if (chunk_bytes != 1 || (bound_bits != 0 && bound_bits != 8)) return fail(MPYC_B200_EINVAL, "prss: GF(2^8) PRF chunks are one byte");
+        tab.gf.resize((size_t)nsub + d);
+        for (int i = 0; i < nsub; i++) tab.gf[i] = (unsigned char)h_coef[i];
+        for (int j = 0; j < d; j++) tab.gf[nsub + j] = (unsigned char)h_weights[j];
+        return MPYC_B200_OK;
+    }
+    if (chunk_bytes > 8 * (int)f->fp.L + 32) return fail(MPYC_B200_EINVAL, "prss: chunk too wide for this field");
+    if (bound_bits < 0 || bound_bits >= (int)f->fp.k) return fail(MPYC_B200_EINVAL, "prss: need 2^bound_bits <= p");
+    if (bound_bits > 0 && chunk_bytes != (bound_bits + 7) / 8) return fail(MPYC_B200_EINVAL, "prss: chunk_bytes != ceil(bound_bits/8)");
+    if ((unsigned)nsub > FF_MAX_LAZY_TERMS || (unsigned)d > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "prss: too many terms");
     const size_t L = f->fp.L;
     std::vector<u64> host(((size_t)nsub + d) * L);
     memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
     memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
     to_table_form(f->fp, host);
     if (host.size() % 2) host.push_back(0);
-    const u32 bytes = (u32)(host.size() * sizeof(u64));
-    if (bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss_combine: coefficient table exceeds shared memory");
-    // per-call table (coefficients depend on the party and subset layout): stream-ordered allocation
-    u64* d_tab = nullptr;
-    CU(cudaMallocAsync(&d_tab, bytes, st));
-    cudaError_t e = cudaMemcpyAsync(d_tab, host.data(), bytes, cudaMemcpyHostToDevice, st);
+    tab.bytes = (u32)(host.size() * sizeof(u64));
+    if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss: coefficient table exceeds shared memory");
+    // the coefficients depend on the party and the subset layout: per call, stream-ordered allocation
+    tab.st = st;
+    CU(cudaMallocAsync(&tab.d_tab, tab.bytes, st));
+    cudaError_t e = cudaMemcpyAsync(tab.d_tab, host.data(), tab.bytes, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vector goes out of scope
-    int rc = e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "prss table upload");
-    if (rc == MPYC_B200_OK)
-        rc = with_limbs((int)L, [&](auto Lc) {
-            constexpr int LL = decltype(Lc)::value;
-            return launch_status(Launch<LL>::prss(f->fp, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, d_tab, bytes,
-                                                  (u64*)d_out, n, st), "prss_combine launch");
-        });
-    cudaFreeAsync(d_tab, st);
-    return rc;
+    return e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "prss table upload");
+}
+
+int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
+                int d, int chunk_bytes, int bound_bits, void* d_out, size_t n, cudaStream_t st) {
+    if (f->kind == MPYC_B200_KIND_GF256)
+        return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.gf.data(), (unsigned char*)d_out, n, st), "gf256 prss");
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int LL = decltype(Lc)::value;
+        return launch_status(Launch<LL>::prss(f->fp, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, tab.d_tab,
+                                              tab.bytes, (u64*)d_out, n, st), "prss_combine launch");
+    });
+}
+
+}   // namespace
+
+MPYC_API int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
+                                      int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                                      const uint64_t* h_weights, void* d_out, size_t n, void* stream) {
+    if (!f || !h_coef || !h_weights || nsub < 1 || d < 1 || chunk_bytes < 1) return fail(MPYC_B200_EINVAL, "prss_combine: bad arguments");
+    if (n == 0) return MPYC_B200_OK;
+    if (!d_prf_bytes || !d_out) return fail(MPYC_B200_EINVAL, "prss_combine: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    PrssTable tab;
+    int rc = prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, st, tab);
+    if (rc) return rc;
+    return prss_launch(f, tab, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, d_out, n, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -999,5 +1027,144 @@ MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const voi
         CU(cudaMemcpyAsync((char*)h_out + off * eb, dout, cn * eb, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    return MPYC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// PRF / PRSS with the XOF inside the library
+// ---------------------------------------------------------------------------------------
+
+MPYC_API int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen) {
+    if ((inlen && !in) || (outlen && !out)) return fail(MPYC_B200_EINVAL, "shake128: null buffer");
+    mpyc_shake::Shake128 x;
+    x.absorb(in, inlen);
+    x.squeeze(out, outlen);
+    return MPYC_B200_OK;
+}
+
+namespace {
+
+struct PinnedStage {   // pinned host staging for the PRF byte streams, one buffer per pipeline slot, per device
+    void* h[kSlots] = {nullptr, nullptr, nullptr};
+    size_t cap = 0;
+};
+PinnedStage g_pin[16];
+
+int reserve_pinned(PinnedStage& p, size_t bytes) {
+    if (bytes <= p.cap) return MPYC_B200_OK;
+    for (int s = 0; s < kSlots; s++) {
+        if (p.h[s]) cudaFreeHost(p.h[s]);
+        p.h[s] = nullptr;
+    }
+    p.cap = 0;
+    for (int s = 0; s < kSlots; s++) CU(cudaHostAlloc(&p.h[s], bytes, cudaHostAllocDefault));
+    p.cap = bytes;
+    return MPYC_B200_OK;
+}
+
+}   // namespace
+
+MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                                   size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                                   const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads) {
+    if (!f || !h_keys || key_bytes < 0 || (uci_bytes && !h_uci) || !h_coef || !h_weights || nsub < 1 || d < 1 || chunk_bytes < 1 ||
+        (n && !h_out))
+        return fail(MPYC_B200_EINVAL, "prss_host: bad arguments");
+    if (n == 0) return MPYC_B200_OK;
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    const size_t per_elem = (size_t)d * chunk_bytes;
+    // elements per pipeline chunk: ~384 KiB of XOF output per sponge (about a millisecond of squeezing),
+    // a multiple of the kernel's 256-element tiles
+    size_t ce = std::max<size_t>((384u << 10) / per_elem / 256 * 256, 256);
+    ce = std::min(ce, round_up(n, 256));
+    const size_t cstride = round_up(ce * per_elem, 16);               // bytes per subset per chunk
+    const size_t nchunks = (n + ce - 1) / ce;
+    Workspace* w;
+    int rc = acquire_workspace(device, &w);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(w->mu);
+    rc = reserve(*w, cstride * nsub, ce * eb);
+    if (rc) return rc;
+    rc = reserve_pinned(g_pin[device], cstride * nsub);
+    if (rc) return rc;
+    PinnedStage& pin = g_pin[device];
+    PrssTable tab;
+    rc = prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, w->streams[0], tab);
+    if (rc) return rc;
+
+    // one sponge per key subset (thresha.py:257: shake_128(key + s)); subsets are dealt round-robin to the workers
+    std::vector<mpyc_shake::Shake128> sponge(nsub);
+    for (int S = 0; S < nsub; S++) {
+        sponge[S].absorb(h_keys + (size_t)S * key_bytes, (size_t)key_bytes);
+        sponge[S].absorb(h_uci, uci_bytes);
+    }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int nthreads = std::min(nsub, max_threads > 0 ? max_threads : hw);
+    if ((size_t)nsub * n * per_elem < (64u << 10)) nthreads = 1;       // tiny calls: thread start-up costs more than it saves
+    std::vector<std::atomic<int>> produced(nchunks);
+    for (auto& p : produced) p.store(0, std::memory_order_relaxed);
+    std::atomic<size_t> consumed{0};                                  // chunks whose pinned slot may be overwritten
+    std::atomic<bool> abort_flag{false};
+    auto produce = [&](int worker) {
+        for (size_t c = 0; c < nchunks; c++) {
+            while (c >= consumed.load(std::memory_order_acquire) + kSlots) {   // slot c % kSlots still in flight
+                if (abort_flag.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            const size_t cn = std::min(ce, n - c * ce);
+            uint8_t* base = (uint8_t*)pin.h[c % kSlots];
+            for (int S = worker; S < nsub; S += nthreads) sponge[S].squeeze(base + (size_t)S * cstride, cn * per_elem);
+            produced[c].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> workers;
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; t++) workers.emplace_back(produce, t);
+    auto finish_workers = [&]() {
+        abort_flag.store(true);
+        for (auto& t : workers) t.join();
+    };
+    cudaEvent_t copied[kSlots];
+    for (int s = 0; s < kSlots; s++) cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming);
+    auto cleanup = [&](int code) {   // error path: stop the producers, drain the streams (the table is freed after this)
+        finish_workers();
+        for (int s = 0; s < kSlots; s++) cudaStreamSynchronize(w->streams[s]);
+        for (int s = 0; s < kSlots; s++) cudaEventDestroy(copied[s]);
+        return code;
+    };
+    for (size_t c = 0; c < nchunks; c++) {
+        const int s = (int)(c % kSlots);
+        const size_t cn = std::min(ce, n - c * ce);
+        cudaStream_t st = w->streams[s];
+        if (nthreads == 1) {
+            if (c >= kSlots) {                                        // slot reuse: its H2D copy must have left the host buffer
+                if (cudaEventSynchronize(copied[s]) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "prss_host event"));
+            }
+            uint8_t* base = (uint8_t*)pin.h[s];
+            for (int S = 0; S < nsub; S++) sponge[S].squeeze(base + (size_t)S * cstride, cn * per_elem);
+        } else {
+            while (produced[c].load(std::memory_order_acquire) < nthreads) std::this_thread::yield();
+        }
+        cudaError_t e = cudaMemcpyAsync(w->d_in[s], pin.h[s], cstride * nsub, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(copied[s], st);
+        if (e != cudaSuccess) return cleanup(cuda_fail(e, "prss_host H2D"));
+        rc = prss_launch(f, tab, (const uint8_t*)w->d_in[s], cstride, nsub, d, chunk_bytes, bound_bits, w->d_out[s], cn, st);
+        if (rc) return cleanup(rc);
+        e = cudaMemcpyAsync((char*)h_out + c * ce * eb, w->d_out[s], cn * eb, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return cleanup(cuda_fail(e, "prss_host D2H"));
+        if (nthreads > 1 && c + 1 >= (size_t)kSlots) {
+            // chunk c+1-kSlots's slot is needed next by the producers: wait until its copy has left the host buffer
+            const size_t old = c + 1 - kSlots;
+            if (cudaEventSynchronize(copied[old % kSlots]) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "prss_host event"));
+            consumed.store(old + 1, std::memory_order_release);
+        }
+    }
+    for (int s = 0; s < kSlots; s++)
+        if (cudaStreamSynchronize(w->streams[s]) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "prss_host sync"));
+    for (auto& t : workers) t.join();
+    workers.clear();
+    for (int s = 0; s < kSlots; s++) cudaEventDestroy(copied[s]);
     return MPYC_B200_OK;
 }

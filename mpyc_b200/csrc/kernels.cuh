@@ -322,8 +322,11 @@ k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, in
 #ifndef MPYC_SPLIT_U
 #define MPYC_SPLIT_U 1
 #endif
+// shares computed per trip of the party loop of split_compute: two independent share evaluations in flight
+// hide the carry-chain latency for fields of >= 2 limbs (measured on B200, C3: K2 0.87 -> 0.955 of the copy
+// peak, C5 shape 0.87 -> 0.94); 1-limb fields are fastest without (0.874 vs 0.852)
 #ifndef MPYC_SPLIT_MU
-#define MPYC_SPLIT_MU 1
+#define MPYC_SPLIT_MU (L == 1 ? 1 : 2)
 #endif
 #ifndef MPYC_REC_U1
 #define MPYC_REC_U1 2
@@ -753,6 +756,113 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
         u32 r[N];
         F::finish(r, outer, f);
         store_limbs<L, false>(out + h * L, r);
+    }
+}
+
+// K4 (tiled form): one CTA owns a tile of MPYC_THREADS consecutive elements and walks the key subsets; the
+// tile's PRF bytes of subset S+1 (MPYC_THREADS*d*chunk_bytes contiguous bytes) are fetched global -> shared
+// memory by ONE TMA bulk copy while the threads convert and accumulate subset S from the other buffer
+// (double buffering, one mbarrier per buffer).  HBM is read in full coalesced lines instead of one byte per
+// thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.
+// smem layout: [table tab_bytes (rounded to 128)] [buffer 0: tile_bytes] [buffer 1: tile_bytes]
+template <int L, int KIND>
+__global__ void MPYC_LB
+k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d, int chunk_bytes,
+             int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out, size_t n, u32 tile_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) u64 mbar_tab;
+    __shared__ __align__(8) u64 mbar_buf[2];
+    u64* stab = reinterpret_cast<u64*>(smem_raw);
+    const u32 tab_room = (tab_bytes + 127u) & ~127u;
+    unsigned char* const buf0 = smem_raw + tab_room;   // buffer b at buf0 + b * tile_bytes
+    tma_stage_table(stab, gtab, tab_bytes, &mbar_tab);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_buf[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_buf[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const u64* coef = stab;
+    const u64* wts = stab + (size_t)nsub * L;
+    const int nl = (chunk_bytes + 7) >> 3;
+    const size_t per_elem = (size_t)d * chunk_bytes;
+    const size_t ntiles = (n + MPYC_THREADS - 1) / MPYC_THREADS;
+    u32 phases = 0;                                      // bit b: parity the next wait on buffer b expects
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t h0 = tile * MPYC_THREADS;
+        const size_t cnt = min((size_t)MPYC_THREADS, n - h0);
+        const u32 nbytes = (u32)((cnt * per_elem + 15) & ~(size_t)15);   // the caller pads every subset to 16 bytes
+        const unsigned char* src0 = bytes + h0 * per_elem;
+        auto issue = [&](int S) {   // thread 0: bulk copy of subset S's bytes for this tile into buffer S & 1
+            const u32 bar = smem_u32(&mbar_buf[S & 1]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(buf0 + (size_t)(S & 1) * tile_bytes)),
+                         "l"(src0 + (size_t)S * subset_stride), "r"(nbytes), "r"(bar)
+                         : "memory");
+        };
+        if (threadIdx.x == 0) issue(0);
+        const size_t h = h0 + threadIdx.x;
+        u32 outer[F::WACC];
+        zero_n<F::WACC>(outer);
+        for (int S = 0; S < nsub; S++) {
+            const int b = S & 1;
+            if (threadIdx.x == 0 && S + 1 < nsub) issue(S + 1);   // buffer (S+1)&1 was released by the barrier below
+            u32 done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(smem_u32(&mbar_buf[b])), "r"((phases >> b) & 1u)
+                    : "memory");
+            }
+            phases ^= 1u << b;
+            if (h < n) {
+                u32 inner[F::WACC];
+                zero_n<F::WACC>(inner);
+                for (int j = 0; j < d; j++) {
+                    const unsigned char* src = buf0 + (size_t)b * tile_bytes + ((size_t)threadIdx.x * d + j) * chunk_bytes;
+                    u32 v[N];
+                    zero_n<N>(v);
+                    for (int w = nl - 1; w >= 0; w--) {
+                        u64 limb = 0;
+                        const int lo = w * 8, hi = min(lo + 8, chunk_bytes);
+                        if ((chunk_bytes & 7) == 0) {
+                            limb = *reinterpret_cast<const u64*>(src + lo);      // tile base 16-byte aligned, chunk % 8 == 0
+                        } else {
+                            for (int bb = hi - 1; bb >= lo; bb--) limb = (limb << 8) | src[bb];
+                        }
+                        if (bound_bits > 0) {
+                            const int top = bound_bits - 64 * w;
+                            if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
+#pragma unroll
+                            for (int l = 0; l < L; l++)
+                                if (l == w) set64(v, l, limb);
+                        } else {
+                            u32 x[N + 2];
+                            set64(x, 0, limb);
+#pragma unroll
+                            for (int l = 0; l < N; l++) x[l + 2] = v[l];
+                            F::reduce_small(v, x, f);
+                        }
+                    }
+                    F::mac(inner, v, as32(wts + (size_t)j * L));
+                }
+                u32 y[N];
+                F::finish(y, inner, f);
+                F::mac(outer, y, as32(coef + (size_t)S * L));
+            }
+            __syncthreads();   // every thread is done with buffer b: it may be refilled (by issue(S+2) next trip)
+        }
+        if (h < n) {
+            u32 r[N];
+            F::finish(r, outer, f);
+            store_limbs<L, false>(out + h * L, r);
+        }
     }
 }
 

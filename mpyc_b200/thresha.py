@@ -38,6 +38,7 @@ __all__ = ['random_split', 'recombine', 'pseudorandom_share', 'pseudorandom_shar
 
 coefficient_source = None     # callable(order, count) -> sequence of ints, or None (CSPRNG)
 device = 0                    # CUDA device ordinal used by the host-buffer entry points
+prss_threads = 0              # host threads for the SHAKE128 sponges of one PRSS call (0 = all hardware threads)
 limb_wire = False             # True: np_random_split returns limb-backed ShareRows (mpyc_b200.wire) that
                               # pickle as fixed-width bytes and feed np_recombine without becoming ints
 
@@ -278,27 +279,24 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
         return np.zeros((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
     if not torch.cuda.is_available():
         raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
-    stride = (n * d * width + 15) // 16 * 16
-    buf = bytearray(stride * len(subsets))
+    # The XOF runs inside the library: one SHAKE128 sponge per key subset on its own host thread, squeezed chunk
+    # by chunk into pinned buffers while the previous chunk is copied and combined on the GPU
+    # (mpyc_b200_prss_host) -- hashlib.shake_128().digest() holds the GIL and would serialise the subsets.
+    keys = [f.key for _, f in subsets]
+    klen = len(keys[0])
+    if any(len(k) != klen for k in keys):
+        raise ValueError('all PRF keys of one call must have the same length')
     coef = []
-    for k, (S, f) in enumerate(subsets):
-        raw = shake_128(f.key + uci).digest(n * d * width)
-        buf[k * stride:k * stride + len(raw)] = raw
-        c = _f_S_i(field, m, i, S)
-        coef.extend(_cabi.int_to_limbs(int(c), nl))
+    for S, f in subsets:
+        coef.extend(_cabi.int_to_limbs(int(_f_S_i(field, m, i, S)), nl))
     wl = []
     for w in weights:
         wl.extend(_cabi.int_to_limbs(int(w), nl))
-    dev = torch.device('cuda', device)
-    d_bytes = torch.frombuffer(buf, dtype=torch.uint8).to(dev)
-    out = torch.empty((n,) if ctx.binary else (n, nl), dtype=torch.uint8 if ctx.binary else torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        check(lib.mpyc_b200_prss_combine(ctx.handle, ctypes.c_void_p(d_bytes.data_ptr()), stride, len(subsets), d, width,
-                                         bound_bits if not ctx.binary else 0, _cabi.u64_array(coef), _cabi.u64_array(wl),
-                                         ctypes.c_void_p(out.data_ptr()), n, st))
-        res = out.cpu().numpy()
-    return res if ctx.binary else res.view(np.uint64)
+    out = np.empty((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
+    check(lib.mpyc_b200_prss_host(ctx.handle, b''.join(keys), klen, bytes(uci), len(uci), len(subsets), d, width,
+                                  bound_bits if not ctx.binary else 0, _cabi.u64_array(coef), _cabi.u64_array(wl),
+                                  _ptr(out), n, device, prss_threads))
+    return out
 
 
 def np_pseudorandom_share(field, m, i, prfs, uci, n):

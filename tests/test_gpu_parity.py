@@ -529,3 +529,35 @@ def test_gf256_vector_kernels_vs_oracle(m, t, n):
         xs = list(range(1, 2 * t + 2))
         rec = dev.shamir_recombine(ctx, xs, [sh.row(x - 1) for x in xs])
         assert [int(v) for v in rec.to_ints()] == s
+
+
+@pytest.mark.parametrize('p,m,t', [(2**256 - 189, 7, 3), (2**69 - 93, 3, 1), (9409569905028393239, 5, 2)],
+                         ids=['p256_m7t3', 'p69_m3t1', 'generic64_m5t2'])
+def test_prss_pipeline_in_library(p, m, t, monkeypatch):
+    """mpyc_b200_prss_host (SHAKE128 sponges on host threads -> pinned chunks -> tiled combine kernel with TMA-staged
+    byte tiles): equal to the oracle on a multi-chunk call, and independent of the thread count and of the kernel
+    form (tiled / untiled) on a call of np_cnnmnist's largest size (n = 213,248)."""
+    F = fakefield.make_prime_field(p)
+    Fo = orc.field_of(p)
+    subsets = list(itertools.combinations(range(m), m - t))
+    keys = {S: bytes([17 * (a + 1) % 256 for a in S] + [0] * (16 - len(S))) for S in subsets}
+    i = 1
+    mine = {S: keys[S] for S in subsets if i in S}
+    uci = b'\x05\x00\x00\x00\x07'
+
+    def prfs(bound):
+        return {S: thresha.PRF(k, bound) for S, k in mine.items()}
+
+    n = 20_011                                   # several 256-element tiles, ragged tail, > 1 pipeline chunk for 48-byte chunks
+    got = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, n).value.tolist()
+    assert got == orc.prss_share(Fo, m, i, {S: orc.prf_values(k, p, uci, n) for S, k in mine.items()}, n)
+    got0 = thresha.np_pseudorandom_share_0(F, m, i, prfs(p), uci, 3001).value.tolist()
+    assert got0 == orc.prss_share_zero_np_order(Fo, m, i, {S: orc.prf_values(k, p, uci, 3001 * t) for S, k in mine.items()}, 3001)
+    big = 213_248
+    ref = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    monkeypatch.setattr(thresha, 'prss_threads', 1)
+    one = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    monkeypatch.setenv('MPYC_B200_PRSS_UNTILED', '1')
+    flat = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    assert ref.tolist() == one.tolist() == flat.tolist()
+    assert ref[:n].tolist() == got               # a longer call extends the same streams (XOF prefix property)
