@@ -354,7 +354,8 @@ def run_prss_arm(a, w):
         t0 = time.perf_counter()
         got = orc.prss_share(Fo, m, party, {S: orc.prf_values(f.key, p, b'uci0', nc) for S, f in prf.items()}, nc)
         dtc = time.perf_counter() - t0
-        assert got == res.value[:nc].tolist(), 'PRSS differs from the oracle'
+        chk = thresha.np_pseudorandom_share(F, m, party, prf, b'uci0', nc)
+        assert got == chk.value.tolist(), 'PRSS differs from the oracle'
         cpu = {'value': nc / dtc, 'unit': 'shares/s', 'cores': 1, 'kind': 'port',
                'sample': f'oracle port of np_pseudorandom_share (hashlib SHAKE128 + Python ints) on {nc} elements, 1 process'}
     if rank == 0:

@@ -444,10 +444,20 @@ static void wide_sub_small(u64* r, int n, u64 v) {
     }
 }
 
-struct ZeroFlag {   // one device int per call, freed on scope exit
+// "saw a zero" flag of the inverse family: one device int per (host thread, device), allocated on first use and
+// kept (cudaMalloc / cudaFree per call cost more than the kernel at the demos' array sizes and synchronise the
+// device).  acquire() returns it cleared on `st`; calls are one per thread per stream, so there is no sharing.
+struct ZeroFlag {
     int* d = nullptr;
-    ~ZeroFlag() {
-        if (d) cudaFree(d);
+    int acquire(cudaStream_t st) {
+        thread_local int* cache[16] = {nullptr};
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 16) return fail(MPYC_B200_EINVAL, "device ordinal out of range");
+        if (!cache[dev]) CU(cudaMalloc(&cache[dev], sizeof(int)));
+        d = cache[dev];
+        CU(cudaMemsetAsync(d, 0, sizeof(int), st));
+        return MPYC_B200_OK;
     }
 };
 
@@ -460,8 +470,7 @@ static int pow_impl(const mpyc_b200_field* f, const void* d_a, const u64* e, int
     ex.ebits = bit_length(ex.e, 8);
     ZeroFlag zf;
     if (check_zero) {
-        CU(cudaMalloc(&zf.d, sizeof(int)));
-        CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+        if (int zrc = zf.acquire(st)) return zrc;
     }
     int rc = with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int L = decltype(Lc)::value;
@@ -495,8 +504,7 @@ MPYC_API int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d
     cudaStream_t st = (cudaStream_t)stream;
     if (f->kind == MPYC_B200_KIND_GF256) {
         ZeroFlag zf;
-        CU(cudaMalloc(&zf.d, sizeof(int)));
-        CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+        if (int zrc = zf.acquire(st)) return zrc;
         int rc = launch_status(gf256_pow(f->gf_poly, (const unsigned char*)d_a, 254, (unsigned char*)d_out, zf.d, n, st), "gf256 inv");
         if (rc) return rc;
         int flag = 0;
@@ -514,8 +522,7 @@ MPYC_API int mpyc_b200_ff_inv(const mpyc_b200_field* f, const void* d_a, void* d
     for (int i = 0; i < 4; i++) ex.e[i] = e[i];
     ex.ebits = bit_length(ex.e, 8);
     ZeroFlag zf;
-    CU(cudaMalloc(&zf.d, sizeof(int)));
-    CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+    if (int zrc = zf.acquire(st)) return zrc;
     int rc = with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int L = decltype(Lc)::value;
         return launch_status(Launch<L>::inv_batch(f->fp, ex, (const u64*)d_a, (u64*)d_out, zf.d, n, st), "ff_inv launch");
@@ -534,8 +541,7 @@ MPYC_API int mpyc_b200_ff_sqrt(const mpyc_b200_field* f, const void* d_a, int in
         // finfields.py:1552-1563: a^(q/2), inverse: a^(q/2 - 1)
         ZeroFlag zf;
         if (inverse) {
-            CU(cudaMalloc(&zf.d, sizeof(int)));
-            CU(cudaMemsetAsync(zf.d, 0, sizeof(int), st));
+            if (int zrc = zf.acquire(st)) return zrc;
         }
         int rc = launch_status(gf256_pow(f->gf_poly, (const unsigned char*)d_a, inverse ? 127 : 128, (unsigned char*)d_out, zf.d, n, st), "gf256 sqrt");
         if (rc || !inverse) return rc;

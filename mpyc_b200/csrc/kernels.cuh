@@ -324,9 +324,10 @@ k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, in
 #endif
 // shares computed per trip of the party loop of split_compute: two independent share evaluations in flight
 // hide the carry-chain latency for fields of >= 2 limbs (measured on B200, C3: K2 0.87 -> 0.955 of the copy
-// peak, C5 shape 0.87 -> 0.94); 1-limb fields are fastest without (0.874 vs 0.852)
+// peak, C5 shape 0.87 -> 0.94); 1-limb fields (0.874 vs 0.852) and the Barrett path of generic primes
+// (0.739 vs 0.677) are fastest without
 #ifndef MPYC_SPLIT_MU
-#define MPYC_SPLIT_MU (L == 1 ? 1 : 2)
+#define MPYC_SPLIT_MU ((L == 1 || KIND == KIND_GENERIC) ? 1 : 2)
 #endif
 #ifndef MPYC_REC_U1
 #define MPYC_REC_U1 2

@@ -68,3 +68,62 @@ def test_sharded_equals_single_gpu_and_gather():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
+
+
+def _reshare_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import mpyc_b200
+        from mpyc_b200 import device as dev, exchange
+        from mpyc_b200.device import DeviceArray, DeviceMatrix
+        for p, m, t, n in ((2**128 - 173, 5, 2, 200_003), (2**64 - 189, 3, 1, 1_000_000), (2**256 - 189, 7, 3, 50_001)):
+            ctx = mpyc_b200.context_for(p)
+            A = DeviceArray.random(ctx, n, seed=3, stream_id=1)          # same inputs and sharings on every rank
+            B = DeviceArray.random(ctx, n, seed=4, stream_id=1)
+            CA, CB = DeviceMatrix.empty(ctx, t, n), DeviceMatrix.empty(ctx, t, n)
+            for j in range(t):
+                CA.t[j].copy_(DeviceArray.random(ctx, n, seed=30 + j, stream_id=2).t)
+                CB.t[j].copy_(DeviceArray.random(ctx, n, seed=40 + j, stream_id=2).t)
+            sa, sb = dev.shamir_split(ctx, A, CA, t, m), dev.shamir_split(ctx, B, CB, t, m)
+            mine = exchange.local_parties(m, world, rank)
+            prod = {j: (sa.row(j) * sb.row(j)).t for j in mine}          # degree-2t local products
+            new = exchange.reshare(exchange.DeviceEngine(ctx), prod, t, m, first_dealer=1)
+            assert sorted(new) == mine
+            # collect every party's new share on every rank and open the product with two different party sets
+            full = [None] * m
+            for i in range(m):
+                buf = new[i].contiguous() if i in new else torch.empty((n, ctx.nlimbs), dtype=torch.int64, device='cuda')
+                dist.broadcast(buf, src=exchange.owner(i, world))
+                full[i] = DeviceArray(ctx, buf)
+            want = A * B
+            for xs in (list(range(1, t + 2)), list(range(m - t, m + 1))):
+                got = dev.shamir_recombine(ctx, xs, [full[x - 1] for x in xs])
+                assert got.count_mismatch(want) == 0, (p.bit_length(), xs)
+        q.put((rank, 'ok'))
+    except Exception:   # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_colocated_reshare_over_nccl():
+    """secure multiplication's resharing step with the parties spread over 2 GPUs -- K2 on every
+    dealer, limb rows exchanged GPU to GPU (grouped ncclSend/ncclRecv), K3s on every party; any t+1 of the new
+    shares open the product."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reshare_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
