@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1117,7 +1118,7 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
         for (size_t c = 0; c < nchunks; c++) {
             while (c >= consumed.load(std::memory_order_acquire) + kSlots) {   // slot c % kSlots still in flight
                 if (abort_flag.load(std::memory_order_relaxed)) return;
-                std::this_thread::yield();
+                std::this_thread::sleep_for(std::chrono::microseconds(50));   // do not burn a core the sponges could use
             }
             const size_t cn = std::min(ce, n - c * ce);
             uint8_t* base = (uint8_t*)pin.h[c % kSlots];
@@ -1151,7 +1152,7 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
             uint8_t* base = (uint8_t*)pin.h[s];
             for (int S = 0; S < nsub; S++) sponge[S].squeeze(base + (size_t)S * cstride, cn * per_elem);
         } else {
-            while (produced[c].load(std::memory_order_acquire) < nthreads) std::this_thread::yield();
+            while (produced[c].load(std::memory_order_acquire) < nthreads) std::this_thread::sleep_for(std::chrono::microseconds(50));
         }
         cudaError_t e = cudaMemcpyAsync(w->d_in[s], pin.h[s], cstride * nsub, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaEventRecord(copied[s], st);

@@ -699,13 +699,121 @@ k_recombine(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
+// PRF chunk -> field element (thresha.py:257-261: int.from_bytes(chunk, 'little') % bound), shared by the K4 kernels.
+//   bound = 2^b (bound_bits > 0): mask, no reduction.
+//   bound = p, pseudo-Mersenne with a limb-aligned power 2^(64L) = cp (mod p), cp = c << (64L - k) < 2^59:
+//       the chunk is cut into L-limb pieces X_q and X = sum_q X_q cp^q is gathered in ONE (L+1)-limb accumulator
+//       with 64-bit-constant multiplications, then reduced once  (PrssFold::ok; e.g. 2^256-189: X0 + 189 X1)
+//   otherwise: Horner over 64-bit limbs from the top, one reduce_small per limb.
+// ---------------------------------------------------------------------------------------
+
+struct PrssFold {
+    u64 pw[5];    // cp^q
+    bool ok;
+};
+
+template <int L, int KIND>
+__device__ __forceinline__ PrssFold prss_fold_setup(const FieldParams& f, int nl) {
+    PrssFold s;
+    s.ok = false;
+#pragma unroll
+    for (int q = 0; q < 5; q++) s.pw[q] = 0;
+    if constexpr (KIND != KIND_GENERIC) {
+        const u32 sh = 64u * L - f.k;                       // 0 for the aligned kind
+        const int pieces = (nl + L - 1) / L;
+        if (f.c < (1ull << 16) && sh <= 43 && pieces <= 5) {   // cp < 2^59
+            const u64 cp = f.c << sh;
+            s.pw[0] = 1;
+            s.ok = true;
+#pragma unroll
+            for (int q = 1; q < 5; q++) {
+                if (q < pieces) {
+                    if (__umul64hi(s.pw[q - 1], cp) != 0) s.ok = false;
+                    s.pw[q] = s.pw[q - 1] * cp;
+                }
+            }
+        }
+    }
+    return s;
+}
+
+// limb w of the chunk at src (little-endian; chunk_bytes need not be a multiple of 8)
+__device__ __forceinline__ u64 prss_chunk_limb(const unsigned char* src, int w, int chunk_bytes, bool aligned8) {
+    const int lo = w * 8;
+    if (lo >= chunk_bytes) return 0;
+    if (aligned8) return *reinterpret_cast<const u64*>(src + lo);
+    const int hi = min(lo + 8, chunk_bytes);
+    u64 limb = 0;
+    for (int bb = hi - 1; bb >= lo; bb--) limb = (limb << 8) | src[bb];
+    return limb;
+}
+
+template <int L, int KIND>
+__device__ __forceinline__ void prss_value(u32* v, const unsigned char* src, int chunk_bytes, int nl, int bound_bits,
+                                           bool aligned8, const PrssFold& fold, const FieldParams& f) {
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    if (bound_bits > 0) {          // bound 2^b <= p: mask, no reduction (nl <= L)
+        zero_n<N>(v);
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+            if (l < nl) {
+                u64 limb = prss_chunk_limb(src, l, chunk_bytes, aligned8);
+                const int top = bound_bits - 64 * l;
+                if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
+                set64(v, l, limb);
+            }
+        }
+        return;
+    }
+    u32 x[N + 2];                  // (L+1)-limb value < 2^(k+64) whose residue is the result
+    constexpr int MAXP = (L + 4 + L - 1) / L;   // pieces of a chunk of at most L+4 limbs
+    // aligned pseudo-Mersenne fields always fold (cp = c < 2^16): the Horner form is not even compiled for them
+    if (KIND == KIND_PM_ALIGNED || fold.ok) {
+#pragma unroll
+        for (int l = 0; l < L; l++) set64(x, l, prss_chunk_limb(src, l, chunk_bytes, aligned8));
+        x[N] = x[N + 1] = 0;
+#pragma unroll
+        for (int q = 1; q < MAXP; q++) {
+            if (q * L < nl) {       // warp-uniform
+                u32 piece[N];
+#pragma unroll
+                for (int l = 0; l < L; l++) set64(piece, l, prss_chunk_limb(src, q * L + l, chunk_bytes, aligned8));
+                F::mac_const(x, piece, fold.pw[q]);
+            }
+        }
+    } else if constexpr (KIND != KIND_PM_ALIGNED) {
+        zero_n<N>(v);
+        for (int w = nl - 1; w >= 1; w--) {   // v <- (v * 2^64 + limb) mod p, limb by limb from the top
+            set64(x, 0, prss_chunk_limb(src, w, chunk_bytes, aligned8));
+#pragma unroll
+            for (int l = 0; l < N; l++) x[l + 2] = v[l];
+            F::reduce_small(v, x, f);
+        }
+        set64(x, 0, prss_chunk_limb(src, 0, chunk_bytes, aligned8));
+#pragma unroll
+        for (int l = 0; l < N; l++) x[l + 2] = v[l];
+    }
+    F::reduce_small(v, x, f);
+}
+
+// table entry == table form of 1 ?  (then multiplying by it and dividing R' back out is the identity)
+template <int L, int KIND>
+__device__ __forceinline__ bool prss_is_one(const u64* w, const FieldParams& f) {
+    bool one = true;
+#pragma unroll
+    for (int l = 0; l < L; l++) one = one && (w[l] == (KIND == KIND_GENERIC ? f.r1[l] : (l == 0 ? 1ull : 0ull)));
+    return one;
+}
+
+// ---------------------------------------------------------------------------------------
 // K4: PRSS linear step.  For element h and subset S the PRF output is d chunks of chunk_bytes
 // little-endian bytes at bytes + S*subset_stride + (h*d + j)*chunk_bytes.
 // tab = [coef_S (nsub entries) | weight_j (d entries)], table form.
 // ---------------------------------------------------------------------------------------
 
 template <int L, int KIND>
-__global__ void MPYC_LB
+__global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
                int chunk_bytes, int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out,
                size_t n) {
@@ -715,6 +823,8 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
     const u64* coef = stab;
     const u64* wts = stab + (size_t)nsub * L;
     const int nl = (chunk_bytes + 7) >> 3;   // limbs per chunk
+    const PrssFold fold = prss_fold_setup<L, KIND>(f, nl);
+    const bool unit_w = d == 1 && prss_is_one<L, KIND>(wts, f);
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
         typedef Fp<L, KIND> F;
@@ -722,36 +832,16 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
         u32 outer[F::WACC];
         zero_n<F::WACC>(outer);
         for (int S = 0; S < nsub; S++) {
-            u32 inner[F::WACC];
+            u32 y[N], inner[F::WACC];
             zero_n<F::WACC>(inner);
             for (int j = 0; j < d; j++) {
-                const unsigned char* src = bytes + (size_t)S * subset_stride + (h * d + j) * (size_t)chunk_bytes;
-                // value = little-endian integer of chunk_bytes bytes, reduced limb by limb from the top:
-                // v <- (v * 2^64 + limb) mod p   ((L+1)-limb value < 2^64 p)
                 u32 v[N];
-                zero_n<N>(v);
-                for (int w = nl - 1; w >= 0; w--) {
-                    u64 limb = 0;
-                    int lo = w * 8, hi = min(lo + 8, chunk_bytes);
-                    for (int bb = hi - 1; bb >= lo; bb--) limb = (limb << 8) | src[bb];
-                    if (bound_bits > 0) {   // bound 2^b <= p: mask, no reduction (nl <= L)
-                        int top = bound_bits - 64 * w;
-                        if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
-#pragma unroll
-                        for (int l = 0; l < L; l++)
-                            if (l == w) set64(v, l, limb);
-                    } else {
-                        u32 x[N + 2];
-                        set64(x, 0, limb);
-#pragma unroll
-                        for (int l = 0; l < N; l++) x[l + 2] = v[l];
-                        F::reduce_small(v, x, f);
-                    }
-                }
-                F::mac(inner, v, as32(wts + (size_t)j * L));
+                prss_value<L, KIND>(v, bytes + (size_t)S * subset_stride + (h * d + j) * (size_t)chunk_bytes, chunk_bytes, nl,
+                                    bound_bits, false, fold, f);
+                if (unit_w) copy_n<N>(y, v);
+                else F::mac(inner, v, as32(wts + (size_t)j * L));
             }
-            u32 y[N];
-            F::finish(y, inner, f);
+            if (!unit_w) F::finish(y, inner, f);
             F::mac(outer, y, as32(coef + (size_t)S * L));
         }
         u32 r[N];
@@ -767,7 +857,7 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 // thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.
 // smem layout: [table tab_bytes (rounded to 128)] [buffer 0: tile_bytes] [buffer 1: tile_bytes]
 template <int L, int KIND>
-__global__ void MPYC_LB
+__global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d, int chunk_bytes,
              int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out, size_t n, u32 tile_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -789,6 +879,9 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
     const size_t per_elem = (size_t)d * chunk_bytes;
     const size_t ntiles = (n + MPYC_THREADS - 1) / MPYC_THREADS;
     u32 phases = 0;                                      // bit b: parity the next wait on buffer b expects
+    const PrssFold fold = prss_fold_setup<L, KIND>(f, nl);
+    const bool unit_w = d == 1 && prss_is_one<L, KIND>(wts, f);
+    const bool aligned8 = (chunk_bytes & 7) == 0;        // tile base is 16-byte aligned
     typedef Fp<L, KIND> F;
     constexpr int N = 2 * L;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -823,38 +916,16 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
             }
             phases ^= 1u << b;
             if (h < n) {
-                u32 inner[F::WACC];
+                const unsigned char* base = buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes;
+                u32 y[N], inner[F::WACC];
                 zero_n<F::WACC>(inner);
                 for (int j = 0; j < d; j++) {
-                    const unsigned char* src = buf0 + (size_t)b * tile_bytes + ((size_t)threadIdx.x * d + j) * chunk_bytes;
                     u32 v[N];
-                    zero_n<N>(v);
-                    for (int w = nl - 1; w >= 0; w--) {
-                        u64 limb = 0;
-                        const int lo = w * 8, hi = min(lo + 8, chunk_bytes);
-                        if ((chunk_bytes & 7) == 0) {
-                            limb = *reinterpret_cast<const u64*>(src + lo);      // tile base 16-byte aligned, chunk % 8 == 0
-                        } else {
-                            for (int bb = hi - 1; bb >= lo; bb--) limb = (limb << 8) | src[bb];
-                        }
-                        if (bound_bits > 0) {
-                            const int top = bound_bits - 64 * w;
-                            if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
-#pragma unroll
-                            for (int l = 0; l < L; l++)
-                                if (l == w) set64(v, l, limb);
-                        } else {
-                            u32 x[N + 2];
-                            set64(x, 0, limb);
-#pragma unroll
-                            for (int l = 0; l < N; l++) x[l + 2] = v[l];
-                            F::reduce_small(v, x, f);
-                        }
-                    }
-                    F::mac(inner, v, as32(wts + (size_t)j * L));
+                    prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
+                    if (unit_w) copy_n<N>(y, v);
+                    else F::mac(inner, v, as32(wts + (size_t)j * L));
                 }
-                u32 y[N];
-                F::finish(y, inner, f);
+                if (!unit_w) F::finish(y, inner, f);
                 F::mac(outer, y, as32(coef + (size_t)S * L));
             }
             __syncthreads();   // every thread is done with buffer b: it may be refilled (by issue(S+2) next trip)

@@ -531,8 +531,9 @@ def test_gf256_vector_kernels_vs_oracle(m, t, n):
         assert [int(v) for v in rec.to_ints()] == s
 
 
-@pytest.mark.parametrize('p,m,t', [(2**256 - 189, 7, 3), (2**69 - 93, 3, 1), (9409569905028393239, 5, 2)],
-                         ids=['p256_m7t3', 'p69_m3t1', 'generic64_m5t2'])
+@pytest.mark.parametrize('p,m,t', [(2**256 - 189, 7, 3), (2**69 - 93, 3, 1), (9409569905028393239, 5, 2), (2**61 - 1, 3, 1),
+                                   (2**128 - 173, 5, 2), (2**127 - 1, 3, 1), (2**192 - 237, 3, 1)],
+                         ids=['p256_m7t3', 'p69_m3t1', 'generic64_m5t2', 'p61_m3t1', 'p128_m5t2', 'p127_m3t1', 'p192_m3t1'])
 def test_prss_pipeline_in_library(p, m, t, monkeypatch):
     """mpyc_b200_prss_host (SHAKE128 sponges on host threads -> pinned chunks -> tiled combine kernel with TMA-staged
     byte tiles): equal to the oracle on a multi-chunk call, and independent of the thread count and of the kernel
