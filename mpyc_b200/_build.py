@@ -14,7 +14,8 @@ SOURCES = ['api.cu', 'inst_L1.cu', 'inst_L2.cu', 'inst_L3.cu', 'inst_L4.cu']
 HEADERS = ['ff_arith.cuh', 'kernels.cuh', 'launch.h', 'launch_impl.cuh', 'gf256.cuh',
            os.path.join('..', '..', 'include', 'mpyc_b200.h')]
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-fno-strict-aliasing', '--expt-relaxed-constexpr']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-fno-strict-aliasing', '--expt-relaxed-constexpr',
+              '-Xfatbin', '-compress-all']   # compressed fatbin: the library travels to the GPU box with every gpurun call
 
 
 def _nvcc():
