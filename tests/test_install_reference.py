@@ -96,3 +96,27 @@ def test_finfields_hooks_installed_and_small_arrays_untouched(mpyc_thresha):
     finally:
         inst.uninstall()
     assert finfields.PrimeFieldArray.__dict__['_reciprocal'] is orig
+
+
+def test_share_rows_interoperate_with_the_reference_field_arrays(mpyc_thresha):
+    """What runtime.py does with a received row over the limb wire (runtime.py:506-509): unmarshal = pickle.loads,
+    then field.array(row, check=False).reshape(shape) -- with the REAL FiniteFieldArray, for a prime field and GF(2^8)."""
+    import pickle
+    import numpy as np
+    thresha, finfields, gfpx = mpyc_thresha
+    import mpyc_b200
+    from mpyc_b200 import codec, wire
+    p = 2**128 - 173
+    F = finfields.GF(p)
+    ctx = mpyc_b200.context_for(p)
+    vals = [3, 1, 4, 1, 5, p - 1]
+    row = pickle.loads(pickle.dumps(wire.ShareRow(ctx, codec.ints_to_limbs(vals, ctx))))
+    a = F.array(row, check=False).reshape(2, 3)
+    assert isinstance(a, F.array) and a.value.tolist() == [[3, 1, 4], [1, 5, p - 1]]
+    assert ((a + a) * 2).value.tolist() == [[(4 * v) % p for v in r] for r in a.value.tolist()]     # ordinary field arithmetic afterwards
+    f256 = finfields.GF(gfpx.GFpX(2)(283))
+    ctx8 = mpyc_b200.context_for(283, binary=True)
+    row8 = pickle.loads(pickle.dumps(wire.ShareRow(ctx8, np.array([0, 1, 0x53, 0xCA], dtype=np.uint8))))
+    b = f256.array(row8, check=False)
+    assert [int(v) for v in b.value] == [0, 1, 0x53, 0xCA]
+    assert int((b * b).value[2]) == int((f256(0x53) * f256(0x53)).value)
