@@ -771,11 +771,73 @@ struct PrssTable {
     u64* d_tab = nullptr;
     u32 bytes = 0;
     std::vector<unsigned char> gf;     // GF(2^8): passed to the kernel by value
+    bool small = false;                // [(|num_S|, sign_S) x nsub | w_j x d | D^-1 (L limbs)]: see prss_small_table
     cudaStream_t st = nullptr;
     ~PrssTable() {
         if (d_tab) cudaFreeAsync(d_tab, st);
     }
 };
+
+// Small-integer form of the subset coefficients.  f_S(i) = prod_{j not in S} (i - j) / (-(j + 1)) (thresha.py:135-141) is a
+// ratio of small integers, so for D = m! the products f_S(i) D are small signed integers: if some D = k!, k <= 20, makes
+// every coef_S D mod p representable as +-v with v < 2^57 (and the weights are plain integers < 2^58, as (i+1)^j is),
+// the kernel multiplies by 64-bit constants into one (L+1)-limb sum -- the K3s trick -- and multiplies the reduced
+// sum by D^-1 once per element instead of doing nsub full products.  Same residues, bit for bit.
+bool prss_small_table(const FieldParams& fp, int nsub, int d, const uint64_t* h_coef, const uint64_t* h_weights,
+                      std::vector<u64>& host) {
+    if (nsub > 64 || d > 32 || getenv("MPYC_B200_PRSS_FULL") != nullptr) return false;
+    const int L = (int)fp.L;
+    for (int j = 0; j < d; j++) {
+        if (h_weights[(size_t)j * L] >= (1ull << 58)) return false;
+        for (int l = 1; l < L; l++)
+            if (h_weights[(size_t)j * L + l]) return false;
+    }
+    bool found = false;
+    with_field(fp, [&](auto Lc, auto Kc) {
+        constexpr int LL = decltype(Lc)::value;
+        constexpr int K = decltype(Kc)::value;
+        typedef Fp<LL, K> F;
+        constexpr int N = 2 * LL;
+        u64 D = 1;
+        for (int k = 1; k <= 20 && !found; k++) {
+            D *= (u64)k;
+            u32 Dm[N];
+            h_from_int<LL, K>(Dm, (int64_t)D, fp);
+            if (is_zero_n<N>(Dm)) continue;                     // p divides k! (tiny fields)
+            std::vector<u64> tab((size_t)2 * nsub + d + LL);
+            bool ok = true;
+            for (int S = 0; S < nsub && ok; S++) {
+                u32 c[N], r[N], neg[N];
+                for (int l = 0; l < LL; l++) set64(c, l, h_coef[(size_t)S * LL + l]);
+                F::mul(r, c, Dm, fp);
+                F::neg(neg, r, fp);
+                auto small = [&](const u32* v) {
+                    for (int l = 1; l < LL; l++)
+                        if (get64(v, l)) return false;
+                    return get64(v, 0) < (1ull << 57);
+                };
+                if (small(r)) {
+                    tab[2 * S] = get64(r, 0);
+                    tab[2 * S + 1] = 0;
+                } else if (small(neg)) {
+                    tab[2 * S] = get64(neg, 0);
+                    tab[2 * S + 1] = 1;
+                } else {
+                    ok = false;
+                }
+            }
+            if (!ok) continue;
+            u32 inv[N];
+            if (!h_inv<LL, K>(inv, Dm, fp)) continue;
+            for (int j = 0; j < d; j++) tab[(size_t)2 * nsub + j] = h_weights[(size_t)j * LL];
+            for (int l = 0; l < LL; l++) tab[(size_t)2 * nsub + d + l] = get64(inv, l);
+            host.swap(tab);
+            found = true;
+        }
+        return MPYC_B200_OK;
+    });
+    return found;
+}
 
 int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                  const uint64_t* h_weights, cudaStream_t st, PrssTable& tab) {
@@ -791,10 +853,14 @@ int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int
     if (bound_bits > 0 && chunk_bytes != (bound_bits + 7) / 8) return fail(MPYC_B200_EINVAL, "prss: chunk_bytes != ceil(bound_bits/8)");
     if ((unsigned)nsub > FF_MAX_LAZY_TERMS || (unsigned)d > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "prss: too many terms");
     const size_t L = f->fp.L;
-    std::vector<u64> host(((size_t)nsub + d) * L);
-    memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
-    memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
-    to_table_form(f->fp, host);
+    std::vector<u64> host;
+    tab.small = prss_small_table(f->fp, nsub, d, h_coef, h_weights, host);
+    if (!tab.small) {
+        host.resize(((size_t)nsub + d) * L);
+        memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
+        memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
+        to_table_form(f->fp, host);
+    }
     if (host.size() % 2) host.push_back(0);
     tab.bytes = (u32)(host.size() * sizeof(u64));
     if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss: coefficient table exceeds shared memory");
@@ -812,8 +878,8 @@ int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d
         return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.gf.data(), (unsigned char*)d_out, n, st), "gf256 prss");
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        return launch_status(Launch<LL>::prss(f->fp, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, tab.d_tab,
-                                              tab.bytes, (u64*)d_out, n, st), "prss_combine launch");
+        return launch_status(Launch<LL>::prss(f->fp, tab.small, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits,
+                                              tab.d_tab, tab.bytes, (u64*)d_out, n, st), "prss_combine launch");
     });
 }
 

@@ -806,13 +806,67 @@ __device__ __forceinline__ bool prss_is_one(const u64* w, const FieldParams& f) 
     return one;
 }
 
+// One key subset's contribution for one element (d chunks at `base`, chunk_bytes apart).
+//   SMALL = false: acc (WACC limbs) += f_S(i) * y   with y = sum_j v_j w_j mod p, full products against table-form constants
+//   SMALL = true : acc (WSM limbs)  += |num_S| * (+-y), y = sum_j v_j w_j mod p with plain-integer weights; the caller
+//                  reduces once and multiplies by D^-1 (api.cu: prss_small_table)
+template <int L, int KIND, bool SMALL>
+__device__ __forceinline__ void prss_subset(u32* acc, const unsigned char* base, int d, int chunk_bytes, int nl, int bound_bits,
+                                            bool aligned8, bool unit_w, const PrssFold& fold, const u64* coef_S, const u64* wts,
+                                            const FieldParams& f) {
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    u32 y[N];
+    if constexpr (SMALL) {
+        u32 inner[F::WSM];
+        zero_n<F::WSM>(inner);
+        for (int j = 0; j < d; j++) {
+            u32 v[N];
+            prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
+            if (unit_w) copy_n<N>(y, v);
+            else F::mac_const(inner, v, wts[j]);
+        }
+        if (!unit_w) F::reduce_small(y, inner, f);
+        if (coef_S[1] != 0) {                 // negative coefficient: -|c| y = |c| (p - y)   (warp-uniform)
+            u32 t[N];
+            sub_n<N>(t, as32(f.p), y);
+            copy_n<N>(y, t);
+        }
+        F::mac_const(acc, y, coef_S[0]);
+    } else {
+        u32 inner[F::WACC];
+        zero_n<F::WACC>(inner);
+        for (int j = 0; j < d; j++) {
+            u32 v[N];
+            prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
+            if (unit_w) copy_n<N>(y, v);
+            else F::mac(inner, v, as32(wts + (size_t)j * L));
+        }
+        if (!unit_w) F::finish(y, inner, f);
+        F::mac(acc, y, as32(coef_S));
+    }
+}
+
+// final value of an element from its accumulator
+template <int L, int KIND, bool SMALL>
+__device__ __forceinline__ void prss_finish(u32* r, const u32* acc, const u64* dinv, const FieldParams& f) {
+    typedef Fp<L, KIND> F;
+    if constexpr (SMALL) {
+        u32 t[2 * L];
+        F::reduce_small(t, acc, f);
+        F::mul(r, t, as32(dinv), f);
+    } else {
+        F::finish(r, acc, f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K4: PRSS linear step.  For element h and subset S the PRF output is d chunks of chunk_bytes
 // little-endian bytes at bytes + S*subset_stride + (h*d + j)*chunk_bytes.
 // tab = [coef_S (nsub entries) | weight_j (d entries)], table form.
 // ---------------------------------------------------------------------------------------
 
-template <int L, int KIND>
+template <int L, int KIND, bool SMALL>
 __global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
                int chunk_bytes, int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out,
@@ -820,32 +874,25 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
     extern __shared__ __align__(16) u64 stab[];
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    constexpr int CS = SMALL ? 2 : L;                      // table words per subset coefficient
+    constexpr int WA = SMALL ? F::WSM : F::WACC;
     const u64* coef = stab;
-    const u64* wts = stab + (size_t)nsub * L;
+    const u64* wts = stab + (size_t)nsub * CS;
+    const u64* dinv = wts + d;                             // SMALL only
     const int nl = (chunk_bytes + 7) >> 3;   // limbs per chunk
     const PrssFold fold = prss_fold_setup<L, KIND>(f, nl);
-    const bool unit_w = d == 1 && prss_is_one<L, KIND>(wts, f);
+    const bool unit_w = d == 1 && (SMALL ? wts[0] == 1 : prss_is_one<L, KIND>(wts, f));
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
-        typedef Fp<L, KIND> F;
-        constexpr int N = 2 * L;
-        u32 outer[F::WACC];
-        zero_n<F::WACC>(outer);
-        for (int S = 0; S < nsub; S++) {
-            u32 y[N], inner[F::WACC];
-            zero_n<F::WACC>(inner);
-            for (int j = 0; j < d; j++) {
-                u32 v[N];
-                prss_value<L, KIND>(v, bytes + (size_t)S * subset_stride + (h * d + j) * (size_t)chunk_bytes, chunk_bytes, nl,
-                                    bound_bits, false, fold, f);
-                if (unit_w) copy_n<N>(y, v);
-                else F::mac(inner, v, as32(wts + (size_t)j * L));
-            }
-            if (!unit_w) F::finish(y, inner, f);
-            F::mac(outer, y, as32(coef + (size_t)S * L));
-        }
+        u32 acc[WA];
+        zero_n<WA>(acc);
+        for (int S = 0; S < nsub; S++)
+            prss_subset<L, KIND, SMALL>(acc, bytes + (size_t)S * subset_stride + h * (size_t)d * chunk_bytes, d, chunk_bytes, nl,
+                                        bound_bits, false, unit_w, fold, coef + (size_t)S * CS, wts, f);
         u32 r[N];
-        F::finish(r, outer, f);
+        prss_finish<L, KIND, SMALL>(r, acc, dinv, f);
         store_limbs<L, false>(out + h * L, r);
     }
 }
@@ -856,7 +903,7 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 // (double buffering, one mbarrier per buffer).  HBM is read in full coalesced lines instead of one byte per
 // thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.
 // smem layout: [table tab_bytes (rounded to 128)] [buffer 0: tile_bytes] [buffer 1: tile_bytes]
-template <int L, int KIND>
+template <int L, int KIND, bool SMALL>
 __global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d, int chunk_bytes,
              int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out, size_t n, u32 tile_bytes) {
@@ -873,17 +920,20 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    typedef Fp<L, KIND> F;
+    constexpr int N = 2 * L;
+    constexpr int CS = SMALL ? 2 : L;                      // table words per subset coefficient
+    constexpr int WA = SMALL ? F::WSM : F::WACC;
     const u64* coef = stab;
-    const u64* wts = stab + (size_t)nsub * L;
+    const u64* wts = stab + (size_t)nsub * CS;
+    const u64* dinv = wts + d;                             // SMALL only
     const int nl = (chunk_bytes + 7) >> 3;
     const size_t per_elem = (size_t)d * chunk_bytes;
     const size_t ntiles = (n + MPYC_THREADS - 1) / MPYC_THREADS;
     u32 phases = 0;                                      // bit b: parity the next wait on buffer b expects
     const PrssFold fold = prss_fold_setup<L, KIND>(f, nl);
-    const bool unit_w = d == 1 && prss_is_one<L, KIND>(wts, f);
+    const bool unit_w = d == 1 && (SMALL ? wts[0] == 1 : prss_is_one<L, KIND>(wts, f));
     const bool aligned8 = (chunk_bytes & 7) == 0;        // tile base is 16-byte aligned
-    typedef Fp<L, KIND> F;
-    constexpr int N = 2 * L;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t h0 = tile * MPYC_THREADS;
         const size_t cnt = min((size_t)MPYC_THREADS, n - h0);
@@ -899,8 +949,8 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
         };
         if (threadIdx.x == 0) issue(0);
         const size_t h = h0 + threadIdx.x;
-        u32 outer[F::WACC];
-        zero_n<F::WACC>(outer);
+        u32 outer[WA];
+        zero_n<WA>(outer);
         for (int S = 0; S < nsub; S++) {
             const int b = S & 1;
             if (threadIdx.x == 0 && S + 1 < nsub) issue(S + 1);   // buffer (S+1)&1 was released by the barrier below
@@ -915,24 +965,14 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
                     : "memory");
             }
             phases ^= 1u << b;
-            if (h < n) {
-                const unsigned char* base = buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes;
-                u32 y[N], inner[F::WACC];
-                zero_n<F::WACC>(inner);
-                for (int j = 0; j < d; j++) {
-                    u32 v[N];
-                    prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
-                    if (unit_w) copy_n<N>(y, v);
-                    else F::mac(inner, v, as32(wts + (size_t)j * L));
-                }
-                if (!unit_w) F::finish(y, inner, f);
-                F::mac(outer, y, as32(coef + (size_t)S * L));
-            }
+            if (h < n)
+                prss_subset<L, KIND, SMALL>(outer, buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes, d, chunk_bytes,
+                                            nl, bound_bits, aligned8, unit_w, fold, coef + (size_t)S * CS, wts, f);
             __syncthreads();   // every thread is done with buffer b: it may be refilled (by issue(S+2) next trip)
         }
         if (h < n) {
             u32 r[N];
-            F::finish(r, outer, f);
+            prss_finish<L, KIND, SMALL>(r, outer, dinv, f);
             store_limbs<L, false>(out + h * L, r);
         }
     }

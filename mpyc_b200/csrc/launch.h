@@ -29,7 +29,8 @@ struct Launch {
     // small: 64-bit signed-magnitude lambda table
     static cudaError_t recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width, const u64* gtab,
                                  u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st);
-    static cudaError_t prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+    // small: subset coefficients as 64-bit signed-magnitude constants + D^-1 (api.cu: prss_small_table)
+    static cudaError_t prss(const FieldParams& fp, bool small, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                             int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                             cudaStream_t st);
     static cudaError_t matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,

@@ -265,11 +265,11 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
 
 // ---- PRSS / utilities ---------------------------------------------------------------------------
 
-template <int L, int KIND>
+template <int L, int KIND, bool SMALL>
 static cudaError_t prss_tiles_k(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                                 int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                                 u32 tile_bytes, size_t smem, cudaStream_t st) {
-    auto kernel = k_prss_tiles<L, KIND>;
+    auto kernel = k_prss_tiles<L, KIND, SMALL>;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -280,7 +280,7 @@ static cudaError_t prss_tiles_k(const FieldParams& fp, const unsigned char* byte
 }
 
 template <int L>
-cudaError_t Launch<L>::prss(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+cudaError_t Launch<L>::prss(const FieldParams& fp, bool small, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                             int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                             cudaStream_t st) {
     // tiled form (TMA-staged PRF bytes) when the byte streams are 16-byte aligned and two tiles fit in shared memory
@@ -289,11 +289,21 @@ cudaError_t Launch<L>::prss(const FieldParams& fp, const unsigned char* bytes, s
     const bool aligned = ((reinterpret_cast<uintptr_t>(bytes) | subset_stride) & 15u) == 0;
     const bool padded = subset_stride >= (((size_t)n * d * chunk_bytes + 15) & ~(size_t)15);   // last tile reads whole 16-byte groups
     if (aligned && padded && smem <= 160u * 1024u && n >= MPYC_THREADS && getenv("MPYC_B200_PRSS_UNTILED") == nullptr) {
-#define M(K) return prss_tiles_k<L, K>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, (u32)tile_bytes, smem, st)
+#define M(K)                                                                                                            \
+    if (small)                                                                                                          \
+        return prss_tiles_k<L, K, true>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, \
+                                        (u32)tile_bytes, smem, st);                                                     \
+    return prss_tiles_k<L, K, false>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, \
+                                     (u32)tile_bytes, smem, st)
         KIND_SWITCH(fp.kind, M)
 #undef M
     }
-#define M(K) return launch_kernel(k_prss_combine<L, K>, n, tab_bytes, st, fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n)
+#define M(K)                                                                                                            \
+    if (small)                                                                                                          \
+        return launch_kernel(k_prss_combine<L, K, true>, n, tab_bytes, st, fp, bytes, subset_stride, nsub, d, chunk_bytes, \
+                             bound_bits, gtab, tab_bytes, out, n);                                                      \
+    return launch_kernel(k_prss_combine<L, K, false>, n, tab_bytes, st, fp, bytes, subset_stride, nsub, d, chunk_bytes,  \
+                         bound_bits, gtab, tab_bytes, out, n)
     KIND_SWITCH(fp.kind, M)
 #undef M
     return cudaErrorInvalidValue;

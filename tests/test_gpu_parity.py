@@ -560,5 +560,12 @@ def test_prss_pipeline_in_library(p, m, t, monkeypatch):
     one = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
     monkeypatch.setenv('MPYC_B200_PRSS_UNTILED', '1')
     flat = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
-    assert ref.tolist() == one.tolist() == flat.tolist()
+    monkeypatch.setenv('MPYC_B200_PRSS_FULL', '1')       # full products with f_S(i) instead of the small-integer form
+    flat_full = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    monkeypatch.delenv('MPYC_B200_PRSS_UNTILED')
+    tiled_full = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    zero_full = thresha.np_pseudorandom_share_0(F, m, i, prfs(p), uci, 3001).value.tolist()
+    monkeypatch.delenv('MPYC_B200_PRSS_FULL')
+    assert zero_full == got0
+    assert ref.tolist() == one.tolist() == flat.tolist() == flat_full.tolist() == tiled_full.tolist()
     assert ref[:n].tolist() == got               # a longer call extends the same streams (XOF prefix property)
