@@ -748,17 +748,22 @@ __device__ __forceinline__ u64 prss_chunk_limb(const unsigned char* src, int w, 
     return limb;
 }
 
-template <int L, int KIND>
+// A8: chunk_bytes % 8 == 0 and src 8-byte aligned (shared-memory tiles): limbs are read as whole words
+template <int L, int KIND, bool A8>
 __device__ __forceinline__ void prss_value(u32* v, const unsigned char* src, int chunk_bytes, int nl, int bound_bits,
-                                           bool aligned8, const PrssFold& fold, const FieldParams& f) {
+                                           const PrssFold& fold, const FieldParams& f) {
     typedef Fp<L, KIND> F;
     constexpr int N = 2 * L;
+    auto limb_at = [&](int w) -> u64 {
+        if constexpr (A8) return w < nl ? reinterpret_cast<const u64*>(src)[w] : 0ull;
+        else return prss_chunk_limb(src, w, chunk_bytes, false);
+    };
     if (bound_bits > 0) {          // bound 2^b <= p: mask, no reduction (nl <= L)
         zero_n<N>(v);
 #pragma unroll
         for (int l = 0; l < L; l++) {
             if (l < nl) {
-                u64 limb = prss_chunk_limb(src, l, chunk_bytes, aligned8);
+                u64 limb = limb_at(l);
                 const int top = bound_bits - 64 * l;
                 if (top < 64) limb &= top > 0 ? ((1ull << top) - 1) : 0ull;
                 set64(v, l, limb);
@@ -771,26 +776,26 @@ __device__ __forceinline__ void prss_value(u32* v, const unsigned char* src, int
     // aligned pseudo-Mersenne fields always fold (cp = c < 2^16): the Horner form is not even compiled for them
     if (KIND == KIND_PM_ALIGNED || fold.ok) {
 #pragma unroll
-        for (int l = 0; l < L; l++) set64(x, l, prss_chunk_limb(src, l, chunk_bytes, aligned8));
+        for (int l = 0; l < L; l++) set64(x, l, limb_at(l));
         x[N] = x[N + 1] = 0;
 #pragma unroll
         for (int q = 1; q < MAXP; q++) {
             if (q * L < nl) {       // warp-uniform
                 u32 piece[N];
 #pragma unroll
-                for (int l = 0; l < L; l++) set64(piece, l, prss_chunk_limb(src, q * L + l, chunk_bytes, aligned8));
+                for (int l = 0; l < L; l++) set64(piece, l, limb_at(q * L + l));
                 F::mac_const(x, piece, fold.pw[q]);
             }
         }
     } else if constexpr (KIND != KIND_PM_ALIGNED) {
         zero_n<N>(v);
         for (int w = nl - 1; w >= 1; w--) {   // v <- (v * 2^64 + limb) mod p, limb by limb from the top
-            set64(x, 0, prss_chunk_limb(src, w, chunk_bytes, aligned8));
+            set64(x, 0, limb_at(w));
 #pragma unroll
             for (int l = 0; l < N; l++) x[l + 2] = v[l];
             F::reduce_small(v, x, f);
         }
-        set64(x, 0, prss_chunk_limb(src, 0, chunk_bytes, aligned8));
+        set64(x, 0, limb_at(0));
 #pragma unroll
         for (int l = 0; l < N; l++) x[l + 2] = v[l];
     }
@@ -810,9 +815,9 @@ __device__ __forceinline__ bool prss_is_one(const u64* w, const FieldParams& f) 
 //   SMALL = false: acc (WACC limbs) += f_S(i) * y   with y = sum_j v_j w_j mod p, full products against table-form constants
 //   SMALL = true : acc (WSM limbs)  += |num_S| * (+-y), y = sum_j v_j w_j mod p with plain-integer weights; the caller
 //                  reduces once and multiplies by D^-1 (api.cu: prss_small_table)
-template <int L, int KIND, bool SMALL>
+template <int L, int KIND, bool SMALL, bool A8>
 __device__ __forceinline__ void prss_subset(u32* acc, const unsigned char* base, int d, int chunk_bytes, int nl, int bound_bits,
-                                            bool aligned8, bool unit_w, const PrssFold& fold, const u64* coef_S, const u64* wts,
+                                            bool unit_w, const PrssFold& fold, const u64* coef_S, const u64* wts,
                                             const FieldParams& f) {
     typedef Fp<L, KIND> F;
     constexpr int N = 2 * L;
@@ -822,7 +827,7 @@ __device__ __forceinline__ void prss_subset(u32* acc, const unsigned char* base,
         zero_n<F::WSM>(inner);
         for (int j = 0; j < d; j++) {
             u32 v[N];
-            prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
+            prss_value<L, KIND, A8>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, fold, f);
             if (unit_w) copy_n<N>(y, v);
             else F::mac_const(inner, v, wts[j]);
         }
@@ -838,7 +843,7 @@ __device__ __forceinline__ void prss_subset(u32* acc, const unsigned char* base,
         zero_n<F::WACC>(inner);
         for (int j = 0; j < d; j++) {
             u32 v[N];
-            prss_value<L, KIND>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, aligned8, fold, f);
+            prss_value<L, KIND, A8>(v, base + (size_t)j * chunk_bytes, chunk_bytes, nl, bound_bits, fold, f);
             if (unit_w) copy_n<N>(y, v);
             else F::mac(inner, v, as32(wts + (size_t)j * L));
         }
@@ -889,8 +894,8 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
         u32 acc[WA];
         zero_n<WA>(acc);
         for (int S = 0; S < nsub; S++)
-            prss_subset<L, KIND, SMALL>(acc, bytes + (size_t)S * subset_stride + h * (size_t)d * chunk_bytes, d, chunk_bytes, nl,
-                                        bound_bits, false, unit_w, fold, coef + (size_t)S * CS, wts, f);
+            prss_subset<L, KIND, SMALL, false>(acc, bytes + (size_t)S * subset_stride + h * (size_t)d * chunk_bytes, d, chunk_bytes,
+                                               nl, bound_bits, unit_w, fold, coef + (size_t)S * CS, wts, f);
         u32 r[N];
         prss_finish<L, KIND, SMALL>(r, acc, dinv, f);
         store_limbs<L, false>(out + h * L, r);
@@ -901,9 +906,10 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 // tile's PRF bytes of subset S+1 (MPYC_THREADS*d*chunk_bytes contiguous bytes) are fetched global -> shared
 // memory by ONE TMA bulk copy while the threads convert and accumulate subset S from the other buffer
 // (double buffering, one mbarrier per buffer).  HBM is read in full coalesced lines instead of one byte per
-// thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.
+// thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.  A8: chunk_bytes % 8 == 0
+// (the tile base is 16-byte aligned, so every chunk is read as whole 64-bit words from shared memory).
 // smem layout: [table tab_bytes (rounded to 128)] [buffer 0: tile_bytes] [buffer 1: tile_bytes]
-template <int L, int KIND, bool SMALL>
+template <int L, int KIND, bool SMALL, bool A8>
 __global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d, int chunk_bytes,
              int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out, size_t n, u32 tile_bytes) {
@@ -933,7 +939,6 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
     u32 phases = 0;                                      // bit b: parity the next wait on buffer b expects
     const PrssFold fold = prss_fold_setup<L, KIND>(f, nl);
     const bool unit_w = d == 1 && (SMALL ? wts[0] == 1 : prss_is_one<L, KIND>(wts, f));
-    const bool aligned8 = (chunk_bytes & 7) == 0;        // tile base is 16-byte aligned
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t h0 = tile * MPYC_THREADS;
         const size_t cnt = min((size_t)MPYC_THREADS, n - h0);
@@ -966,8 +971,8 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
             }
             phases ^= 1u << b;
             if (h < n)
-                prss_subset<L, KIND, SMALL>(outer, buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes, d, chunk_bytes,
-                                            nl, bound_bits, aligned8, unit_w, fold, coef + (size_t)S * CS, wts, f);
+                prss_subset<L, KIND, SMALL, A8>(outer, buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes, d,
+                                                chunk_bytes, nl, bound_bits, unit_w, fold, coef + (size_t)S * CS, wts, f);
             __syncthreads();   // every thread is done with buffer b: it may be refilled (by issue(S+2) next trip)
         }
         if (h < n) {

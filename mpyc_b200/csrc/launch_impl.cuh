@@ -265,11 +265,11 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
 
 // ---- PRSS / utilities ---------------------------------------------------------------------------
 
-template <int L, int KIND, bool SMALL>
+template <int L, int KIND, bool SMALL, bool A8>
 static cudaError_t prss_tiles_k(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                                 int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                                 u32 tile_bytes, size_t smem, cudaStream_t st) {
-    auto kernel = k_prss_tiles<L, KIND, SMALL>;
+    auto kernel = k_prss_tiles<L, KIND, SMALL, A8>;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -289,14 +289,18 @@ cudaError_t Launch<L>::prss(const FieldParams& fp, bool small, const unsigned ch
     const bool aligned = ((reinterpret_cast<uintptr_t>(bytes) | subset_stride) & 15u) == 0;
     const bool padded = subset_stride >= (((size_t)n * d * chunk_bytes + 15) & ~(size_t)15);   // last tile reads whole 16-byte groups
     if (aligned && padded && smem <= 160u * 1024u && n >= MPYC_THREADS && getenv("MPYC_B200_PRSS_UNTILED") == nullptr) {
-#define M(K)                                                                                                            \
-    if (small)                                                                                                          \
-        return prss_tiles_k<L, K, true>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, \
-                                        (u32)tile_bytes, smem, st);                                                     \
-    return prss_tiles_k<L, K, false>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, \
-                                     (u32)tile_bytes, smem, st)
+#define TILES(K, SM, A8) \
+    return prss_tiles_k<L, K, SM, A8>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, (u32)tile_bytes, smem, st)
+#define M(K)                                   \
+    if (small) {                               \
+        if (chunk_bytes % 8 == 0) TILES(K, true, true);  \
+        TILES(K, true, false);                 \
+    }                                          \
+    if (chunk_bytes % 8 == 0) TILES(K, false, true);     \
+    TILES(K, false, false)
         KIND_SWITCH(fp.kind, M)
 #undef M
+#undef TILES
     }
 #define M(K)                                                                                                            \
     if (small)                                                                                                          \
