@@ -126,6 +126,13 @@ int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secr
                                     size_t share_stride, size_t n, int t, int m,
                                     const uint8_t key32[32], uint64_t nonce, void* stream);
 
+/* Same, every share row written to its own destination: d_share_rows is a HOST array of m device pointers (m <= 32),
+ * row i of n elements.  The pointers may refer to another GPU's memory mapped into this process (CUDA IPC / peer
+ * access): a dealer then writes each recipient's row straight into the recipient GPU over NVLink -- the exchange
+ * step of runtime.py:660-669 fused into share generation (mpyc_b200.exchange.PeerReshare). */
+int mpyc_b200_shamir_split_generate_rows(const mpyc_b200_field* f, const void* d_secrets, void* const* d_share_rows,
+                                         size_t n, int t, int m, const uint8_t key32[32], uint64_t nonce, void* stream);
+
 /* ---- Lagrange recombination ----------------------------------------------------------------
  * thresha._recombination_vector (mpyc/thresha.py:67-85): lambda[r][i] for x-coordinates xs[0..k)
  * and recombination points x_rs[0..width); written as width*k*L host limbs, canonical. */
@@ -163,6 +170,10 @@ int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key
 /* SHAKE128 (FIPS 202) of `in`, squeezed to outlen bytes: hashlib.shake_128(in).digest(outlen), the XOF of
  * thresha.PRF (mpyc/thresha.py:257).  Host only; no GPU involved. */
 int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen);
+
+/* Lets kernels launched on `device` load/store memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent).
+ * Needed once per pair before mpyc_b200_shamir_split_generate_rows is given rows on another GPU. */
+int mpyc_b200_enable_peer_access(int device, int peer_device);
 
 /* ---- utilities -------------------------------------------------------------------------------
  * deterministic synthetic residues (tests, bench): element h = (L+1 SplitMix64 words of counter

@@ -63,6 +63,8 @@ _SIGNATURES = {
                                        c_int, c_int, c_void_p]),
     'mpyc_b200_shamir_split_generate': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
                                                 POINTER(c_uint8), c_uint64, c_void_p]),
+    'mpyc_b200_shamir_split_generate_rows': (c_int, [_field_p, c_void_p, POINTER(c_void_p), c_size_t, c_int, c_int,
+                                                     POINTER(c_uint8), c_uint64, c_void_p]),
     'mpyc_b200_recombination_vector': (c_int, [_field_p, POINTER(c_int64), c_int, POINTER(c_int64), c_int,
                                                POINTER(c_uint64)]),
     'mpyc_b200_shamir_recombine': (c_int, [_field_p, POINTER(c_void_p), POINTER(c_int64), c_int, POINTER(c_int64),
@@ -71,6 +73,7 @@ _SIGNATURES = {
                                        POINTER(c_uint64), c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_prss_host': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int, c_int,
                                     POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_int, c_int]),
+    'mpyc_b200_enable_peer_access': (c_int, [c_int, c_int]),
     'mpyc_b200_shake128': (c_int, [c_char_p, c_size_t, c_void_p, c_size_t]),
     'mpyc_b200_fill_random': (c_int, [_field_p, c_void_p, c_size_t, c_uint64, c_uint64, c_void_p]),
     'mpyc_b200_count_mismatch': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

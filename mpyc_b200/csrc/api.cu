@@ -628,22 +628,25 @@ MPYC_API int mpyc_b200_shamir_split(const mpyc_b200_field* f, const void* d_secr
     const size_t L = f->fp.L;
     return with_limbs((int)L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
+        ShareDst dst = {};
+        dst.base = (u64*)d_shares;
+        dst.stride = share_stride * LL;
         return launch_status(Launch<LL>::split(f->fp, tab.full, (const u64*)d_secrets, (const u64*)d_coeffs,
-                                               coeff_stride * LL, (u64*)d_shares, share_stride * LL, n, t, m, tab.d,
-                                               tab.bytes, st),
+                                               coeff_stride * LL, dst, n, t, m, tab.d, tab.bytes, st),
                              "shamir_split launch");
     });
 }
 
-MPYC_API int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secrets, void* d_shares,
-                                             size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
-                                             uint64_t nonce, void* stream) {
+static int split_generate_impl(const mpyc_b200_field* f, const void* d_secrets, void* d_shares, size_t share_stride,
+                               void* const* d_share_rows, size_t n, int t, int m, const uint8_t key32[32], uint64_t nonce,
+                               void* stream) {
     if (!f || !key32) return fail(MPYC_B200_EINVAL, "shamir_split_generate: null argument");
     if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
     REQUIRE_PRIME(f, "shamir_split_generate");
     if (t > 4) return fail(MPYC_B200_EUNSUPPORTED, "shamir_split_generate: t <= 4 (use explicit coefficients beyond)");
+    if (d_share_rows && m > MPYC_MAX_SHARE_ROWS) return fail(MPYC_B200_EUNSUPPORTED, "shamir_split_generate_rows: at most 32 rows");
     if (n == 0) return MPYC_B200_OK;
-    if (!d_secrets || !d_shares || share_stride < n) return fail(MPYC_B200_EINVAL, "shamir_split_generate: bad buffers");
+    if (!d_secrets || (!d_share_rows && (!d_shares || share_stride < n))) return fail(MPYC_B200_EINVAL, "shamir_split_generate: bad buffers");
     DevTable tab;
     int rc = split_table(f, t, m, &tab);
     if (rc) return rc;
@@ -655,10 +658,33 @@ MPYC_API int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const voi
     cudaStream_t st = (cudaStream_t)stream;
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        return launch_status(Launch<LL>::split_gen(f->fp, tab.full, key, (const u64*)d_secrets, (u64*)d_shares,
-                                                   share_stride * LL, n, t, m, tab.d, tab.bytes, st),
+        ShareDst dst = {};
+        if (d_share_rows) {
+            dst.use_rows = 1;
+            for (int i = 0; i < m; i++) {
+                if (!d_share_rows[i]) return fail(MPYC_B200_EINVAL, "shamir_split_generate_rows: null row");
+                dst.rows[i] = (u64*)d_share_rows[i];
+            }
+        } else {
+            dst.base = (u64*)d_shares;
+            dst.stride = share_stride * LL;
+        }
+        return launch_status(Launch<LL>::split_gen(f->fp, tab.full, key, (const u64*)d_secrets, dst, n, t, m, tab.d, tab.bytes, st),
                              "shamir_split_generate launch");
     });
+}
+
+MPYC_API int mpyc_b200_shamir_split_generate(const mpyc_b200_field* f, const void* d_secrets, void* d_shares,
+                                             size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
+                                             uint64_t nonce, void* stream) {
+    return split_generate_impl(f, d_secrets, d_shares, share_stride, nullptr, n, t, m, key32, nonce, stream);
+}
+
+MPYC_API int mpyc_b200_shamir_split_generate_rows(const mpyc_b200_field* f, const void* d_secrets, void* const* d_share_rows,
+                                                  size_t n, int t, int m, const uint8_t key32[32], uint64_t nonce,
+                                                  void* stream) {
+    if (!d_share_rows) return fail(MPYC_B200_EINVAL, "shamir_split_generate_rows: null row table");
+    return split_generate_impl(f, d_secrets, nullptr, 0, d_share_rows, n, t, m, key32, nonce, stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1106,6 +1132,23 @@ MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const voi
 // ---------------------------------------------------------------------------------------
 // PRF / PRSS with the XOF inside the library
 // ---------------------------------------------------------------------------------------
+
+MPYC_API int mpyc_b200_enable_peer_access(int device, int peer_device) {
+    if (device == peer_device) return MPYC_B200_OK;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) return fail(MPYC_B200_EUNSUPPORTED, "enable_peer_access: the devices cannot access each other's memory");
+    int prev = 0;
+    CU(cudaGetDevice(&prev));
+    CU(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();   // clear the sticky-less error state
+        e = cudaSuccess;
+    }
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "cudaDeviceEnablePeerAccess");
+}
 
 MPYC_API int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen) {
     if ((inlen && !in) || (outlen && !out)) return fail(MPYC_B200_EINVAL, "shake128: null buffer");

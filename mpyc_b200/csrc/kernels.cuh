@@ -26,6 +26,18 @@ struct RowPtrs {
     const u64* p[MPYC_MAX_POINTS];
 };
 
+// Destination of the m share rows of K2: base + i*stride (limbs), or -- rows mode -- one explicit pointer per party.
+// Rows mode is how a dealer writes each recipient's row straight into that recipient GPU's memory (peer pointers
+// over NVLink, mpyc_b200.exchange.PeerReshare) instead of into a local matrix that is copied afterwards.
+#define MPYC_MAX_SHARE_ROWS 32
+struct ShareDst {
+    u64* base;
+    size_t stride;
+    int use_rows;
+    u64* rows[MPYC_MAX_SHARE_ROWS];
+    __device__ __forceinline__ u64* row(int i) const { return use_rows ? rows[i] : base + (size_t)i * stride; }
+};
+
 struct ScalarParam {
     u64 v[4];
 };
@@ -341,8 +353,8 @@ k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, in
 
 // shares of one item (E elements) from its t+1 polynomial coefficient rows held in registers
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
-__device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], u64* shares,
-                                              size_t sstride, int m, const u64* tab, size_t limb_off) {
+__device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], const ShareDst& dst,
+                                              int m, const u64* tab, size_t limb_off) {
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
     constexpr int MU = MPYC_SPLIT_MU;   // shares computed per trip of the party loop
@@ -367,7 +379,7 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
                 else copy_n<N>(r + e * N, acc);
             }
         }
-        store_limbs<E * L, VEC>(shares + (size_t)i * sstride + limb_off, r);
+        store_limbs<E * L, VEC>(dst.row(i) + limb_off, r);
     }
 }
 
@@ -375,7 +387,7 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
 // issued before the first multiply so that U*(t+1) 16-byte requests per thread are in flight.
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, int U>
 __device__ __forceinline__ void split_items(const FieldParams& f, const u64* secrets, const u64* coeffs,
-                                            size_t cstride, u64* shares, size_t sstride, int m, const u64* tab,
+                                            size_t cstride, const ShareDst& dst, int m, const u64* tab,
                                             size_t limb_off, size_t limb_step) {
     constexpr int N = 2 * L;
     u32 M[U][TP1][E * N];
@@ -388,7 +400,7 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
-        split_compute<L, KIND, TP1, FULL, E, VEC>(f, M[u], shares, sstride, m, tab, limb_off + u * limb_step);
+        split_compute<L, KIND, TP1, FULL, E, VEC>(f, M[u], dst, m, tab, limb_off + u * limb_step);
 }
 
 #ifndef MPYC_SPLIT_MINB
@@ -397,7 +409,7 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
 __global__ void __launch_bounds__(MPYC_THREADS, MPYC_SPLIT_MINB)
 k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
-        u64* __restrict__ shares, size_t sstride, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
+        ShareDst dst, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
     extern __shared__ __align__(16) u64 stab[];
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
@@ -408,14 +420,14 @@ k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ 
     const size_t n_items = n / E;
     size_t it = tid;
     for (; it + (U - 1) * nth < n_items; it += U * nth)
-        split_items<L, KIND, TP1, FULL, E, VEC, U>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+        split_items<L, KIND, TP1, FULL, E, VEC, U>(f, secrets, coeffs, cstride, dst, m, stab,
                                                    it * (size_t)(E * L), nth * (size_t)(E * L));
     for (; it < n_items; it += nth)
-        split_items<L, KIND, TP1, FULL, E, VEC, 1>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+        split_items<L, KIND, TP1, FULL, E, VEC, 1>(f, secrets, coeffs, cstride, dst, m, stab,
                                                    it * (size_t)(E * L), 0);
     if constexpr (E > 1) {
         for (size_t h = n_items * E + tid; h < n; h += nth)
-            split_items<L, KIND, TP1, FULL, 1, false, 1>(f, secrets, coeffs, cstride, shares, sstride, m, stab,
+            split_items<L, KIND, TP1, FULL, 1, false, 1>(f, secrets, coeffs, cstride, dst, m, stab,
                                                          h * (size_t)L, 0);
     }
 }
@@ -470,7 +482,7 @@ struct GenLayout {
 
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
 __device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaChaKey& key, u64 counter0,
-                                               const u64* secrets, u64* shares, size_t sstride, int m,
+                                               const u64* secrets, const ShareDst& dst, int m,
                                                const u64* tab, size_t limb_off) {
     constexpr int N = 2 * L;
     constexpr int NC = (TP1 - 1) * E;   // coefficients of this item
@@ -494,12 +506,12 @@ __device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaCh
         const int j = 1 + c / E, e = c % E;
         Fp<L, KIND>::reduce_small(M[j] + e * N, x, f);
     }
-    split_compute<L, KIND, TP1, FULL, E, VEC>(f, M, shares, sstride, m, tab, limb_off);
+    split_compute<L, KIND, TP1, FULL, E, VEC>(f, M, dst, m, tab, limb_off);
 }
 
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
 __global__ void MPYC_LB
-k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, u64* __restrict__ shares, size_t sstride,
+k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, ShareDst dst,
             size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
     extern __shared__ __align__(16) u64 stab[];
     __shared__ __align__(8) u64 mbar;
@@ -510,13 +522,13 @@ k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, u64* 
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
     for (size_t it = tid; it < n_items; it += nth)
-        split_gen_item<L, KIND, TP1, FULL, E, VEC>(f, key, (u64)it * BPI, secrets, shares, sstride, m, stab,
+        split_gen_item<L, KIND, TP1, FULL, E, VEC>(f, key, (u64)it * BPI, secrets, dst, m, stab,
                                                    it * (size_t)(E * L));
     if constexpr (E > 1) {
         ChaChaKey tail = key;
         tail.nonce[1] ^= 0x80000000u;   // disjoint keystream for the scalar tail
         for (size_t h = n_items * E + tid; h < n; h += nth)
-            split_gen_item<L, KIND, TP1, FULL, 1, false>(f, tail, (u64)h * BPI, secrets, shares, sstride, m, stab,
+            split_gen_item<L, KIND, TP1, FULL, 1, false>(f, tail, (u64)h * BPI, secrets, dst, m, stab,
                                                          h * (size_t)L);
     }
 }

@@ -21,11 +21,12 @@ struct Launch {
     // out[h] = a[h]^-1 (0 for a[h] == 0, reported in zero_flag); ex = p - 2; a and out must not alias
     static cudaError_t inv_batch(const FieldParams& fp, const ExpParams& ex, const u64* a, u64* out, int* zero_flag,
                                  size_t n, cudaStream_t st);
+    // dst: strided matrix (base, stride in limbs) or explicit row pointers (use_rows)
     static cudaError_t split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
-                             u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
+                             const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st);
-    static cudaError_t split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets, u64* shares,
-                                 size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st);
+    static cudaError_t split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets,
+                                 const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st);
     // small: 64-bit signed-magnitude lambda table
     static cudaError_t recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width, const u64* gtab,
                                  u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st);

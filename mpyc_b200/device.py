@@ -299,6 +299,20 @@ def shamir_split_generate(ctx, secrets: DeviceArray, t, m, key=None, nonce=0, ou
     return out
 
 
+def shamir_split_generate_rows(ctx, secrets: DeviceArray, t, m, row_ptrs, key=None, nonce=0):
+    """As shamir_split_generate, every share row written to its own destination: row_ptrs = m device addresses
+    (ints), each with room for n elements, 32-byte aligned for the vector path.  A row may live on another GPU
+    (memory mapped through CUDA IPC with peer access enabled): the kernel then stores it there over NVLink."""
+    import os
+    key = os.urandom(32) if key is None else bytes(key)
+    if len(key) != 32 or len(row_ptrs) != m:
+        raise ValueError('key must be 32 bytes and row_ptrs must hold m addresses')
+    secrets._check_contiguous()
+    kbuf = (ctypes.c_uint8 * 32).from_buffer_copy(key)
+    check(lib.mpyc_b200_shamir_split_generate_rows(ctx.handle, secrets.ptr, _cabi.ptr_array([int(a) for a in row_ptrs]),
+                                                   secrets.n, t, m, kbuf, int(nonce) & (2**63 - 1), _stream_ptr()))
+
+
 def matmul(ctx, A, B, r, k, c):
     """C = A @ B mod p for row-major DeviceArrays A (r*k elements) and B (k*c elements): DeviceArray of r*c
     elements (FiniteFieldArray.__matmul__, mpyc/finfields.py:1126-1146)."""

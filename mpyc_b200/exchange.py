@@ -16,6 +16,9 @@ order, which is how NCCL matches sends with receives between a pair of ranks.
 The arithmetic is injected as an `engine` (split / recombine on tensors) so that the routing can be exercised on
 CPU tensors over gloo (tests/test_exchange_gloo.py) with the oracle standing in for the kernels; on the GPU the
 engine is `DeviceEngine` below (mpyc_b200.device: K2 in generate mode, K3).
+
+`PeerReshare` goes one step further on NVLink-connected GPUs: K2 itself stores each recipient's row into the
+recipient GPU's memory, so the exchange is no separate pass at all.
 """
 import torch
 import torch.distributed as dist
@@ -91,6 +94,71 @@ def reshare(engine, shares, t, m, group=None, first_dealer=0):
     # 3. every local party recombines the 2t+1 rows it now holds
     xs = [j + 1 for j in dealers]
     return {i: engine.recombine(xs, recv[i]) for i in mine}
+
+
+class PeerReshare:
+    """The resharing round with the exchange fused into share generation: every dealer's K2 stores row i straight
+    into the receive buffer of party i's GPU (peer memory mapped through CUDA IPC, stores travel over NVLink), one
+    stream-ordered all-reduce tells every rank that all rows have landed, K3s recombines.  No staging matrix, no copy
+    pass: a share row crosses HBM once on the way out instead of three times (K2 write, NCCL read, NCCL write).
+
+    Receive buffers are double-buffered by round parity; a dealer can only be one round ahead of a recipient
+    (the all-reduce of round r+1 cannot complete before the recipient has issued its K3 of round r), so the rows
+    of round r+2 never overwrite rows still being read.  One instance per (field, m, t, n)."""
+
+    def __init__(self, ctx, m, t, n, group=None, first_dealer=0):
+        from torch.multiprocessing.reductions import reduce_tensor
+        from mpyc_b200._cabi import lib, check
+        self.ctx, self.m, self.t, self.n, self.group = ctx, m, t, n, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.mine = local_parties(m, self.world, self.rank)
+        self.dealers = [(first_dealer + a) % m for a in range(2 * t + 1)]
+        if len(set(self.dealers)) != len(self.dealers) or m > 32:
+            raise ValueError('peer resharing needs 2t+1 <= m <= 32')
+        L = ctx.nlimbs
+        self.row_words = (n * L * 8 + 31) // 32 * 4            # int64 words per row, rows 32-byte aligned
+        slots = max(len(local_parties(m, self.world, r)) for r in range(self.world))
+        self.dev = torch.cuda.current_device()
+        self.buf = torch.zeros((2, slots, len(self.dealers), self.row_words), dtype=torch.int64, device='cuda')
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.dev, reduce_tensor(self.buf)), group=group)
+        self.peer = {}
+        for r, (peer_dev, (rebuild, args)) in enumerate(handles):
+            if r == self.rank:
+                self.peer[r] = self.buf
+            else:
+                self.peer[r] = rebuild(*args)                 # maps the peer's buffer into this process (cudaIpcOpenMemHandle)
+                if peer_dev != self.dev:
+                    check(lib.mpyc_b200_enable_peer_access(self.dev, peer_dev))
+        self.flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        self.round = 0
+        self._nonce = 0
+        dist.barrier(group)                                    # nobody writes before every mapping exists
+
+    def _row_ptr(self, gen, party, dealer_index):
+        t = self.peer[owner(party, self.world)]
+        return t[gen, party // self.world, dealer_index].data_ptr()
+
+    def reshare(self, shares):
+        """shares: {party j: limb tensor (n, L)} for the local parties; returns {party i: new share tensor (n, L)}."""
+        from mpyc_b200 import device as dev
+        if sorted(shares) != self.mine:
+            raise ValueError(f'rank {self.rank} hosts parties {self.mine}, got shares for {sorted(shares)}')
+        gen = self.round & 1
+        for a, j in enumerate(self.dealers):
+            if j in shares:
+                self._nonce += 1
+                dev.shamir_split_generate_rows(self.ctx, dev.DeviceArray(self.ctx, shares[j]), self.t, self.m,
+                                               [self._row_ptr(gen, i, a) for i in range(self.m)], nonce=self._nonce)
+        dist.all_reduce(self.flag, group=self.group)           # stream-ordered: completes once every rank's K2s are done
+        xs = [j + 1 for j in self.dealers]
+        L, n = self.ctx.nlimbs, self.n
+        out = {}
+        for i in self.mine:
+            rows = [dev.DeviceArray(self.ctx, self.buf[gen, i // self.world, a, :n * L].view(n, L)) for a in range(len(self.dealers))]
+            out[i] = dev.shamir_recombine(self.ctx, xs, rows).t
+        self.round += 1
+        return out
 
 
 def _global_rank(group_rank, group):

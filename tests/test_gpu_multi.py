@@ -90,7 +90,13 @@ def _reshare_worker(rank, world, port, q):
             sa, sb = dev.shamir_split(ctx, A, CA, t, m), dev.shamir_split(ctx, B, CB, t, m)
             mine = exchange.local_parties(m, world, rank)
             prod = {j: (sa.row(j) * sb.row(j)).t for j in mine}          # degree-2t local products
-            new = exchange.reshare(exchange.DeviceEngine(ctx), prod, t, m, first_dealer=1)
+            if os.environ.get('MPYC_TEST_PEER') == '1':
+                # exchange fused into K2: rows stored straight into the recipient GPU (three rounds: both buffer parities)
+                peer = exchange.PeerReshare(ctx, m, t, n, first_dealer=1)
+                for _ in range(3):
+                    new = peer.reshare(prod)
+            else:
+                new = exchange.reshare(exchange.DeviceEngine(ctx), prod, t, m, first_dealer=1)
             assert sorted(new) == mine
             # collect every party's new share on every rank and open the product with two different party sets
             full = [None] * m
@@ -110,10 +116,13 @@ def _reshare_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_colocated_reshare_over_nccl():
+@pytest.mark.parametrize('mode', ['nccl', 'peer'])
+def test_colocated_reshare_over_nccl(mode, monkeypatch):
     """secure multiplication's resharing step with the parties spread over 2 GPUs -- K2 on every
-    dealer, limb rows exchanged GPU to GPU (grouped ncclSend/ncclRecv), K3s on every party; any t+1 of the new
-    shares open the product."""
+    dealer, limb rows exchanged GPU to GPU (mode nccl: grouped ncclSend/ncclRecv; mode peer: K2 stores each row
+    straight into the recipient GPU's memory over NVLink), K3s on every party; any t+1 of the new shares open the
+    product."""
+    monkeypatch.setenv('MPYC_TEST_PEER', '1' if mode == 'peer' else '0')
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
     port = s.getsockname()[1]
