@@ -175,6 +175,15 @@ int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t out
  * Needed once per pair before mpyc_b200_shamir_split_generate_rows is given rows on another GPU. */
 int mpyc_b200_enable_peer_access(int device, int peer_device);
 
+/* Device buffers that kernels of ANOTHER process (one process per GPU) can store into: peer_alloc = cudaMalloc (zeroed)
+ * + cudaIpcGetMemHandle; peer_open maps an exported buffer into the calling process in the current device's context
+ * with peer access to the exporting GPU enabled (cudaIpcOpenMemHandle, cudaIpcMemLazyEnablePeerAccess).  The owner
+ * frees with peer_free after every importer has called peer_close. */
+int mpyc_b200_peer_alloc(size_t bytes, void** d_ptr, uint8_t handle[64]);
+int mpyc_b200_peer_open(const uint8_t handle[64], void** d_ptr);
+int mpyc_b200_peer_close(void* d_ptr);
+int mpyc_b200_peer_free(void* d_ptr);
+
 /* ---- utilities -------------------------------------------------------------------------------
  * deterministic synthetic residues (tests, bench): element h = (L+1 SplitMix64 words of counter
  * seed + (stream_id << 56) + h*(L+1) + w, truncated to bits(p)+64 bits) mod p -- same recipe as

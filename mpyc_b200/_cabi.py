@@ -74,6 +74,10 @@ _SIGNATURES = {
     'mpyc_b200_prss_host': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int, c_int,
                                     POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_int, c_int]),
     'mpyc_b200_enable_peer_access': (c_int, [c_int, c_int]),
+    'mpyc_b200_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), POINTER(c_uint8)]),
+    'mpyc_b200_peer_open': (c_int, [POINTER(c_uint8), POINTER(c_void_p)]),
+    'mpyc_b200_peer_close': (c_int, [c_void_p]),
+    'mpyc_b200_peer_free': (c_int, [c_void_p]),
     'mpyc_b200_shake128': (c_int, [c_char_p, c_size_t, c_void_p, c_size_t]),
     'mpyc_b200_fill_random': (c_int, [_field_p, c_void_p, c_size_t, c_uint64, c_uint64, c_void_p]),
     'mpyc_b200_count_mismatch': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -1150,6 +1150,44 @@ MPYC_API int mpyc_b200_enable_peer_access(int device, int peer_device) {
     return e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "cudaDeviceEnablePeerAccess");
 }
 
+// Receive buffers another process's kernels can store into: plain cudaMalloc allocations exported / imported with
+// CUDA IPC.  The importer opens the handle in ITS OWN device's context (cudaIpcMemLazyEnablePeerAccess turns peer
+// access to the exporting GPU on), so kernels it launches can address the memory directly over NVLink.
+MPYC_API int mpyc_b200_peer_alloc(size_t bytes, void** d_ptr, uint8_t handle[64]) {
+    if (!d_ptr || !handle || bytes == 0) return fail(MPYC_B200_EINVAL, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "peer_alloc");
+    }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_peer_open(const uint8_t handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return fail(MPYC_B200_EINVAL, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_peer_close(void* d_ptr) {
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_peer_free(void* d_ptr) {
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return MPYC_B200_OK;
+}
+
 MPYC_API int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen) {
     if ((inlen && !in) || (outlen && !out)) return fail(MPYC_B200_EINVAL, "shake128: null buffer");
     mpyc_shake::Shake128 x;

@@ -107,7 +107,7 @@ class PeerReshare:
     of round r+2 never overwrite rows still being read.  One instance per (field, m, t, n)."""
 
     def __init__(self, ctx, m, t, n, group=None, first_dealer=0):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes
         from mpyc_b200._cabi import lib, check
         self.ctx, self.m, self.t, self.n, self.group = ctx, m, t, n, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -116,32 +116,51 @@ class PeerReshare:
         if len(set(self.dealers)) != len(self.dealers) or m > 32:
             raise ValueError('peer resharing needs 2t+1 <= m <= 32')
         L = ctx.nlimbs
-        self.row_words = (n * L * 8 + 31) // 32 * 4            # int64 words per row, rows 32-byte aligned
-        slots = max(len(local_parties(m, self.world, r)) for r in range(self.world))
-        self.dev = torch.cuda.current_device()
-        self.buf = torch.zeros((2, slots, len(self.dealers), self.row_words), dtype=torch.int64, device='cuda')
+        self.row_bytes = (n * L * 8 + 31) // 32 * 32            # rows 32-byte aligned (256-bit stores)
+        self.slots = max(len(local_parties(m, self.world, r)) for r in range(self.world))
+        nbytes = 2 * self.slots * len(self.dealers) * self.row_bytes
+        # own receive buffer: [generation][local party slot][dealer index] rows, exported to the other ranks
+        own, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        check(lib.mpyc_b200_peer_alloc(nbytes, ctypes.byref(own), handle))
+        self._own = own.value
         handles = [None] * self.world
-        dist.all_gather_object(handles, (self.dev, reduce_tensor(self.buf)), group=group)
-        self.peer = {}
-        for r, (peer_dev, (rebuild, args)) in enumerate(handles):
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.base = {}
+        for r, h in enumerate(handles):
             if r == self.rank:
-                self.peer[r] = self.buf
+                self.base[r] = self._own
             else:
-                self.peer[r] = rebuild(*args)                 # maps the peer's buffer into this process (cudaIpcOpenMemHandle)
-                if peer_dev != self.dev:
-                    check(lib.mpyc_b200_enable_peer_access(self.dev, peer_dev))
+                ptr = ctypes.c_void_p()
+                check(lib.mpyc_b200_peer_open((ctypes.c_uint8 * 64).from_buffer_copy(h), ctypes.byref(ptr)))
+                self.base[r] = ptr.value
         self.flag = torch.zeros(1, dtype=torch.int32, device='cuda')
         self.round = 0
         self._nonce = 0
         dist.barrier(group)                                    # nobody writes before every mapping exists
 
+    def close(self):
+        """Unmap the peers' buffers and free the own one (collective: every rank must call it)."""
+        from mpyc_b200._cabi import lib, check
+        if self._own is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        for r, ptr in self.base.items():
+            if r != self.rank:
+                check(lib.mpyc_b200_peer_close(ptr))
+        dist.barrier(self.group)
+        check(lib.mpyc_b200_peer_free(self._own))
+        self._own = None
+
     def _row_ptr(self, gen, party, dealer_index):
-        t = self.peer[owner(party, self.world)]
-        return t[gen, party // self.world, dealer_index].data_ptr()
+        slot = party // self.world
+        return self.base[owner(party, self.world)] + ((gen * self.slots + slot) * len(self.dealers) + dealer_index) * self.row_bytes
 
     def reshare(self, shares):
         """shares: {party j: limb tensor (n, L)} for the local parties; returns {party i: new share tensor (n, L)}."""
-        from mpyc_b200 import device as dev
+        import ctypes
+        from mpyc_b200 import _cabi, device as dev
+        from mpyc_b200._cabi import lib, check
         if sorted(shares) != self.mine:
             raise ValueError(f'rank {self.rank} hosts parties {self.mine}, got shares for {sorted(shares)}')
         gen = self.round & 1
@@ -151,12 +170,16 @@ class PeerReshare:
                 dev.shamir_split_generate_rows(self.ctx, dev.DeviceArray(self.ctx, shares[j]), self.t, self.m,
                                                [self._row_ptr(gen, i, a) for i in range(self.m)], nonce=self._nonce)
         dist.all_reduce(self.flag, group=self.group)           # stream-ordered: completes once every rank's K2s are done
-        xs = [j + 1 for j in self.dealers]
-        L, n = self.ctx.nlimbs, self.n
+        xs = _cabi.i64_array([j + 1 for j in self.dealers])
+        zero = _cabi.i64_array([0])
+        L, n, k = self.ctx.nlimbs, self.n, len(self.dealers)
         out = {}
         for i in self.mine:
-            rows = [dev.DeviceArray(self.ctx, self.buf[gen, i // self.world, a, :n * L].view(n, L)) for a in range(len(self.dealers))]
-            out[i] = dev.shamir_recombine(self.ctx, xs, rows).t
+            res = torch.empty((n, L), dtype=torch.int64, device='cuda')
+            rows = _cabi.ptr_array([self._row_ptr(gen, i, a) for a in range(k)])
+            check(lib.mpyc_b200_shamir_recombine(self.ctx.handle, rows, xs, k, zero, 1, ctypes.c_void_p(res.data_ptr()), n, n,
+                                                 dev._stream_ptr()))
+            out[i] = res
         self.round += 1
         return out
 

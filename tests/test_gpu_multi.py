@@ -95,6 +95,7 @@ def _reshare_worker(rank, world, port, q):
                 peer = exchange.PeerReshare(ctx, m, t, n, first_dealer=1)
                 for _ in range(3):
                     new = peer.reshare(prod)
+                peer.close()
             else:
                 new = exchange.reshare(exchange.DeviceEngine(ctx), prod, t, m, first_dealer=1)
             assert sorted(new) == mine

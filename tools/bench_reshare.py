@@ -50,5 +50,5 @@ for p, m, t, n in ((2**128 - 173, 5, 2, 20_000_000), (2**256 - 189, 7, 3, 213_24
                           'exchange_GBps_aggregate': crossing * n * eb / (float(ms.item()) * 1e-3) / 1e9,
                           'ms_per_round_peer_stores': results['peer_stores_in_K2'],
                           'elements_reshared_per_s_peer_stores': m * n / (results['peer_stores_in_K2'] * 1e-3)}), flush=True)
-    del peer
+    peer.close()
 dist.destroy_process_group()
