@@ -62,7 +62,7 @@ def build(force=False, verbose=False, defines=(), lib=None):
             OBJ, LIB = saved
     os.makedirs(OBJ, exist_ok=True)
     build_codec(force=False)
-    stamp = os.path.join(OBJ, 'digest.txt')
+    stamp = LIB + '.digest'   # next to the library: travels with it to the GPU box, where nothing is rebuilt
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
