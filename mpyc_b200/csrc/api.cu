@@ -628,11 +628,9 @@ MPYC_API int mpyc_b200_shamir_split(const mpyc_b200_field* f, const void* d_secr
     const size_t L = f->fp.L;
     return with_limbs((int)L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        ShareDst dst = {};
-        dst.base = (u64*)d_shares;
-        dst.stride = share_stride * LL;
         return launch_status(Launch<LL>::split(f->fp, tab.full, (const u64*)d_secrets, (const u64*)d_coeffs,
-                                               coeff_stride * LL, dst, n, t, m, tab.d, tab.bytes, st),
+                                               coeff_stride * LL, (u64*)d_shares, share_stride * LL, n, t, m, tab.d,
+                                               tab.bytes, st),
                              "shamir_split launch");
     });
 }
@@ -658,7 +656,7 @@ static int split_generate_impl(const mpyc_b200_field* f, const void* d_secrets, 
     cudaStream_t st = (cudaStream_t)stream;
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        ShareDst dst = {};
+        ShareDst dst;
         if (d_share_rows) {
             dst.use_rows = 1;
             for (int i = 0; i < m; i++) {

@@ -26,16 +26,19 @@ struct RowPtrs {
     const u64* p[MPYC_MAX_POINTS];
 };
 
-// Destination of the m share rows of K2: base + i*stride (limbs), or -- rows mode -- one explicit pointer per party.
-// Rows mode is how a dealer writes each recipient's row straight into that recipient GPU's memory (peer pointers
-// over NVLink, mpyc_b200.exchange.PeerReshare) instead of into a local matrix that is copied afterwards.
+// Destination of the m share rows of K2 (a template parameter of the split kernels, so that the strided form costs
+// nothing): StridedDst = base + i*stride (limbs); RowsDst = one explicit pointer per party -- how a dealer writes each
+// recipient's row straight into that recipient GPU's memory (peer pointers over NVLink,
+// mpyc_b200.exchange.PeerReshare) instead of into a local matrix that is copied afterwards.
 #define MPYC_MAX_SHARE_ROWS 32
-struct ShareDst {
+struct StridedDst {
     u64* base;
     size_t stride;
-    int use_rows;
+    __device__ __forceinline__ u64* row(int i) const { return base + (size_t)i * stride; }
+};
+struct RowsDst {
     u64* rows[MPYC_MAX_SHARE_ROWS];
-    __device__ __forceinline__ u64* row(int i) const { return use_rows ? rows[i] : base + (size_t)i * stride; }
+    __device__ __forceinline__ u64* row(int i) const { return rows[i]; }
 };
 
 struct ScalarParam {
@@ -352,8 +355,8 @@ k_inv_batch(FieldParams f, ExpParams ex, const u64* __restrict__ a, u64* out, in
 #endif
 
 // shares of one item (E elements) from its t+1 polynomial coefficient rows held in registers
-template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
-__device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], const ShareDst& dst,
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, class DST>
+__device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*M)[E * 2 * L], const DST& dst,
                                               int m, const u64* tab, size_t limb_off) {
     constexpr int N = 2 * L;
     typedef Fp<L, KIND> F;
@@ -387,7 +390,7 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
 // issued before the first multiply so that U*(t+1) 16-byte requests per thread are in flight.
 template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, int U>
 __device__ __forceinline__ void split_items(const FieldParams& f, const u64* secrets, const u64* coeffs,
-                                            size_t cstride, const ShareDst& dst, int m, const u64* tab,
+                                            size_t cstride, const StridedDst& dst, int m, const u64* tab,
                                             size_t limb_off, size_t limb_step) {
     constexpr int N = 2 * L;
     u32 M[U][TP1][E * N];
@@ -409,7 +412,8 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
 __global__ void __launch_bounds__(MPYC_THREADS, MPYC_SPLIT_MINB)
 k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
-        ShareDst dst, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
+        u64* __restrict__ shares, size_t sstride, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
+    const StridedDst dst = {shares, sstride};
     extern __shared__ __align__(16) u64 stab[];
     __shared__ __align__(8) u64 mbar;
     tma_stage_table(stab, gtab, tab_bytes, &mbar);
@@ -480,9 +484,9 @@ struct GenLayout {
     static constexpr int PER_BLOCK = 16 / SLOT;
 };
 
-template <int L, int KIND, int TP1, bool FULL, int E, bool VEC>
+template <int L, int KIND, int TP1, bool FULL, int E, bool VEC, class DST>
 __device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaChaKey& key, u64 counter0,
-                                               const u64* secrets, const ShareDst& dst, int m,
+                                               const u64* secrets, const DST& dst, int m,
                                                const u64* tab, size_t limb_off) {
     constexpr int N = 2 * L;
     constexpr int NC = (TP1 - 1) * E;   // coefficients of this item
@@ -509,9 +513,9 @@ __device__ __forceinline__ void split_gen_item(const FieldParams& f, const ChaCh
     split_compute<L, KIND, TP1, FULL, E, VEC>(f, M, dst, m, tab, limb_off);
 }
 
-template <int L, int KIND, int TP1, bool FULL, bool VEC>
+template <int L, int KIND, int TP1, bool FULL, bool VEC, class DST>
 __global__ void MPYC_LB
-k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, ShareDst dst,
+k_split_gen(FieldParams f, ChaChaKey key, const u64* __restrict__ secrets, DST dst,
             size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
     extern __shared__ __align__(16) u64 stab[];
     __shared__ __align__(8) u64 mbar;

@@ -7,6 +7,14 @@
 
 extern std::atomic<unsigned long long> g_mpyc_launches;
 
+// host-side description of where K2 (generate mode) puts its m share rows
+struct ShareDst {
+    u64* base = nullptr;
+    size_t stride = 0;
+    int use_rows = 0;
+    u64* rows[MPYC_MAX_SHARE_ROWS] = {};
+};
+
 // persistent-grid sizing: enough CTAs to cover the items, capped at one full wave
 int mpyc_grid_size(const void* kernel, size_t items, size_t dyn_smem);
 
@@ -21,10 +29,10 @@ struct Launch {
     // out[h] = a[h]^-1 (0 for a[h] == 0, reported in zero_flag); ex = p - 2; a and out must not alias
     static cudaError_t inv_batch(const FieldParams& fp, const ExpParams& ex, const u64* a, u64* out, int* zero_flag,
                                  size_t n, cudaStream_t st);
-    // dst: strided matrix (base, stride in limbs) or explicit row pointers (use_rows)
     static cudaError_t split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
-                             const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
+                             u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st);
+    // dst: strided matrix (base, stride in limbs) or explicit row pointers (use_rows; small-form tables only)
     static cudaError_t split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets,
                                  const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st);
     // small: 64-bit signed-magnitude lambda table

@@ -113,8 +113,8 @@ cudaError_t Launch<L>::inv_batch(const FieldParams& fp, const ExpParams& ex, con
 // ---- split ----------------------------------------------------------------------------------
 
 template <int L, int KIND, bool FULL, bool VEC>
-static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, const ShareDst& dst,
-                           size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, u64* shares,
+                           size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
     constexpr int E = VEC ? VecItem<L>::E : 1;
     size_t items = (n + E - 1) / E;
     constexpr int MAXT = FULL ? 5 : 9;
@@ -122,7 +122,7 @@ static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64*
     case T:                                                                                                      \
         if constexpr (T <= MAXT)                                                                                 \
             return launch_kernel(k_split<L, KIND, T, FULL, VEC>, items, tab_bytes, st, fp, secrets, coeffs,      \
-                                 cstride, dst, n, m, gtab, tab_bytes);                               \
+                                 cstride, shares, sstride, n, m, gtab, tab_bytes);                               \
         break
     switch (t + 1) {
         SPLIT_CASE(1);
@@ -141,14 +141,14 @@ static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64*
 }
 
 template <int L, bool FULL, bool VEC>
-static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride,
-                              const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, u64* shares,
+                              size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
     if constexpr (FULL) {
-#define M(K) return split_k<L, K, true, VEC>(fp, secrets, coeffs, cstride, dst, n, t, m, gtab, tab_bytes, st)
+#define M(K) return split_k<L, K, true, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
         KIND_SWITCH(fp.kind, M)
 #undef M
     } else {
-#define M(K) return split_k<L, K, false, VEC>(fp, secrets, coeffs, cstride, dst, n, t, m, gtab, tab_bytes, st)
+#define M(K) return split_k<L, K, false, VEC>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
         KIND_SWITCH(fp.kind, M)
 #undef M
     }
@@ -157,21 +157,20 @@ static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u
 
 template <int L>
 cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
-                             const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
+                             u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st) {
-    const bool vec = L != 3 && aligned32(secrets) && dst_aligned32(dst, m) && (t == 0 || aligned32(coeffs)) &&
-                     (cstride % 4 == 0 || t <= 1);   // strides in limbs
+    const bool vec = L != 3 && aligned32(secrets) && aligned32(shares) && (t == 0 || aligned32(coeffs)) &&
+                     (cstride % 4 == 0 || t <= 1) && (sstride % 4 == 0 || m <= 1);   // strides in limbs
     const int maxt = full ? 5 : 9;
     if (t + 1 > maxt) {
         if (!full) return cudaErrorInvalidValue;   // api.cu asks for full tables whenever t > 8
-    if (dst.use_rows) return cudaErrorNotSupported;   // the any-t kernel writes strided matrices only
-#define M(K) return launch_kernel(k_split_dyn<L, K>, n, 0, st, fp, secrets, coeffs, cstride, dst.base, dst.stride, n, m, t + 1, gtab)
+#define M(K) return launch_kernel(k_split_dyn<L, K>, n, 0, st, fp, secrets, coeffs, cstride, shares, sstride, n, m, t + 1, gtab)
         KIND_SWITCH(fp.kind, M)
 #undef M
     }
 #define GO(VECF)                                                                                                   \
-    return full ? split_kind<L, true, VECF>(fp, secrets, coeffs, cstride, dst, n, t, m, gtab, tab_bytes, st) \
-                : split_kind<L, false, VECF>(fp, secrets, coeffs, cstride, dst, n, t, m, gtab, tab_bytes, st)
+    return full ? split_kind<L, true, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st) \
+                : split_kind<L, false, VECF>(fp, secrets, coeffs, cstride, shares, sstride, n, t, m, gtab, tab_bytes, st)
     if constexpr (L != 3) {
         if (vec) {
             GO(true);
@@ -190,8 +189,17 @@ static cudaError_t split_gen_k(const FieldParams& fp, const ChaChaKey& key, cons
     size_t items = (n + E - 1) / E;
 #define GEN_CASE(T)                                                                                                 \
     case T:                                                                                                         \
-        return launch_kernel(k_split_gen<L, KIND, T, FULL, VEC>, items, tab_bytes, st, fp, key, secrets, dst,       \
-                             n, m, gtab, tab_bytes)
+        if constexpr (!FULL) {                                                                                      \
+            if (dst.use_rows) {                                                                                     \
+                RowsDst rd;                                                                                         \
+                for (int i = 0; i < MPYC_MAX_SHARE_ROWS; i++) rd.rows[i] = dst.rows[i];                             \
+                return launch_kernel(k_split_gen<L, KIND, T, FULL, VEC, RowsDst>, items, tab_bytes, st, fp, key,    \
+                                     secrets, rd, n, m, gtab, tab_bytes);                                           \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (dst.use_rows) return cudaErrorNotSupported;                                                             \
+        return launch_kernel(k_split_gen<L, KIND, T, FULL, VEC, StridedDst>, items, tab_bytes, st, fp, key, secrets, \
+                             StridedDst{dst.base, dst.stride}, n, m, gtab, tab_bytes)
     switch (t + 1) {
         GEN_CASE(1);
         GEN_CASE(2);
