@@ -332,22 +332,6 @@ struct Fp {
             }
             csub(r, 0, f);
         } else if constexpr (KIND == KIND_PM_ALIGNED) {
-            if constexpr (L == 1 && W == N + 2) {
-                // one-limb field, 96-bit value (the usual case of K2's small form: multipliers (i+1)^j < 2^32, the same
-                // for every thread, so the branch does not diverge): one product folds the third limb
-                if (x[N + 1] == 0) {
-                    const u64 u = (u64)x[N] * c;                 // < 2^48
-                    u32 uu[N] = {(u32)u, (u32)(u >> 32)};
-                    u32 cy = add_n<N>(r, x, uu);
-                    if (cy) {                                    // 2^64 = c (mod p); the wrapped sum is < 2^48: no second carry
-                        uu[0] = c;
-                        uu[1] = 0;
-                        add_n<N>(r, r, uu);
-                    }
-                    csub(r, 0, f);
-                    return;
-                }
-            }
             copy_n<N>(r1, x);
             r1[N] = r1[N + 1] = 0;
             mac_small<HM, N + 2>(r1, x + N, c);

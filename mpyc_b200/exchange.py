@@ -72,7 +72,7 @@ def reshare(engine, shares, t, m, group=None, first_dealer=0):
         raise ValueError('resharing needs m >= 2t+1 parties')
     # 1. every local dealer splits its share vector: dealt[j] is (m, n, L), row i goes to party i
     dealt = {j: engine.split(shares[j], t, m) for j in dealers if j in shares}
-    some = next(iter(shares.values()))
+    some = next(iter(shares.values()), None)             # None: this rank hosts no party (world > m) and only joins the group calls
     # 2. exchange: recv[i][a] = row i of dealer dealers[a]'s matrix
     recv = {i: [None] * len(dealers) for i in mine}
     ops = []

@@ -69,7 +69,8 @@ def _worker(rank, world, port, m, t, n, first_dealer, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,m,t,n,first_dealer', [(2, 3, 1, 37, 0), (3, 5, 2, 16, 3), (2, 7, 3, 9, 5), (2, 2, 0, 5, 1)])
+@pytest.mark.parametrize('world,m,t,n,first_dealer', [(2, 3, 1, 37, 0), (3, 5, 2, 16, 3), (2, 7, 3, 9, 5), (2, 2, 0, 5, 1),
+                                                      (3, 2, 0, 4, 0)])   # last: more ranks than parties
 def test_reshare_routes_rows_between_ranks(world, m, t, n, first_dealer):
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
