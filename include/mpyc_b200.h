@@ -201,6 +201,12 @@ int mpyc_b200_count_mismatch(const mpyc_b200_field* f, const void* d_a, const vo
 int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
                                 size_t coeff_stride, void* h_shares, size_t share_stride, size_t n,
                                 int t, int m, int device);
+/* np_random_split as the reference defines it -- secrets in, shares out, randomness drawn inside (thresha.py:47-64):
+ * generate mode through the same chunk pipeline.  Chunk c uses nonce + c with the caller's key: pass a fresh key per
+ * call (t <= 4). */
+int mpyc_b200_shamir_split_generate_host(const mpyc_b200_field* f, const void* h_secrets, void* h_shares,
+                                         size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
+                                         uint64_t nonce, int device);
 int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const void* const* h_share_rows,
                                     const int64_t* xs, int k, const int64_t* x_rs, int width,
                                     void* h_out, size_t out_stride, size_t n, int device);

@@ -83,6 +83,8 @@ _SIGNATURES = {
     'mpyc_b200_count_mismatch': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     'mpyc_b200_shamir_split_host': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,
                                             c_int, c_int, c_int]),
+    'mpyc_b200_shamir_split_generate_host': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
+                                                     POINTER(c_uint8), c_uint64, c_int]),
     'mpyc_b200_shamir_recombine_host': (c_int, [_field_p, POINTER(c_void_p), POINTER(c_int64), c_int,
                                                 POINTER(c_int64), c_int, c_void_p, c_size_t, c_size_t, c_int]),
     'mpyc_b200_ff_binop_host': (c_int, [_field_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),

@@ -1061,6 +1061,40 @@ MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h
     return MPYC_B200_OK;
 }
 
+MPYC_API int mpyc_b200_shamir_split_generate_host(const mpyc_b200_field* f, const void* h_secrets, void* h_shares,
+                                                    size_t share_stride, size_t n, int t, int m, const uint8_t key32[32],
+                                                    uint64_t nonce, int device) {
+    if (!f || !key32) return fail(MPYC_B200_EINVAL, "shamir_split_generate_host: null argument");
+    if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
+    if (n == 0) return MPYC_B200_OK;
+    if (!h_secrets || !h_shares || share_stride < n) return fail(MPYC_B200_EINVAL, "shamir_split_generate_host: bad buffers");
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    const size_t ch = chunk_elems(n, eb * (size_t)(1 + m));
+    Workspace* w;
+    int rc = acquire_workspace(device, &w);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(w->mu);
+    rc = reserve(*w, ch * eb, ch * eb * (size_t)m);
+    if (rc) return rc;
+    size_t c = 0;
+    for (size_t off = 0; off < n; off += ch, c++) {
+        const int s = (int)(c % kSlots);
+        const size_t cn = std::min(ch, n - off);
+        cudaStream_t st = w->streams[s];
+        char* din = (char*)w->d_in[s];
+        char* dout = (char*)w->d_out[s];
+        CU(cudaMemcpyAsync(din, (const char*)h_secrets + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+        // every chunk draws from its own keystream: the kernel's block counters restart at 0 per launch
+        rc = mpyc_b200_shamir_split_generate(f, din, dout, ch, cn, t, m, key32, nonce + c, st);
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m,
+                             cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    return MPYC_B200_OK;
+}
+
 MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const void* const* h_share_rows, const int64_t* xs,
                                                int k, const int64_t* x_rs, int width, void* h_out, size_t out_stride,
                                                size_t n, int device) {

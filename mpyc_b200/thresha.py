@@ -102,18 +102,16 @@ _nonce = [int.from_bytes(os.urandom(7), 'little')]
 
 def _split_generate(ctx, sec, t, m):
     """Default (CSPRNG) path for prime fields: secrets go to the GPU, the coefficients are generated INSIDE
-    the kernel from a ChaCha20 stream keyed with fresh OS randomness (mpyc_b200_shamir_split_generate) and
-    never exist in memory; shares come back as a limb array (m, n, L)."""
-    import torch
-    from mpyc_b200.device import DeviceArray, shamir_split_generate
-    if not torch.cuda.is_available():
-        raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
-    _nonce[0] = (_nonce[0] + 1) & (2**63 - 1)
-    dev = torch.device('cuda', device)
-    with torch.cuda.device(dev):
-        S = DeviceArray.from_limbs(ctx, sec, device=dev)
-        sh = shamir_split_generate(ctx, S, t, m, key=os.urandom(32), nonce=_nonce[0])
-        return sh.t.contiguous().cpu().numpy().view(np.uint64)
+    the kernel from a ChaCha20 stream keyed with 32 fresh bytes of OS randomness per call
+    (mpyc_b200_shamir_split_generate_host: H2D copy, kernel and D2H copy pipelined chunk by chunk) and never
+    exist in memory; shares come back as a limb array (m, n, L)."""
+    n = sec.shape[0]
+    sec = np.ascontiguousarray(sec)
+    shares = np.empty((m, n, ctx.nlimbs), dtype=np.uint64)
+    _nonce[0] = (_nonce[0] + (1 << 20)) & (2**63 - 1)        # the library uses nonce + chunk index (< 2^20 chunks per call)
+    key = (ctypes.c_uint8 * 32).from_buffer_copy(os.urandom(32))
+    check(lib.mpyc_b200_shamir_split_generate_host(ctx.handle, _ptr(sec), _ptr(shares), n, n, t, m, key, _nonce[0], device))
+    return shares
 
 
 def _use_generate(ctx, t, n):
@@ -259,7 +257,6 @@ def _f_S_i(field, m, i, S):
 
 def _prss(field, m, i, prfs, uci, n, d, weights):
     """Shared engine call: sum_S f_S(i) * sum_j PRF_S[h*d + j] * weights[j]  as a limb array (n, L)."""
-    import torch
     ctx = context_of_field(field)
     subsets = list(prfs.items())
     bound = subsets[0][1].max
@@ -277,8 +274,6 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
         return np.zeros((0,) if ctx.binary else (0, nl), dtype=np.uint8 if ctx.binary else np.uint64)
     if width == 0:   # bound == 1: all PRF values are 0
         return np.zeros((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
-    if not torch.cuda.is_available():
-        raise RuntimeError('mpyc_b200: no CUDA device available (there is no CPU fallback)')
     # The XOF runs inside the library: one SHAKE128 sponge per key subset on its own host thread, squeezed chunk
     # by chunk into pinned buffers while the previous chunk is copied and combined on the GPU
     # (mpyc_b200_prss_host) -- hashlib.shake_128().digest() holds the GIL and would serialise the subsets.
