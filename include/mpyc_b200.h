@@ -45,7 +45,7 @@ extern "C" {
 #define MPYC_B200_MAX_POINTS    64  /* max shares per recombination call                         */
 
 /* field kinds reported by mpyc_b200_field_info */
-#define MPYC_B200_KIND_GENERIC     0   /* odd prime, Montgomery with guard limb                  */
+#define MPYC_B200_KIND_GENERIC     0   /* odd prime: Barrett / Montgomery (guard limb) reductions */
 #define MPYC_B200_KIND_PM_ALIGNED  1   /* p = 2^(64L) - c                                        */
 #define MPYC_B200_KIND_PM_SHIFT    2   /* p = 2^k - c, k % 64 != 0                               */
 #define MPYC_B200_KIND_GF256       3   /* GF(2^8) = GF(2)[X]/(modulus), one byte per element     */

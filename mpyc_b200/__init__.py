@@ -8,7 +8,9 @@ ctypes C ABI (include/mpyc_b200.h):
     mpyc_b200.device      DeviceArray / DeviceMatrix: limb tensors resident in HBM + shamir_split/recombine
     mpyc_b200.field       FieldContext: one handle per modulus (reduction family, cached tables)
     mpyc_b200.install     install()/uninstall(): swap the engine in behind an imported `mpyc`
+    mpyc_b200.wire        limb wire format: ShareRow objects that pickle as fixed-width bytes, never Python ints
     mpyc_b200.sharding    element-axis sharding over the GPUs of one box (torch.distributed)
+    mpyc_b200.exchange    co-located resharing: NCCL send/recv of limb rows, or K2 storing into the peer GPU
 
 There is no CPU fallback: importing the package needs libmpyc_b200.so (built in-tree by
 mpyc_b200._build), and every compute call needs a CUDA device.

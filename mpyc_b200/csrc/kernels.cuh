@@ -1,14 +1,17 @@
 // sm_100a kernels for the GF(p) Shamir hot path.  All kernels are persistent grid-stride
-// streamers: one CTA wave sized from the SM count, 128-bit global loads/stores on the limb
-// arrays (read-once data bypasses L1 allocation), per-call constant tables (Vandermonde /
-// Lagrange, a few hundred bytes) staged global -> shared memory once per CTA with a TMA bulk
-// copy (cp.async.bulk + mbarrier; UBLKCP in SASS).  Integer modular work: no tensor cores.
+// streamers: one CTA wave sized from the SM count, 256-bit global loads/stores on the limb
+// arrays (LDG.E.256 / STG.E.256; read-once data bypasses L1 allocation), per-call constant tables
+// (Vandermonde / Lagrange, a few hundred bytes) staged global -> shared memory once per CTA with a
+// TMA bulk copy (cp.async.bulk + mbarrier; UBLKCP in SASS); K4 also stages its PRF byte tiles that
+// way, double-buffered.  Integer modular work: no tensor cores.
 //
-//   K1  k_binop / k_binop_scalar / k_neg     finfields.py:1056-1124,1189-1192
-//   K1b k_pow (pow / inverse / sqrt / is_sqr) finfields.py:1408-1470
-//   K2  k_split_small / k_split_full          thresha.py:47-64
-//   K3  k_recombine                           thresha.py:119-132
-//   K4  k_prss_combine                        thresha.py:163-173,201-217
+//   K1   k_binop                                finfields.py:1056-1124,1189-1192
+//   K1b  k_pow (pow / sqrt / is_sqr), k_inv_batch (Montgomery-trick inverse)   finfields.py:1408-1470
+//   K1c  k_matmul                               finfields.py:1126-1146
+//   K2   k_split (small / full tables), k_split_gen (ChaCha20 coefficients, strided or per-row destinations),
+//        k_split_dyn (any t)                    thresha.py:47-64
+//   K3   k_recombine, k_recombine_small         thresha.py:119-132
+//   K4   k_prss_tiles, k_prss_combine           thresha.py:163-173,201-217
 #pragma once
 #include "ff_arith.cuh"
 

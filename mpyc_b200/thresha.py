@@ -18,7 +18,7 @@ Randomness.  The reference draws coefficients with secrets.randbelow per element
 used instead -- the parity tests inject deterministic streams this way, in the reference's own
 consumption order (np: (t, n) row-major; list: element-major, Horner order).  When None (default)
 the coefficients are generated inside the kernel from a ChaCha20 stream keyed with 32 fresh bytes of
-OS randomness per call (mpyc_b200_shamir_split_generate; t <= 4), or drawn from os.urandom in bulk
+OS randomness per call (mpyc_b200_shamir_split_generate_host; t <= 4), or drawn from os.urandom in bulk
 (64 bits wider than the modulus, then reduced) for GF(2^8) and t > 4.
 """
 import ctypes
