@@ -1013,16 +1013,23 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
 
 #define MPYC_MM_KT 64   // k-chunk of the A tile held in shared memory
 
+// Split-k form (ksplit > 1; few output rows, long dot products -- e.g. np_cnnmnist's 1 x 3136 @ 3136 x 1024 layer, which
+// has only 4 column tiles): work item w = (slice s, tile) computes the partial products over k-slice s and writes them,
+// reduced, to C + s*r*c; k_sum_slices adds the slices.  ksplit == 1 writes the result itself.
 template <int L, int KIND, int TM>
 __global__ void MPYC_LB
 k_matmul(FieldParams f, const u64* __restrict__ A, const u64* __restrict__ B, u64* __restrict__ C, size_t r, size_t k,
-         size_t c) {
+         size_t c, size_t kslice, size_t ksplit) {
     typedef Fp<L, KIND> F;
     constexpr int N = 2 * L;
     __shared__ u32 sA[TM][MPYC_MM_KT][N];
     const size_t col_tiles = (c + MPYC_THREADS - 1) / MPYC_THREADS;
     const size_t row_tiles = (r + TM - 1) / TM;
-    for (size_t tile = blockIdx.x; tile < col_tiles * row_tiles; tile += gridDim.x) {
+    const size_t tiles = col_tiles * row_tiles;
+    for (size_t w = blockIdx.x; w < tiles * ksplit; w += gridDim.x) {
+        const size_t tile = w % tiles, slice = w / tiles;
+        const size_t k_lo = slice * kslice, k_hi = min(k, k_lo + kslice);
+        u64* Cs = C + slice * r * c * L;
         const size_t i0 = (tile / col_tiles) * TM;
         const size_t j = (tile % col_tiles) * MPYC_THREADS + threadIdx.x;
         u32 acc[TM][F::WACC];
@@ -1033,8 +1040,8 @@ k_matmul(FieldParams f, const u64* __restrict__ A, const u64* __restrict__ B, u6
             zero_n<N>(partial[a]);
         }
         u32 lazy = 0;
-        for (size_t l0 = 0; l0 < k; l0 += MPYC_MM_KT) {
-            const int kt = (int)min((size_t)MPYC_MM_KT, k - l0);
+        for (size_t l0 = k_lo; l0 < k_hi; l0 += MPYC_MM_KT) {
+            const int kt = (int)min((size_t)MPYC_MM_KT, k_hi - l0);
             __syncthreads();
             for (int idx = threadIdx.x; idx < TM * kt; idx += MPYC_THREADS) {
                 const int a = idx / kt, l = idx % kt;
@@ -1078,10 +1085,27 @@ k_matmul(FieldParams f, const u64* __restrict__ A, const u64* __restrict__ B, u6
                     u32 t[N];
                     F::finish(t, acc[a], f);
                     F::add(t, t, partial[a], f);
-                    store_limbs<L, false>(C + ((i0 + a) * c + j) * L, t);
+                    store_limbs<L, false>(Cs + ((i0 + a) * c + j) * L, t);
                 }
             }
         }
+    }
+}
+
+// out[e] = sum over the ksplit slices of part[s][e] (mod p), e < count elements
+template <int L, int KIND>
+__global__ void MPYC_LB
+k_sum_slices(FieldParams f, const u64* __restrict__ part, u64* __restrict__ out, size_t count, size_t ksplit) {
+    constexpr int N = 2 * L;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += nth) {
+        u32 acc[N], x[N];
+        load_limbs<L, false>(acc, part + e * L);
+        for (size_t s = 1; s < ksplit; s++) {
+            load_limbs<L, false>(x, part + (s * count + e) * L);
+            Fp<L, KIND>::add(acc, acc, x, f);
+        }
+        store_limbs<L, false>(out + e * L, acc);
     }
 }
 

@@ -2,6 +2,7 @@
 // path, compile-time t+1) and launches it on a persistent grid.
 #pragma once
 #include <stdlib.h>
+#include <algorithm>
 #include "launch.h"
 
 static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
@@ -341,16 +342,35 @@ template <int L>
 cudaError_t Launch<L>::matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,
                               cudaStream_t st) {
     const size_t col_tiles = (c + MPYC_THREADS - 1) / MPYC_THREADS;
-    // TM rows per thread: 4 when there are enough rows, else 1 (vector-matrix products)
-    if (r >= 4) {
-        const size_t tiles = col_tiles * ((r + 3) / 4);
-#define M(K) return launch_kernel(k_matmul<L, K, 4>, tiles * MPYC_THREADS, 0, st, fp, A, B, C, r, k, c)
-        KIND_SWITCH(fp.kind, M)
-#undef M
+    const int tm = r >= 4 ? 4 : 1;      // rows per thread: 4 when there are enough rows, else 1 (vector-matrix products)
+    const size_t tiles = col_tiles * ((r + tm - 1) / tm);
+    // split-k when the output alone cannot fill the machine: aim at ~4 CTAs per SM, slices of >= 64 terms
+    size_t ksplit = 1;
+    const size_t want = (size_t)mpyc_sm_count() * 4;
+    if (tiles < want && k >= 256) ksplit = std::min((want + tiles - 1) / tiles, k / 64);
+    if (ksplit < 2) ksplit = 1;
+    const size_t kslice = ((k + ksplit - 1) / ksplit + MPYC_MM_KT - 1) / MPYC_MM_KT * MPYC_MM_KT;   // whole shared-memory chunks
+    ksplit = (k + kslice - 1) / kslice;
+    u64* dst = C;
+    u64* part = nullptr;
+    if (ksplit > 1) {
+        cudaError_t e = cudaMallocAsync(&part, ksplit * r * c * L * sizeof(u64), st);
+        if (e != cudaSuccess) return e;
+        dst = part;
     }
-    const size_t tiles = col_tiles * r;
-#define M(K) return launch_kernel(k_matmul<L, K, 1>, tiles * MPYC_THREADS, 0, st, fp, A, B, C, r, k, c)
-    KIND_SWITCH(fp.kind, M)
+    cudaError_t e = cudaErrorInvalidValue;
+#define M(K)                                                                                                              \
+    e = tm == 4 ? launch_kernel(k_matmul<L, K, 4>, tiles * ksplit * MPYC_THREADS, 0, st, fp, A, B, dst, r, k, c, kslice, ksplit) \
+                : launch_kernel(k_matmul<L, K, 1>, tiles * ksplit * MPYC_THREADS, 0, st, fp, A, B, dst, r, k, c, kslice, ksplit); \
+    if (e == cudaSuccess && ksplit > 1) e = launch_kernel(k_sum_slices<L, K>, r * c, 0, st, fp, part, C, r * c, ksplit);  \
+    break
+    switch (fp.kind) {
+        case KIND_GENERIC: M(KIND_GENERIC);
+        case KIND_PM_ALIGNED: M(KIND_PM_ALIGNED);
+        case KIND_PM_SHIFT: M(KIND_PM_SHIFT);
+        default: break;
+    }
 #undef M
-    return cudaErrorInvalidValue;
+    if (part) cudaFreeAsync(part, st);
+    return e;
 }

@@ -419,7 +419,8 @@ def test_golden_matmul(case):
 
 
 @pytest.mark.parametrize('p', [P61, P64, P64G, P69, P128, GEN['128'], 2**192 - 237, P256, GEN['256'], 101], ids=lambda p: f'p{p.bit_length()}_{p & 0xffff:x}')
-@pytest.mark.parametrize('shape', [(1, 1, 1), (1, 3136, 300), (5, 70, 257), (9, 64, 3), (2, 129, 600), (4, 0, 3)])
+@pytest.mark.parametrize('shape', [(1, 1, 1), (1, 3136, 300), (5, 70, 257), (9, 64, 3), (2, 129, 600), (4, 0, 3), (3, 1000, 257), (5, 513, 70),
+                                   (7, 257, 9)])   # k >= 256 with few output tiles: split-k form
 def test_matmul_vs_oracle(p, shape):
     r, k, c = shape
     ctx = mpyc_b200.context_for(p)
