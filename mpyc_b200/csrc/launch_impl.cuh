@@ -349,8 +349,8 @@ cudaError_t Launch<L>::matmul(const FieldParams& fp, const u64* A, const u64* B,
     const size_t want = (size_t)mpyc_sm_count() * 4;
     if (tiles < want && k >= 256) ksplit = std::min((want + tiles - 1) / tiles, k / 64);
     if (ksplit < 2) ksplit = 1;
-    const size_t kslice = ((k + ksplit - 1) / ksplit + MPYC_MM_KT - 1) / MPYC_MM_KT * MPYC_MM_KT;   // whole shared-memory chunks
-    ksplit = (k + kslice - 1) / kslice;
+    const size_t kslice = std::max<size_t>(((k + ksplit - 1) / ksplit + MPYC_MM_KT - 1) / MPYC_MM_KT * MPYC_MM_KT, MPYC_MM_KT);   // whole shared-memory chunks (k may be 0)
+    ksplit = std::max<size_t>((k + kslice - 1) / kslice, 1);
     u64* dst = C;
     u64* part = nullptr;
     if (ksplit > 1) {
