@@ -1057,7 +1057,7 @@ MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h
         CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m,
                              cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
     return MPYC_B200_OK;
 }
 
@@ -1091,7 +1091,7 @@ MPYC_API int mpyc_b200_shamir_split_generate_host(const mpyc_b200_field* f, cons
         CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m,
                              cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
     return MPYC_B200_OK;
 }
 
@@ -1127,7 +1127,7 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
         if (rc) return rc;
         CU(cudaMemcpy2DAsync((char*)h_out + off * eb, out_stride * eb, dout, ch * eb, cn * eb, width, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
     return MPYC_B200_OK;
 }
 
@@ -1157,7 +1157,7 @@ MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const voi
         if (rc) return rc;
         CU(cudaMemcpyAsync((char*)h_out + off * eb, dout, cn * eb, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < kSlots; s++) CU(cudaStreamSynchronize(w->streams[s]));
+    for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
     return MPYC_B200_OK;
 }
 

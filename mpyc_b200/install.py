@@ -30,10 +30,26 @@ def _covered(field):
         return False
 
 
-def _wrap(name, ours, theirs, strict):
+def _batch_size(name, args):
+    """Number of elements a call works on (for the min_size routing of install())."""
+    try:
+        if name in ('random_split', 'np_random_split'):
+            return len(args[0])
+        if name in ('recombine', 'np_recombine'):
+            return len(args[0][0][1])
+        return int(args[-1])            # PRSS functions: (m, i, prfs, uci, n)
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def _wrap(name, ours, theirs, strict, min_size=0):
     @functools.wraps(theirs)
     def call(field, *args, **kwargs):
         if _covered(field):
+            if min_size:
+                n = _batch_size(name, args)
+                if n is not None and n < min_size:
+                    return theirs(field, *args, **kwargs)     # the reference's own code, as without install()
             return ours(field, *args, **kwargs)
         if strict:
             raise UnsupportedFieldError(f'mpyc_b200 does not cover field {getattr(field, "__name__", field)}')
@@ -78,10 +94,13 @@ _saved_ff = {}
 
 
 def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256,
-            limb_wire=False):
+            limb_wire=False, min_size=0):
     """Patch `mpyc.thresha` (or the module passed in); with finfields_module also the batched
     inverse/pow/sqrt/is_sqr of PrimeFieldArray.  limb_wire=True: shares travel between parties as limb
-    buffers (mpyc_b200.wire; every party must run mpyc_b200).  Returns the list of patched names."""
+    buffers (mpyc_b200.wire; every party must run mpyc_b200).  min_size > 0: calls on fewer elements are left to
+    the reference's own functions -- a GPU round trip costs ~35 us per call, which the reference beats below a few
+    dozen 64-bit elements; the default 0 sends every covered call to the GPU.
+    Returns the list of patched names."""
     if thresha_module is None:
         import mpyc.thresha as thresha_module
     if _saved:
@@ -98,7 +117,8 @@ def install(thresha_module=None, strict=False, device=0, finfields_module=None, 
             ours = functools.cache(getattr(engine, name))
         else:
             ours = getattr(engine, name)
-        setattr(thresha_module, name, _wrap(name, ours, theirs, strict))
+        routed = min_size if name not in ('_recombination_vector', '_f_S_i') else 0
+        setattr(thresha_module, name, _wrap(name, ours, theirs, strict, routed))
     return list(_NAMES)
 
 

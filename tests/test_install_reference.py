@@ -120,3 +120,22 @@ def test_share_rows_interoperate_with_the_reference_field_arrays(mpyc_thresha):
     b = f256.array(row8, check=False)
     assert [int(v) for v in b.value] == [0, 1, 0x53, 0xCA]
     assert int((b * b).value[2]) == int((f256(0x53) * f256(0x53)).value)
+
+
+def test_min_size_routes_small_calls_to_the_reference(mpyc_thresha):
+    """install(min_size=n): calls on fewer elements run the reference's own code (no GPU needed here), larger ones go
+    to the engine (which, without a GPU, must raise rather than compute)."""
+    thresha, finfields, gfpx = mpyc_thresha
+    from mpyc_b200 import install as inst
+    F = finfields.GF(2**61 - 1)
+    inst.install(thresha, min_size=8)
+    try:
+        a = [F(3), F(1), F(4)]
+        sh = thresha.random_split(F, a, 1, 3)                      # 3 < 8 elements: reference path
+        assert thresha.recombine(F, [(1, sh[0]), (2, sh[1])]) == a
+        import torch
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError):
+                thresha.random_split(F, [F(i) for i in range(8)], 1, 3)   # 8 >= 8: engine, no CPU fallback
+    finally:
+        inst.uninstall()
