@@ -139,3 +139,15 @@ def test_min_size_routes_small_calls_to_the_reference(mpyc_thresha):
                 thresha.random_split(F, [F(i) for i in range(8)], 1, 3)   # 8 >= 8: engine, no CPU fallback
     finally:
         inst.uninstall()
+
+
+def test_install_sets_and_clears_the_limb_wire_flag(mpyc_thresha):
+    thresha, finfields, gfpx = mpyc_thresha
+    from mpyc_b200 import install as inst, thresha as engine
+    assert engine.limb_wire is False
+    inst.install(thresha, limb_wire=True)
+    try:
+        assert engine.limb_wire is True
+    finally:
+        inst.uninstall()
+    assert engine.limb_wire is False
