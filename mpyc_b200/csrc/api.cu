@@ -796,6 +796,7 @@ struct PrssTable {
     u32 bytes = 0;
     std::vector<unsigned char> gf;     // GF(2^8): passed to the kernel by value
     bool small = false;                // [(|num_S|, sign_S) x nsub | w_j x d | D^-1 (L limbs)]: see prss_small_table
+    bool simple = false;               // small, d == 1 and weight 1: the plain pseudorandom share
     cudaStream_t st = nullptr;
     ~PrssTable() {
         if (d_tab) cudaFreeAsync(d_tab, st);
@@ -879,6 +880,7 @@ int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int
     const size_t L = f->fp.L;
     std::vector<u64> host;
     tab.small = prss_small_table(f->fp, nsub, d, h_coef, h_weights, host);
+    tab.simple = tab.small && d == 1 && h_weights[0] == 1;   // small form: weights are plain integers in limb 0
     if (!tab.small) {
         host.resize(((size_t)nsub + d) * L);
         memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
@@ -902,7 +904,7 @@ int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d
         return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.gf.data(), (unsigned char*)d_out, n, st), "gf256 prss");
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        return launch_status(Launch<LL>::prss(f->fp, tab.small, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits,
+        return launch_status(Launch<LL>::prss(f->fp, tab.small, tab.simple, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits,
                                               tab.d_tab, tab.bytes, (u64*)d_out, n, st), "prss_combine launch");
     });
 }

@@ -834,14 +834,23 @@ __device__ __forceinline__ bool prss_is_one(const u64* w, const FieldParams& f) 
 //   SMALL = false: acc (WACC limbs) += f_S(i) * y   with y = sum_j v_j w_j mod p, full products against table-form constants
 //   SMALL = true : acc (WSM limbs)  += |num_S| * (+-y), y = sum_j v_j w_j mod p with plain-integer weights; the caller
 //                  reduces once and multiplies by D^-1 (api.cu: prss_small_table)
-template <int L, int KIND, bool SMALL, bool A8>
+//   SIMPLE (with SMALL): d == 1 and weight 1 known at compile time -- the plain pseudorandom share of thresha.py:163-173
+template <int L, int KIND, bool SMALL, bool A8, bool SIMPLE = false>
 __device__ __forceinline__ void prss_subset(u32* acc, const unsigned char* base, int d, int chunk_bytes, int nl, int bound_bits,
                                             bool unit_w, const PrssFold& fold, const u64* coef_S, const u64* wts,
                                             const FieldParams& f) {
     typedef Fp<L, KIND> F;
     constexpr int N = 2 * L;
     u32 y[N];
-    if constexpr (SMALL) {
+    if constexpr (SMALL && SIMPLE) {
+        prss_value<L, KIND, A8>(y, base, chunk_bytes, nl, bound_bits, fold, f);
+        if (coef_S[1] != 0) {                 // negative coefficient: -|c| y = |c| (p - y)   (warp-uniform)
+            u32 t[N];
+            sub_n<N>(t, as32(f.p), y);
+            copy_n<N>(y, t);
+        }
+        F::mac_const(acc, y, coef_S[0]);
+    } else if constexpr (SMALL) {
         u32 inner[F::WSM];
         zero_n<F::WSM>(inner);
         for (int j = 0; j < d; j++) {
@@ -928,7 +937,7 @@ k_prss_combine(FieldParams f, const unsigned char* __restrict__ bytes, size_t su
 // thread at a stride of chunk_bytes.  Requires bytes and subset_stride 16-byte aligned.  A8: chunk_bytes % 8 == 0
 // (the tile base is 16-byte aligned, so every chunk is read as whole 64-bit words from shared memory).
 // smem layout: [table tab_bytes (rounded to 128)] [buffer 0: tile_bytes] [buffer 1: tile_bytes]
-template <int L, int KIND, bool SMALL, bool A8>
+template <int L, int KIND, bool SMALL, bool A8, bool SIMPLE>
 __global__ void __launch_bounds__(MPYC_THREADS, 2)
 k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d, int chunk_bytes,
              int bound_bits, const u64* __restrict__ gtab, u32 tab_bytes, u64* __restrict__ out, size_t n, u32 tile_bytes) {
@@ -990,8 +999,8 @@ k_prss_tiles(FieldParams f, const unsigned char* __restrict__ bytes, size_t subs
             }
             phases ^= 1u << b;
             if (h < n)
-                prss_subset<L, KIND, SMALL, A8>(outer, buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes, d,
-                                                chunk_bytes, nl, bound_bits, unit_w, fold, coef + (size_t)S * CS, wts, f);
+                prss_subset<L, KIND, SMALL, A8, SIMPLE>(outer, buf0 + (size_t)b * tile_bytes + (size_t)threadIdx.x * d * chunk_bytes, d,
+                                                        chunk_bytes, nl, bound_bits, unit_w, fold, coef + (size_t)S * CS, wts, f);
             __syncthreads();   // every thread is done with buffer b: it may be refilled (by issue(S+2) next trip)
         }
         if (h < n) {

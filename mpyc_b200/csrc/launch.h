@@ -39,7 +39,8 @@ struct Launch {
     static cudaError_t recombine(const FieldParams& fp, bool small, const RowPtrs& rows, int k, int width, const u64* gtab,
                                  u32 tab_bytes, u64* out, size_t ostride, size_t n, cudaStream_t st);
     // small: subset coefficients as 64-bit signed-magnitude constants + D^-1 (api.cu: prss_small_table)
-    static cudaError_t prss(const FieldParams& fp, bool small, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+    // simple (with small): d == 1 and the weight is 1
+    static cudaError_t prss(const FieldParams& fp, bool small, bool simple, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                             int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                             cudaStream_t st);
     static cudaError_t matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,

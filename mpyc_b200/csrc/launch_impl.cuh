@@ -282,11 +282,11 @@ cudaError_t Launch<L>::recombine(const FieldParams& fp, bool small, const RowPtr
 
 // ---- PRSS / utilities ---------------------------------------------------------------------------
 
-template <int L, int KIND, bool SMALL, bool A8>
+template <int L, int KIND, bool SMALL, bool A8, bool SIMPLE>
 static cudaError_t prss_tiles_k(const FieldParams& fp, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                                 int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                                 u32 tile_bytes, size_t smem, cudaStream_t st) {
-    auto kernel = k_prss_tiles<L, KIND, SMALL, A8>;
+    auto kernel = k_prss_tiles<L, KIND, SMALL, A8, SIMPLE>;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -297,7 +297,7 @@ static cudaError_t prss_tiles_k(const FieldParams& fp, const unsigned char* byte
 }
 
 template <int L>
-cudaError_t Launch<L>::prss(const FieldParams& fp, bool small, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
+cudaError_t Launch<L>::prss(const FieldParams& fp, bool small, bool simple, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
                             int chunk_bytes, int bound_bits, const u64* gtab, u32 tab_bytes, u64* out, size_t n,
                             cudaStream_t st) {
     // tiled form (TMA-staged PRF bytes) when the byte streams are 16-byte aligned and two tiles fit in shared memory
@@ -306,15 +306,19 @@ cudaError_t Launch<L>::prss(const FieldParams& fp, bool small, const unsigned ch
     const bool aligned = ((reinterpret_cast<uintptr_t>(bytes) | subset_stride) & 15u) == 0;
     const bool padded = subset_stride >= (((size_t)n * d * chunk_bytes + 15) & ~(size_t)15);   // last tile reads whole 16-byte groups
     if (aligned && padded && smem <= 160u * 1024u && n >= MPYC_THREADS && getenv("MPYC_B200_PRSS_UNTILED") == nullptr) {
-#define TILES(K, SM, A8) \
-    return prss_tiles_k<L, K, SM, A8>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, (u32)tile_bytes, smem, st)
+#define TILES(K, SM, A8, SI) \
+    return prss_tiles_k<L, K, SM, A8, SI>(fp, bytes, subset_stride, nsub, d, chunk_bytes, bound_bits, gtab, tab_bytes, out, n, (u32)tile_bytes, smem, st)
 #define M(K)                                   \
-    if (small) {                               \
-        if (chunk_bytes % 8 == 0) TILES(K, true, true);  \
-        TILES(K, true, false);                 \
+    if (small && simple) {                     \
+        if (chunk_bytes % 8 == 0) TILES(K, true, true, true);   \
+        TILES(K, true, false, true);           \
     }                                          \
-    if (chunk_bytes % 8 == 0) TILES(K, false, true);     \
-    TILES(K, false, false)
+    if (small) {                               \
+        if (chunk_bytes % 8 == 0) TILES(K, true, true, false);  \
+        TILES(K, true, false, false);          \
+    }                                          \
+    if (chunk_bytes % 8 == 0) TILES(K, false, true, false);     \
+    TILES(K, false, false, false)
         KIND_SWITCH(fp.kind, M)
 #undef M
 #undef TILES
