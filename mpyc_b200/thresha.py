@@ -44,7 +44,7 @@ limb_wire = False             # True: np_random_split returns limb-backed ShareR
 
 
 def _ptr(a):
-    return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(a.__array_interface__['data'][0])
 
 
 def _values_of(field, s):
@@ -132,6 +132,8 @@ def np_random_split(field, s, t, m):
         shares = _split_limbs(ctx, sec, C, t, m)
     if limb_wire:
         return ShareRows(ctx, shares, type(field.modulus) if ctx.binary else None)
+    if not ctx.binary:
+        return codec.limbs_to_ints(shares.reshape(m * n, ctx.nlimbs), ctx).reshape(m, n)   # one pass over all m rows
     out = np.empty((m, n), dtype=object)
     for i in range(m):
         out[i] = _wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))
