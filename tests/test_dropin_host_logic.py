@@ -1,0 +1,94 @@
+"""Host logic of the drop-in adapter (mpyc_b200/thresha.py) WITHOUT a GPU: the two device round trips
+(`_split_limbs`, `_recombine_limbs`) are replaced by the CPU oracle working on the same limb arrays, and the
+reference-generated golden cases are replayed through np_random_split / random_split / np_recombine / recombine.
+What this pins on CPU: argument handling (lists, field elements, field arrays), the int <-> limb codec, the
+consumption order of the coefficient stream (np: (t, n) row-major; list: element-major with Horner reversal,
+thresha.py:37-43,58-60), shapes and return types -- BASELINE configs[0] ("bit-exact plumbing, no GPU").  The
+kernels themselves are covered by the -m gpu tests with the very same fixtures."""
+import itertools
+
+import numpy as np
+import pytest
+
+import fakefield
+from golden_util import load, unhex
+from oracle import shamir_oracle as orc
+from mpyc_b200 import codec, thresha, wire
+
+SR = load('split_recombine.json')
+
+
+@pytest.fixture
+def oracle_device(monkeypatch):
+    """thresha's device calls answered by the oracle on the limb arrays the adapter built."""
+    def split_limbs(ctx, sec, C, t, m):
+        F = orc.field_of(ctx.modulus)
+        s = codec.limbs_to_ints(sec, ctx).tolist()
+        rows = [codec.limbs_to_ints(C[j], ctx).tolist() for j in range(t)]
+        shares = orc.split_np_order(F, s, rows, m)
+        return np.stack([codec.ints_to_limbs(r, ctx) for r in shares]) if s else np.zeros((m, 0, ctx.nlimbs), dtype=np.uint64)
+
+    def recombine_limbs(ctx, xs, rows, pts):
+        F = orc.field_of(ctx.modulus)
+        vals = orc.recombine(F, list(xs), [codec.limbs_to_ints(r, ctx).tolist() for r in rows], list(pts))
+        n = rows[0].shape[0]
+        return np.stack([codec.ints_to_limbs(v, ctx) for v in vals]) if n else np.zeros((len(pts), 0, ctx.nlimbs), dtype=np.uint64)
+
+    monkeypatch.setattr(thresha, '_split_limbs', split_limbs)
+    monkeypatch.setattr(thresha, '_recombine_limbs', recombine_limbs)
+
+    def inject(stream):
+        it = iter(stream)
+        monkeypatch.setattr(thresha, 'coefficient_source', lambda order, count: list(itertools.islice(it, count)))
+    return inject
+
+
+@pytest.mark.parametrize('case', SR['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_m{c['m']}t{c['t']}")
+def test_golden_cases_through_the_adapter(case, oracle_device):
+    p, m, t = int(case['p'], 16), case['m'], case['t']
+    F = fakefield.make_prime_field(p)
+    s, stream = unhex(case['secrets']), unhex(case['stream'])
+    oracle_device(stream)
+    sh_np = thresha.np_random_split(F, F.array(np.array(s, dtype=object)), t, m)
+    assert sh_np.dtype == object and sh_np.shape == (m, len(s)) and sh_np.tolist() == unhex(case['shares_np'])
+    oracle_device(stream)
+    sh_li = thresha.random_split(F, list(s), t, m)
+    assert sh_li == unhex(case['shares_list'])
+    oracle_device(stream)
+    assert thresha.random_split(F, [F(x) for x in s], t, m) == unhex(case['shares_list'])     # field elements in
+    for rec in case['recombine']:
+        xs = rec['xs']
+        y0 = thresha.np_recombine(F, [(x, sh_np[x - 1]) for x in xs])
+        assert isinstance(y0, F.array) and y0.value.tolist() == unhex(rec['y0'])
+        assert thresha.np_recombine(F, [(x, sh_np[x - 1]) for x in xs], rec['x_rs']).value.tolist() == unhex(rec['yw'])
+        assert thresha.recombine(F, [(x, unhex(case['shares_np'])[x - 1]) for x in xs]) == unhex(rec['y0'])
+        ye = thresha.recombine(F, [(x, [F(v) for v in sh_li[x - 1]]) for x in xs], [0])
+        assert all(isinstance(v, F) for v in ye[0])
+
+
+def test_c1_plumbing_and_limb_wire(oracle_device, monkeypatch):
+    """BASELINE configs[0]: 1024 secrets, p = 2^61-1, m = 3, t = 1 -- adapter == oracle bit for bit on an injected
+    coefficient stream, for the np and the list variant; and the limb-wire form of the same call recombines to the
+    same values after a pickle round trip of every row."""
+    import pickle
+    import random
+    p, m, t, n = 2**61 - 1, 3, 1, 1024
+    F, Fo = fakefield.make_prime_field(p), orc.field_of(p)
+    rnd = random.Random(1)
+    s = [rnd.randrange(p) for _ in range(n)]
+    stream = [rnd.randrange(p) for _ in range(t * n)]
+    oracle_device(stream)
+    sh = thresha.np_random_split(F, np.array(s, dtype=object), t, m)
+    assert sh.tolist() == orc.split_np_order(Fo, s, [stream[:n]], m)
+    oracle_device(stream)
+    sl = thresha.random_split(F, s, t, m)
+    assert sl == orc.split_np_order(Fo, s, [stream], m)            # t = 1: element-major == row-major
+    assert thresha.np_recombine(F, [(1, sh[0]), (3, sh[2])]).value.tolist() == s
+    monkeypatch.setattr(thresha, 'limb_wire', True)
+    oracle_device(stream)
+    rows = thresha.np_random_split(F, np.array(s, dtype=object), t, m)
+    assert isinstance(rows, wire.ShareRows) and len(rows) == m
+    shipped = [pickle.loads(pickle.dumps(r)) for r in rows]
+    assert all(isinstance(r, wire.ShareRow) for r in shipped)
+    assert [r.tolist() for r in shipped] == sh.tolist()
+    assert thresha.np_recombine(F, [(2, shipped[1]), (3, shipped[2])]).value.tolist() == s
