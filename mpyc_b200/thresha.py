@@ -289,10 +289,15 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
     wl = []
     for w in weights:
         wl.extend(_cabi.int_to_limbs(int(w), nl))
+    return _prss_device(ctx, keys, bytes(uci), d, width, bound_bits if not ctx.binary else 0, coef, wl, n)
+
+
+def _prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n):
+    """The device round trip of a PRSS call (mpyc_b200_prss_host): keys / uci / constants in, limb array (n, L) out."""
+    nl = max(ctx.nlimbs, 1)
     out = np.empty((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
-    check(lib.mpyc_b200_prss_host(ctx.handle, b''.join(keys), klen, bytes(uci), len(uci), len(subsets), d, width,
-                                  bound_bits if not ctx.binary else 0, _cabi.u64_array(coef), _cabi.u64_array(wl),
-                                  _ptr(out), n, device, prss_threads))
+    check(lib.mpyc_b200_prss_host(ctx.handle, b''.join(keys), len(keys[0]), uci, len(uci), len(keys), d, width, bound_bits,
+                                  _cabi.u64_array(coef), _cabi.u64_array(weights), _ptr(out), n, device, prss_threads))
     return out
 
 

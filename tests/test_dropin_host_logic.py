@@ -92,3 +92,57 @@ def test_c1_plumbing_and_limb_wire(oracle_device, monkeypatch):
     assert all(isinstance(r, wire.ShareRow) for r in shipped)
     assert [r.tolist() for r in shipped] == sh.tolist()
     assert thresha.np_recombine(F, [(2, shipped[1]), (3, shipped[2])]).value.tolist() == s
+
+
+# ---- PRSS adapter: keys, coefficients f_S(i) (computed by the library's HOST code), weights and their order ----------
+
+PRSS = load('prss.json')
+
+
+@pytest.fixture
+def oracle_prss(monkeypatch):
+    """thresha._prss_device answered on the CPU: SHAKE128 streams via the library's own host XOF (checked against hashlib
+    in test_shake128.py), chunk -> value and the linear combination on Python ints, straight from the formula of
+    include/mpyc_b200.h (out = sum_S coef_S * sum_j value_{S,h,j} * w_j)."""
+    import ctypes
+    from mpyc_b200 import _cabi
+
+    def prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n):
+        assert not ctx.binary
+        p, L = ctx.modulus, ctx.nlimbs
+        cs = [_cabi.limbs_to_int(coef[i * L:(i + 1) * L]) for i in range(len(keys))]
+        ws = [_cabi.limbs_to_int(weights[j * L:(j + 1) * L]) for j in range(d)]
+        acc = [0] * n
+        for key, c in zip(keys, cs):
+            raw = ctypes.create_string_buffer(n * d * width)
+            _cabi.check(_cabi.lib.mpyc_b200_shake128(key + uci, len(key) + len(uci), raw, n * d * width))
+            raw = raw.raw
+            for h in range(n):
+                y = 0
+                for j in range(d):
+                    v = int.from_bytes(raw[(h * d + j) * width:(h * d + j + 1) * width], 'little')
+                    v = v % p if bound_bits == 0 else v & ((1 << bound_bits) - 1)
+                    y += v * ws[j]
+                acc[h] += c * y
+        return codec.ints_to_limbs([a % p for a in acc], ctx)
+
+    monkeypatch.setattr(thresha, '_prss_device', prss_device)
+
+
+@pytest.mark.parametrize('case', PRSS['cases'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_m{c['m']}t{c['t']}")
+def test_golden_prss_through_the_adapter(case, oracle_prss):
+    p, m, t, n = int(case['p'], 16), case['m'], case['t'], case['n']
+    F = fakefield.make_prime_field(p)
+    uci = bytes.fromhex(case['uci'])
+    keys = {tuple(int(x) for x in k.split(',')): bytes.fromhex(v) for k, v in case['keys'].items()}
+    for party in case['parties']:
+        i = party['i']
+        prfs = {S: thresha.PRF(k, p) for S, k in keys.items() if i in S}
+        for S in prfs:
+            assert thresha._f_S_i(F, m, i, S) == int(party['f_S_i'][','.join(map(str, S))], 16) % p
+        a_np = thresha.np_pseudorandom_share(F, m, i, prfs, uci, n)
+        assert isinstance(a_np, F.array) and a_np.value.tolist() == unhex(party['share_np'])
+        assert [x.value for x in thresha.pseudorandom_share(F, m, i, prfs, uci, n)] == unhex(party['share_list'])
+        assert [x.value for x in thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)] == unhex(party['zero_list'])
+        if t:
+            assert thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n).value.tolist() == unhex(party['zero_np'])
