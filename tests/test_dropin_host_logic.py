@@ -21,18 +21,21 @@ SR = load('split_recombine.json')
 @pytest.fixture
 def oracle_device(monkeypatch):
     """thresha's device calls answered by the oracle on the limb arrays the adapter built."""
+    def empty(ctx, rows):
+        return np.zeros((rows, 0) if ctx.binary else (rows, 0, ctx.nlimbs), dtype=np.uint8 if ctx.binary else np.uint64)
+
     def split_limbs(ctx, sec, C, t, m):
-        F = orc.field_of(ctx.modulus)
-        s = codec.limbs_to_ints(sec, ctx).tolist()
-        rows = [codec.limbs_to_ints(C[j], ctx).tolist() for j in range(t)]
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        s = [int(v) for v in codec.limbs_to_ints(sec, ctx)]
+        rows = [[int(v) for v in codec.limbs_to_ints(C[j], ctx)] for j in range(t)]
         shares = orc.split_np_order(F, s, rows, m)
-        return np.stack([codec.ints_to_limbs(r, ctx) for r in shares]) if s else np.zeros((m, 0, ctx.nlimbs), dtype=np.uint64)
+        return np.stack([codec.ints_to_limbs(r, ctx) for r in shares]) if s else empty(ctx, m)
 
     def recombine_limbs(ctx, xs, rows, pts):
-        F = orc.field_of(ctx.modulus)
-        vals = orc.recombine(F, list(xs), [codec.limbs_to_ints(r, ctx).tolist() for r in rows], list(pts))
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        vals = orc.recombine(F, list(xs), [[int(v) for v in codec.limbs_to_ints(r, ctx)] for r in rows], list(pts))
         n = rows[0].shape[0]
-        return np.stack([codec.ints_to_limbs(v, ctx) for v in vals]) if n else np.zeros((len(pts), 0, ctx.nlimbs), dtype=np.uint64)
+        return np.stack([codec.ints_to_limbs(v, ctx) for v in vals]) if n else empty(ctx, len(pts))
 
     monkeypatch.setattr(thresha, '_split_limbs', split_limbs)
     monkeypatch.setattr(thresha, '_recombine_limbs', recombine_limbs)
@@ -92,6 +95,27 @@ def test_c1_plumbing_and_limb_wire(oracle_device, monkeypatch):
     assert all(isinstance(r, wire.ShareRow) for r in shipped)
     assert [r.tolist() for r in shipped] == sh.tolist()
     assert thresha.np_recombine(F, [(2, shipped[1]), (3, shipped[2])]).value.tolist() == s
+
+
+def test_gf256_golden_through_the_adapter(oracle_device):
+    """GF(2^8) (np_aes's field): values cross the Python surface as polynomial objects, points are the field elements
+    with integer encoding i+1 (thresha.py:54,61); np and list draw orders as for prime fields."""
+    G = load('gf256.json')
+    F = fakefield.make_gf256(G['modulus'])
+    for case in G['split']:
+        m, t = case['m'], case['t']
+        s, stream = unhex(case['secrets']), unhex(case['stream'])
+        oracle_device(stream)
+        sh = thresha.np_random_split(F, np.array([fakefield.Poly(x) for x in s], dtype=object), t, m)
+        assert all(isinstance(v, fakefield.Poly) for v in sh[0])
+        assert [[int(v) for v in row] for row in sh] == unhex(case['shares_np'])
+        oracle_device(stream)
+        sl = thresha.random_split(F, [F(x) for x in s], t, m)
+        assert [[int(v) for v in row] for row in sl] == unhex(case['shares_list'])
+        xs = case['xs']
+        assert [int(v) for v in thresha._recombination_vector(F, tuple(xs), 0)] == unhex(case['lambda0'])
+        y = thresha.np_recombine(F, [(x, sh[x - 1]) for x in xs])
+        assert [int(v) for v in y.value] == unhex(case['y0'])
 
 
 # ---- PRSS adapter: keys, coefficients f_S(i) (computed by the library's HOST code), weights and their order ----------
