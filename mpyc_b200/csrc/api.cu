@@ -880,9 +880,9 @@ int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int
     const size_t L = f->fp.L;
     std::vector<u64> host;
     tab.small = prss_small_table(f->fp, nsub, d, h_coef, h_weights, host);
-    // small form: weights are plain integers in limb 0.  The compile-time plain-share kernel is opt-in until it has been
-    // through the GPU parity suite (MPYC_B200_PRSS_SIMPLE=1; tests/test_gpu_parity.py runs both forms)
-    tab.simple = tab.small && d == 1 && h_weights[0] == 1 && getenv("MPYC_B200_PRSS_SIMPLE") != nullptr;
+    // small form: weights are plain integers in limb 0; d == 1 with weight 1 (the plain pseudorandom share) has its own
+    // compile-time kernel variant (MPYC_B200_PRSS_NO_SIMPLE=1 selects the general small form: parity tests compare both)
+    tab.simple = tab.small && d == 1 && h_weights[0] == 1 && getenv("MPYC_B200_PRSS_NO_SIMPLE") == nullptr;
     if (!tab.small) {
         host.resize(((size_t)nsub + d) * L);
         memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));

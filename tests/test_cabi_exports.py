@@ -78,3 +78,35 @@ def test_codec_roundtrip():
         assert len(wire) == len(vals) * ctx.byte_length
         assert wire == b''.join((v % p).to_bytes(ctx.byte_length, 'little') for v in vals)
         assert np.array_equal(codec.wire_to_limbs(wire, ctx), limbs)
+
+
+def test_argument_errors_and_no_gpu_errors_of_the_newer_entry_points():
+    """Bad arguments are rejected before any CUDA call (ValueError / TypeError, also without a GPU); with valid arguments
+    and no CUDA device every compute / peer entry point fails with MPYC_B200_ECUDA (RuntimeError) -- PRSS included:
+    the library's host SHAKE128 never produces a result on its own."""
+    import numpy as np
+    import mpyc_b200
+    from mpyc_b200 import _cabi, thresha
+    from mpyc_b200._cabi import lib, check
+    import fakefield
+    torch = pytest.importorskip('torch')
+    ctx = mpyc_b200.context_for(2**61 - 1)
+    one = _cabi.u64_array([1])
+    out = np.zeros((4, 1), dtype=np.uint64)
+    with pytest.raises(ValueError):      # nsub = 0
+        check(lib.mpyc_b200_prss_host(ctx.handle, b'k' * 16, 16, b'u', 1, 0, 1, 24, 0, one, one, out.ctypes.data, 4, 0, 0))
+    with pytest.raises(ValueError):      # null row table
+        check(lib.mpyc_b200_shamir_split_generate_rows(ctx.handle, out.ctypes.data, None, 4, 1, 3,
+                                                       (ctypes.c_uint8 * 32)(), 0, None))
+    with pytest.raises(ValueError):      # t >= m
+        check(lib.mpyc_b200_shamir_split_generate_host(ctx.handle, out.ctypes.data, out.ctypes.data, 4, 4, 3, 3,
+                                                       (ctypes.c_uint8 * 32)(), 0, 0))
+    if torch.cuda.is_available():
+        return
+    F = fakefield.make_prime_field(2**61 - 1)
+    prfs = {(0, 1): thresha.PRF(b'k' * 16, 2**61 - 1), (0, 2): thresha.PRF(b'j' * 16, 2**61 - 1)}
+    with pytest.raises(RuntimeError):
+        thresha.np_pseudorandom_share(F, 3, 0, prfs, b'uci', 5)
+    ptr, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+    with pytest.raises(RuntimeError):
+        check(lib.mpyc_b200_peer_alloc(1024, ctypes.byref(ptr), handle))

@@ -567,10 +567,10 @@ def test_prss_pipeline_in_library(p, m, t, monkeypatch):
     tiled_full = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
     zero_full = thresha.np_pseudorandom_share_0(F, m, i, prfs(p), uci, 3001).value.tolist()
     monkeypatch.delenv('MPYC_B200_PRSS_FULL')
-    monkeypatch.setenv('MPYC_B200_PRSS_SIMPLE', '1')     # compile-time plain-share form of the tiled kernel
-    simple = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
-    monkeypatch.delenv('MPYC_B200_PRSS_SIMPLE')
-    assert simple.tolist() == ref.tolist()
+    monkeypatch.setenv('MPYC_B200_PRSS_NO_SIMPLE', '1')  # general small form instead of the compile-time plain-share variant
+    general = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    monkeypatch.delenv('MPYC_B200_PRSS_NO_SIMPLE')
+    assert general.tolist() == ref.tolist()
     assert zero_full == got0
     assert ref.tolist() == one.tolist() == flat.tolist() == flat_full.tolist() == tiled_full.tolist()
     assert ref[:n].tolist() == got               # a longer call extends the same streams (XOF prefix property)
