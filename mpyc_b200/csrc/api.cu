@@ -797,9 +797,10 @@ struct PrssTable {
     std::vector<unsigned char> gf;     // GF(2^8): passed to the kernel by value
     bool small = false;                // [(|num_S|, sign_S) x nsub | w_j x d | D^-1 (L limbs)]: see prss_small_table
     bool simple = false;               // small, d == 1 and weight 1: the plain pseudorandom share
+    bool owned = false;                // false: d_tab lives in the field handle's table cache
     cudaStream_t st = nullptr;
     ~PrssTable() {
-        if (d_tab) cudaFreeAsync(d_tab, st);
+        if (d_tab && owned) cudaFreeAsync(d_tab, st);
     }
 };
 
@@ -878,26 +879,57 @@ int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int
     if (bound_bits > 0 && chunk_bytes != (bound_bits + 7) / 8) return fail(MPYC_B200_EINVAL, "prss: chunk_bytes != ceil(bound_bits/8)");
     if ((unsigned)nsub > FF_MAX_LAZY_TERMS || (unsigned)d > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "prss: too many terms");
     const size_t L = f->fp.L;
-    std::vector<u64> host;
-    tab.small = prss_small_table(f->fp, nsub, d, h_coef, h_weights, host);
-    // small form: weights are plain integers in limb 0; d == 1 with weight 1 (the plain pseudorandom share) has its own
-    // compile-time kernel variant (MPYC_B200_PRSS_NO_SIMPLE=1 selects the general small form: parity tests compare both)
-    tab.simple = tab.small && d == 1 && h_weights[0] == 1 && getenv("MPYC_B200_PRSS_NO_SIMPLE") == nullptr;
-    if (!tab.small) {
-        host.resize(((size_t)nsub + d) * L);
-        memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
-        memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
-        to_table_form(f->fp, host);
+    auto build = [&](std::vector<u64>& host, bool& full) {
+        const bool small = prss_small_table(f->fp, nsub, d, h_coef, h_weights, host);
+        if (!small) {
+            host.resize(((size_t)nsub + d) * L);
+            memcpy(host.data(), h_coef, (size_t)nsub * L * sizeof(u64));
+            memcpy(host.data() + (size_t)nsub * L, h_weights, (size_t)d * L * sizeof(u64));
+            to_table_form(f->fp, host);
+        }
+        if (host.size() * sizeof(u64) > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss: coefficient table exceeds shared memory");
+        full = !small;
+        return MPYC_B200_OK;
+    };
+    // The constants depend only on (m, t, party): a handful of distinct tables per computation.  They are kept in the
+    // field handle's cache, keyed by their bytes, so that a call costs no allocation, upload or synchronisation;
+    // beyond 512 cached tables (a caller inventing coefficients per call) the table is uploaded per call instead.
+    mpyc_b200_field* fm = const_cast<mpyc_b200_field*>(f);
+    bool cache_ok;
+    {
+        std::lock_guard<std::mutex> g(fm->mu);
+        cache_ok = fm->tables.size() < 512;
     }
-    if (host.size() % 2) host.push_back(0);
-    tab.bytes = (u32)(host.size() * sizeof(u64));
-    if (tab.bytes > MAX_SMEM_TABLE) return fail(MPYC_B200_EUNSUPPORTED, "prss: coefficient table exceeds shared memory");
-    // the coefficients depend on the party and the subset layout: per call, stream-ordered allocation
-    tab.st = st;
-    CU(cudaMallocAsync(&tab.d_tab, tab.bytes, st));
-    cudaError_t e = cudaMemcpyAsync(tab.d_tab, host.data(), tab.bytes, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vector goes out of scope
-    return e == cudaSuccess ? MPYC_B200_OK : cuda_fail(e, "prss table upload");
+    bool full = false;
+    if (cache_ok) {
+        std::string key = "prss:" + std::to_string(current_device()) + ":" + std::to_string(nsub) + ":" + std::to_string(d) + ":" +
+                          (getenv("MPYC_B200_PRSS_FULL") ? "F" : "S") + ":";
+        key.append((const char*)h_coef, (size_t)nsub * L * sizeof(u64));
+        key.append((const char*)h_weights, (size_t)d * L * sizeof(u64));
+        DevTable t;
+        int rc = get_table(fm, key, &t, build);
+        if (rc) return rc;
+        tab.d_tab = t.d;
+        tab.bytes = t.bytes;
+        full = t.full;
+    } else {
+        std::vector<u64> host;
+        int rc = build(host, full);
+        if (rc) return rc;
+        if (host.size() % 2) host.push_back(0);
+        tab.bytes = (u32)(host.size() * sizeof(u64));
+        tab.st = st;
+        tab.owned = true;
+        CU(cudaMallocAsync(&tab.d_tab, tab.bytes, st));
+        cudaError_t e = cudaMemcpyAsync(tab.d_tab, host.data(), tab.bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host vector goes out of scope
+        if (e != cudaSuccess) return cuda_fail(e, "prss table upload");
+    }
+    tab.small = !full;
+    // d == 1 with weight 1 (the plain pseudorandom share) has its own compile-time kernel variant
+    // (MPYC_B200_PRSS_NO_SIMPLE=1 selects the general small form: parity tests compare both)
+    tab.simple = tab.small && d == 1 && h_weights[0] == 1 && getenv("MPYC_B200_PRSS_NO_SIMPLE") == nullptr;
+    return MPYC_B200_OK;
 }
 
 int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
