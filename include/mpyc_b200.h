@@ -158,6 +158,12 @@ int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes,
                            int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                            const uint64_t* h_weights, void* d_out, size_t n, void* stream);
 
+/* Host-only: the small-integer form K4 uses when it exists.  f_S(i) (thresha.py:135-141) is a ratio of small integers, so
+ * for some k <= 20 every h_coef[S] * k! mod p is a small signed integer num_S (|num_S| < 2^57): h_num[S] receives it and
+ * h_scale_inv (L limbs, may be NULL) receives (k!)^-1 mod p, i.e. coef_S = num_S * scale_inv mod p.  EUNSUPPORTED if the
+ * coefficients (or the weights, which must be plain integers < 2^58) have no such form; the kernel then uses full products. */
+int mpyc_b200_prss_small_form(const mpyc_b200_field* f, int nsub, int d, const uint64_t* h_coef,
+                              const uint64_t* h_weights, int64_t* h_num, uint64_t* h_scale_inv);
 /* The same with the PRF evaluated inside the library (thresha.PRF.__call__, mpyc/thresha.py:240-266, and the
  * callers thresha.py:163-217): subset S's stream is SHAKE128(key_S || uci) squeezed to n*d*chunk_bytes bytes.
  * h_keys: nsub keys of key_bytes bytes each (PRF.key), h_uci: the unique call identifier bytes.  One sponge is

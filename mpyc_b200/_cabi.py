@@ -71,6 +71,8 @@ _SIGNATURES = {
                                            c_int, c_void_p, c_size_t, c_size_t, c_void_p]),
     'mpyc_b200_prss_combine': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, POINTER(c_uint64),
                                        POINTER(c_uint64), c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_prss_small_form': (c_int, [_field_p, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int64),
+                                          POINTER(c_uint64)]),
     'mpyc_b200_prss_host': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int, c_int,
                                     POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_int, c_int]),
     'mpyc_b200_enable_peer_access': (c_int, [c_int, c_int]),

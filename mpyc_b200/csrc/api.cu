@@ -945,6 +945,19 @@ int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d
 
 }   // namespace
 
+// Host-only view of prss_small_table (no GPU involved): which scale k! makes the subset coefficients small integers.
+MPYC_API int mpyc_b200_prss_small_form(const mpyc_b200_field* f, int nsub, int d, const uint64_t* h_coef,
+                                         const uint64_t* h_weights, int64_t* h_num, uint64_t* h_scale_inv) {
+    if (!f || !h_coef || !h_weights || !h_num || nsub < 1 || d < 1) return fail(MPYC_B200_EINVAL, "prss_small_form: bad arguments");
+    REQUIRE_PRIME(f, "prss_small_form");
+    std::vector<u64> tab;
+    if (!prss_small_table(f->fp, nsub, d, h_coef, h_weights, tab)) return fail(MPYC_B200_EUNSUPPORTED, "prss_small_form: no small-integer form");
+    for (int S = 0; S < nsub; S++) h_num[S] = tab[2 * S + 1] ? -(int64_t)tab[2 * S] : (int64_t)tab[2 * S];
+    if (h_scale_inv)
+        for (size_t l = 0; l < f->fp.L; l++) h_scale_inv[l] = tab[(size_t)2 * nsub + d + l];
+    return MPYC_B200_OK;
+}
+
 MPYC_API int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
                                       int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                                       const uint64_t* h_weights, void* d_out, size_t n, void* stream) {

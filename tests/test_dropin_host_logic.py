@@ -170,3 +170,47 @@ def test_golden_prss_through_the_adapter(case, oracle_prss):
         assert [x.value for x in thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)] == unhex(party['zero_list'])
         if t:
             assert thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n).value.tolist() == unhex(party['zero_np'])
+
+
+def test_small_integer_form_of_the_prss_coefficients():
+    """The host detection behind K4's small form (api.cu: prss_small_table): for every party i of every (m, t) up to 9
+    parties, the coefficients f_S(i) of the party's key subsets times some k! are exactly the small signed integers the
+    rational formula prod_{j not in S} (i - j) / (-(j + 1)) predicts -- checked with Fractions, no GPU involved."""
+    import ctypes
+    import math
+    from fractions import Fraction
+    import mpyc_b200
+    from mpyc_b200 import _cabi
+    for p in (2**61 - 1, 2**128 - 173, 2**256 - 189, 9409569905028393239):
+        ctx = mpyc_b200.context_for(p)
+        L = ctx.nlimbs
+        F = fakefield.make_prime_field(p)
+        for m, t in ((3, 1), (5, 2), (7, 3), (9, 4), (4, 1), (6, 2)):
+            for i in range(m):
+                subsets = [S for S in itertools.combinations(range(m), m - t) if i in S]
+                coef = []
+                for S in subsets:
+                    coef.extend(_cabi.int_to_limbs(int(thresha._f_S_i(F, m, i, S)), L))
+                num = (ctypes.c_int64 * len(subsets))()
+                inv = (ctypes.c_uint64 * L)()
+                rc = _cabi.lib.mpyc_b200_prss_small_form(ctx.handle, len(subsets), 1, _cabi.u64_array(coef),
+                                                         _cabi.u64_array(_cabi.int_to_limbs(1, L)), num, inv)
+                if len(subsets) > 64:          # more than 64 subsets (m = 9, t = 4: 70): the kernel keeps full products
+                    assert rc == _cabi.EUNSUPPORTED
+                    continue
+                _cabi.check(rc)
+                scale_inv = _cabi.limbs_to_int(list(inv))
+                D = pow(scale_inv, -1, p)
+                assert any(D == math.factorial(k) % p for k in range(1, 21))
+                for S, n_S in zip(subsets, num):
+                    exact = Fraction(1)
+                    for j in range(m):
+                        if j not in S:
+                            exact *= Fraction(i - j, -(j + 1))
+                    assert n_S * scale_inv % p == exact.numerator * pow(exact.denominator, -1, p) % p
+                    assert abs(n_S) < 2**57
+    # coefficients that are not small rationals have no small form
+    ctx = mpyc_b200.context_for(2**128 - 173)
+    junk = _cabi.u64_array(_cabi.int_to_limbs(0x123456789abcdef0123456789abcdef % (2**128 - 173), 2))
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):
+        _cabi.check(_cabi.lib.mpyc_b200_prss_small_form(ctx.handle, 1, 1, junk, _cabi.u64_array([1, 0]), (ctypes.c_int64 * 1)(), None))
