@@ -153,7 +153,9 @@ int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* const* d_sh
  * with h_coef[S] = f_S(i) (thresha.py:135-141) and h_weights[j] = 1 (d = 1, share) or (i+1)^(j+1)
  * (share_0), both canonical host limbs.  bound_bits == 0: the PRF bound is the field order (chunks are
  * reduced mod p); bound_bits = b > 0: the bound is 2^b <= p (runtime.py:4076, chunks are masked to b
- * bits, chunk_bytes == ceil(b/8)). */
+ * bits, chunk_bytes == ceil(b/8)).  GF(2^8): one byte per chunk, bound_bits = b in 1..8 masks it to b bits (bound 2^b;
+ * b = 1 is runtime.random_bits on a characteristic-2 field, runtime.py:4138,4218), 0 = the whole byte.  Any other bound:
+ * mpyc_b200_prf_reduce first. */
 int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes,
                            int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                            const uint64_t* h_weights, void* d_out, size_t n, void* stream);
@@ -173,6 +175,25 @@ int mpyc_b200_prss_small_form(const mpyc_b200_field* f, int nsub, int d, const u
 int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
                         size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                         const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads);
+/* PRF values for an ARBITRARY bound (thresha.PRF.__call__, mpyc/thresha.py:257-261: int.from_bytes(chunk, 'little') % bound).
+ * The two bounds of the secure-randomness protocols (the field order, 2^b <= p) are folded into prss_combine; every other
+ * bound -- runtime._convert's (1 << (k+l)) // comb(m,t) + 1 (mpyc/runtime.py:735-739), the source field's order used on a
+ * smaller target field (runtime.py:758-760), a power of two above p -- is reduced by this kernel first.  h_bound:
+ * bound_nlimbs (<= 5) little-endian host limbs, 2 <= bound <= 2^256.  For each of nsub streams, `count` chunks of
+ * chunk_bytes (<= 8 * (limbs(bound) + 2)) bytes are read from d_prf_bytes + S * subset_stride_bytes and
+ * d_values + S * value_stride_bytes receives `count` values of *value_bytes bytes each: 8 * limbs(bound - 1)
+ * little-endian bytes, or, when f is a GF(2^8) handle, ONE byte -- the GF(2)[X] polynomial whose integer encoding is the
+ * reduced chunk (gfpx's int coercion, mpyc/gfpx.py:73-81) modulo the field polynomial.  f may be NULL (plain integers).
+ * Feed the values to mpyc_b200_prss_combine with chunk_bytes = *value_bytes, bound_bits = 0. */
+int mpyc_b200_prf_reduce(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
+                         size_t count, int chunk_bytes, const uint64_t* h_bound, int bound_nlimbs, void* d_values,
+                         size_t value_stride_bytes, int* value_bytes, void* stream);
+/* mpyc_b200_prss_host for an arbitrary PRF bound (see mpyc_b200_prf_reduce): per pipeline chunk the library runs
+ * the reduction kernel and then the combine kernel on the reduced values. */
+int mpyc_b200_prss_host_bound(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                              size_t uci_bytes, int nsub, int d, int chunk_bytes, const uint64_t* h_bound, int bound_nlimbs,
+                              const uint64_t* h_coef, const uint64_t* h_weights, void* h_out, size_t n, int device,
+                              int max_threads);
 /* SHAKE128 (FIPS 202) of `in`, squeezed to outlen bytes: hashlib.shake_128(in).digest(outlen), the XOF of
  * thresha.PRF (mpyc/thresha.py:257).  Host only; no GPU involved. */
 int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen);

@@ -11,8 +11,12 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libmpyc_b200.so')
 SOURCES = ['api.cu', 'inst_L1.cu', 'inst_L2.cu', 'inst_L3.cu', 'inst_L4.cu']
-HEADERS = ['ff_arith.cuh', 'kernels.cuh', 'launch.h', 'launch_impl.cuh', 'gf256.cuh',
-           os.path.join('..', '..', 'include', 'mpyc_b200.h')]
+PUBLIC_HEADER = os.path.join('..', '..', 'include', 'mpyc_b200.h')
+
+
+def _headers():
+    """Every header a translation unit may include: all of csrc/*.h, *.cuh plus the public C header."""
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))) + [PUBLIC_HEADER]
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-fno-strict-aliasing', '--expt-relaxed-constexpr',
               '-Xfatbin', '-compress-all']   # compressed fatbin: the library travels to the GPU box with every gpurun call
@@ -27,7 +31,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
-    for name in SOURCES + HEADERS:
+    for name in SOURCES + _headers():
         with open(os.path.join(CSRC, name), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -37,15 +41,32 @@ CODEC_SRC = os.path.join(CSRC, 'pycodec.c')
 CODEC_LIB = os.path.join(HERE, '_pycodec.so')
 
 
+def _codec_digest():
+    """Source hash + the interpreter's ABI: pycodec.c reads CPython's long-object digits directly, so an extension
+    built for another interpreter must never be loaded (it is rebuilt instead)."""
+    import sys
+    import sysconfig
+    h = hashlib.sha256()
+    with open(CODEC_SRC, 'rb') as fh:
+        h.update(fh.read())
+    h.update(repr((sys.implementation.name, sys.version_info[:3], sysconfig.get_config_var('EXT_SUFFIX'),
+                   sys.int_info.bits_per_digit)).encode())
+    return h.hexdigest()
+
+
 def build_codec(force=False):
     """The small CPython extension that packs/unpacks Python ints (gcc, no CUDA involved)."""
     import sysconfig
-    if not force and os.path.exists(CODEC_LIB) and os.path.getmtime(CODEC_LIB) >= os.path.getmtime(CODEC_SRC):
+    stamp = CODEC_LIB + '.digest'
+    digest = _codec_digest()
+    if not force and os.path.exists(CODEC_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return CODEC_LIB
     inc = sysconfig.get_paths()['include']
     r = subprocess.run(['gcc', '-O2', '-shared', '-fPIC', '-I' + inc, CODEC_SRC, '-o', CODEC_LIB], capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError('gcc failed for pycodec.c:\n' + r.stderr[-4000:])
+    with open(stamp, 'w') as fh:
+        fh.write(digest)
     return CODEC_LIB
 
 

@@ -30,11 +30,8 @@ def _load():
     spec = importlib.util.spec_from_file_location('_mpyc_b200_build', os.path.join(_HERE, '_build.py'))
     builder = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(builder)
-    try:
-        builder.build()
-    except RuntimeError:
-        if not (os.path.exists(LIB_PATH) and os.path.exists(os.path.join(_HERE, '_pycodec.so'))):
-            raise
+    builder.build()   # returns at once when the library's digest stamp matches the sources; a library whose stamp does
+    #                   not match is NEVER loaded (no stale-binary fallback): without nvcc this raises
     return ctypes.CDLL(os.path.join(_HERE, _VARIANT) if _VARIANT else LIB_PATH)
 
 
@@ -75,6 +72,11 @@ _SIGNATURES = {
                                           POINTER(c_uint64)]),
     'mpyc_b200_prss_host': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int, c_int,
                                     POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_int, c_int]),
+    'mpyc_b200_prss_host_bound': (c_int, [_field_p, c_char_p, c_int, c_char_p, c_size_t, c_int, c_int, c_int,
+                                          POINTER(c_uint64), c_int, POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t,
+                                          c_int, c_int]),
+    'mpyc_b200_prf_reduce': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_size_t, c_int, POINTER(c_uint64), c_int, c_void_p,
+                                     c_size_t, POINTER(c_int), c_void_p]),
     'mpyc_b200_enable_peer_access': (c_int, [c_int, c_int]),
     'mpyc_b200_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), POINTER(c_uint8)]),
     'mpyc_b200_peer_open': (c_int, [POINTER(c_uint8), POINTER(c_void_p)]),

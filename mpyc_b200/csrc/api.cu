@@ -23,6 +23,7 @@
 #include "field_setup.h"
 #include "gf256.cuh"
 #include "launch.h"
+#include "prf_reduce.cuh"
 #include "shake128.h"
 
 #define MPYC_API extern "C" __attribute__((visibility("default")))
@@ -868,7 +869,7 @@ bool prss_small_table(const FieldParams& fp, int nsub, int d, const uint64_t* h_
 int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
                  const uint64_t* h_weights, cudaStream_t st, PrssTable& tab) {
     if (f->kind == MPYC_B200_KIND_GF256) {
-        if (chunk_bytes != 1 || (bound_bits != 0 && bound_bits != 8)) return fail(MPYC_B200_EINVAL, "prss: GF(2^8) PRF chunks are one byte");
+        if (chunk_bytes != 1 || bound_bits < 0 || bound_bits > 8) return fail(MPYC_B200_EINVAL, "prss: GF(2^8) PRF chunks are one byte, bound 2^b <= 256");
         tab.gf.resize((size_t)nsub + d);
         for (int i = 0; i < nsub; i++) tab.gf[i] = (unsigned char)h_coef[i];
         for (int j = 0; j < d; j++) tab.gf[nsub + j] = (unsigned char)h_weights[j];
@@ -935,7 +936,8 @@ int prss_prepare(const mpyc_b200_field* f, int nsub, int d, int chunk_bytes, int
 int prss_launch(const mpyc_b200_field* f, const PrssTable& tab, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
                 int d, int chunk_bytes, int bound_bits, void* d_out, size_t n, cudaStream_t st) {
     if (f->kind == MPYC_B200_KIND_GF256)
-        return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.gf.data(), (unsigned char*)d_out, n, st), "gf256 prss");
+        return launch_status(gf256_prss(f->gf_poly, d_prf_bytes, subset_stride_bytes, nsub, d, tab.gf.data(),
+                                        bound_bits > 0 && bound_bits < 8 ? (1u << bound_bits) - 1u : 0xFFu, (unsigned char*)d_out, n, st), "gf256 prss");
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
         return launch_status(Launch<LL>::prss(f->fp, tab.small, tab.simple, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits,
@@ -969,6 +971,74 @@ MPYC_API int mpyc_b200_prss_combine(const mpyc_b200_field* f, const uint8_t* d_p
     int rc = prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, st, tab);
     if (rc) return rc;
     return prss_launch(f, tab, d_prf_bytes, subset_stride_bytes, nsub, d, chunk_bytes, bound_bits, d_out, n, st);
+}
+
+namespace {
+
+// description of a general PRF bound for prf_reduce.cuh
+struct BoundSpec {
+    FieldParams fb;        // Barrett constants (not used for powers of two)
+    int pow2_bits = 0;     // > 0: bound = 2^pow2_bits
+    int LB = 1;            // 64-bit limbs of a reduced value
+};
+
+// h_bound: nlimbs little-endian limbs of the bound (leading zero limbs allowed), 3 <= bound <= 2^256 (2 = 2^1 too)
+int bound_spec(const uint64_t* h_bound, int nlimbs, BoundSpec& b) {
+    if (!h_bound || nlimbs < 1 || nlimbs > 5) return fail(MPYC_B200_EINVAL, "prf bound: 1..5 limbs");
+    int nz = nlimbs;
+    while (nz > 0 && h_bound[nz - 1] == 0) nz--;
+    if (nz == 0) return fail(MPYC_B200_EINVAL, "prf bound: zero");
+    int pop = 0;
+    for (int i = 0; i < nz; i++) pop += __builtin_popcountll(h_bound[i]);
+    const int bits = 64 * (nz - 1) + 64 - __builtin_clzll(h_bound[nz - 1]);
+    if (pop == 1) {
+        b.pow2_bits = bits - 1;
+        if (b.pow2_bits < 1) return fail(MPYC_B200_EINVAL, "prf bound: must be >= 2");
+        if (b.pow2_bits > 256) return fail(MPYC_B200_EUNSUPPORTED, "prf bound wider than 256 bits");
+        b.LB = std::max(1, (b.pow2_bits + 63) / 64);
+        memset(&b.fb, 0, sizeof b.fb);
+        return MPYC_B200_OK;
+    }
+    if (nz > 4) return fail(MPYC_B200_EUNSUPPORTED, "prf bound wider than 256 bits");
+    if (nz == 1 && h_bound[0] < 3) return fail(MPYC_B200_EINVAL, "prf bound: must be >= 2");
+    b.pow2_bits = 0;
+    b.LB = nz;
+    bound_params_init(h_bound, nz, &b.fb);
+    return MPYC_B200_OK;
+}
+
+int prf_reduce_launch(const BoundSpec& b, unsigned gf_poly, const uint8_t* d_bytes, size_t subset_stride, int nsub, size_t count,
+                      int chunk_bytes, void* d_values, size_t value_stride, cudaStream_t st) {
+    if (chunk_bytes < 1 || chunk_bytes > 8 * (b.LB + 2)) return fail(MPYC_B200_EINVAL, "prf_reduce: chunk too wide for this bound");
+    if (!gf_poly && (((uintptr_t)d_values | value_stride) & 7u)) return fail(MPYC_B200_EINVAL, "prf_reduce: values must be 8-byte aligned");
+    const size_t total = (size_t)nsub * count;
+    return with_limbs(b.LB, [&](auto Lc) {
+        constexpr int LB = decltype(Lc)::value;
+        if (total == 0) return (int)MPYC_B200_OK;
+        const int grid = mpyc_grid_size((const void*)k_prf_reduce<LB>, total, 0);
+        if (grid <= 0) return fail(MPYC_B200_ECUDA, "prf_reduce: no device");
+        k_prf_reduce<LB><<<grid, MPYC_THREADS, 0, st>>>(b.fb, b.pow2_bits, (const unsigned char*)d_bytes, subset_stride, nsub, count, chunk_bytes,
+                                                        (unsigned char*)d_values, value_stride, gf_poly);
+        g_mpyc_launches.fetch_add(1);
+        return launch_status(cudaGetLastError(), "prf_reduce launch");
+    });
+}
+
+}   // namespace
+
+MPYC_API int mpyc_b200_prf_reduce(const mpyc_b200_field* f, const uint8_t* d_prf_bytes, size_t subset_stride_bytes, int nsub,
+                                    size_t count, int chunk_bytes, const uint64_t* h_bound, int bound_nlimbs, void* d_values,
+                                    size_t value_stride_bytes, int* value_bytes, void* stream) {
+    if (nsub < 1 || chunk_bytes < 1) return fail(MPYC_B200_EINVAL, "prf_reduce: bad arguments");
+    BoundSpec b;
+    int rc = bound_spec(h_bound, bound_nlimbs, b);
+    if (rc) return rc;
+    const bool gf = f && f->kind == MPYC_B200_KIND_GF256;
+    if (value_bytes) *value_bytes = gf ? 1 : 8 * b.LB;
+    if (count == 0) return MPYC_B200_OK;
+    if (!d_prf_bytes || !d_values) return fail(MPYC_B200_EINVAL, "prf_reduce: null buffer");
+    return prf_reduce_launch(b, gf ? f->gf_poly : 0u, d_prf_bytes, subset_stride_bytes, nsub, count, chunk_bytes, d_values,
+                             value_stride_bytes, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1017,14 +1087,32 @@ struct Workspace {
     cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
     void* d_in[kSlots] = {nullptr, nullptr, nullptr};
     void* d_out[kSlots] = {nullptr, nullptr, nullptr};
-    size_t in_cap = 0, out_cap = 0;
+    void* d_tmp[kSlots] = {nullptr, nullptr, nullptr};   // intermediate values (PRSS with a general PRF bound)
+    size_t in_cap = 0, out_cap = 0, tmp_cap = 0;
     std::mutex mu;
 };
 
 Workspace g_ws[16];
 std::mutex g_ws_mu;
 
-// creates the per-device workspace (streams) on first use; the caller then locks w->mu and calls reserve()
+// Restores the calling thread's current CUDA device when it goes out of scope: the host-buffer entry points select
+// `device` for their copies and launches and must not leave a multi-GPU caller (one torch process driving several
+// GPUs, or rank r on cuda:r calling with the default device 0) on another device than it was on.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// creates the per-device workspace (streams) on first use; the caller then locks w->mu and calls reserve().
+// Callers hold a DeviceGuard: the current device is switched here and restored when the entry point returns.
 int acquire_workspace(int device, Workspace** out) {
     if (device < 0 || device >= 16) return fail(MPYC_B200_EINVAL, "device ordinal out of range");
     CU(cudaSetDevice(device));
@@ -1063,6 +1151,18 @@ int reserve(Workspace& w, size_t in_bytes, size_t out_bytes) {
     return MPYC_B200_OK;
 }
 
+int reserve_tmp(Workspace& w, size_t bytes) {
+    if (bytes <= w.tmp_cap) return MPYC_B200_OK;
+    for (int s = 0; s < kSlots; s++) {
+        if (w.d_tmp[s]) cudaFree(w.d_tmp[s]);
+        w.d_tmp[s] = nullptr;
+    }
+    w.tmp_cap = 0;
+    for (int s = 0; s < kSlots; s++) CU(cudaMalloc(&w.d_tmp[s], bytes));
+    w.tmp_cap = bytes;
+    return MPYC_B200_OK;
+}
+
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // elements per pipeline chunk: ~32 MiB of traffic per chunk, multiple of 16 elements
@@ -1084,6 +1184,7 @@ MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * (size_t)(t + 1 + m));
+    DeviceGuard guard;
     Workspace* w;
     int rc = acquire_workspace(device, &w);
     if (rc) return rc;
@@ -1120,6 +1221,7 @@ MPYC_API int mpyc_b200_shamir_split_generate_host(const mpyc_b200_field* f, cons
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * (size_t)(1 + m));
+    DeviceGuard guard;
     Workspace* w;
     int rc = acquire_workspace(device, &w);
     if (rc) return rc;
@@ -1154,6 +1256,7 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * (size_t)(k + width));
+    DeviceGuard guard;
     Workspace* w;
     int rc = acquire_workspace(device, &w);
     if (rc) return rc;
@@ -1187,6 +1290,7 @@ MPYC_API int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const voi
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t ch = chunk_elems(n, eb * 3);
+    DeviceGuard guard;
     Workspace* w;
     int rc = acquire_workspace(device, &w);
     if (rc) return rc;
@@ -1299,13 +1403,18 @@ int reserve_pinned(PinnedStage& p, size_t bytes) {
 
 }   // namespace
 
-MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
-                                   size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
-                                   const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads) {
+// general: PRF bound given by `general` (two kernels per chunk: k_prf_reduce, then K4 on the reduced values);
+// otherwise bound_bits as in mpyc_b200_prss_combine
+static int prss_host_impl(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                          size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const BoundSpec* general,
+                          const uint64_t* h_coef, const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads) {
     if (!f || !h_keys || key_bytes < 0 || (uci_bytes && !h_uci) || !h_coef || !h_weights || nsub < 1 || d < 1 || chunk_bytes < 1 ||
         (n && !h_out))
         return fail(MPYC_B200_EINVAL, "prss_host: bad arguments");
     if (n == 0) return MPYC_B200_OK;
+    const bool gf = f->kind == MPYC_B200_KIND_GF256;
+    const int vbytes = general ? (gf ? 1 : 8 * general->LB) : 0;      // width of a reduced value (general bounds)
+    if (general && (chunk_bytes > 8 * (general->LB + 2))) return fail(MPYC_B200_EINVAL, "prss_host: chunk too wide for this bound");
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t per_elem = (size_t)d * chunk_bytes;
@@ -1315,6 +1424,7 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
     ce = std::min(ce, round_up(n, 256));
     const size_t cstride = round_up(ce * per_elem, 16);               // bytes per subset per chunk
     const size_t nchunks = (n + ce - 1) / ce;
+    DeviceGuard guard;
     Workspace* w;
     int rc = acquire_workspace(device, &w);
     if (rc) return rc;
@@ -1323,9 +1433,15 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
     if (rc) return rc;
     rc = reserve_pinned(g_pin[device], cstride * nsub);
     if (rc) return rc;
+    const size_t vstride = general ? round_up(ce * (size_t)d * vbytes, 16) : 0;   // reduced values per subset per chunk
+    if (general) {
+        rc = reserve_tmp(*w, vstride * nsub);
+        if (rc) return rc;
+    }
     PinnedStage& pin = g_pin[device];
     PrssTable tab;
-    rc = prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, w->streams[0], tab);
+    rc = general ? prss_prepare(f, nsub, d, vbytes, 0, h_coef, h_weights, w->streams[0], tab)
+                 : prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, w->streams[0], tab);
     if (rc) return rc;
 
     // one sponge per key subset (thresha.py:257: shake_128(key + s)); subsets are dealt round-robin to the workers
@@ -1385,7 +1501,13 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
         cudaError_t e = cudaMemcpyAsync(w->d_in[s], pin.h[s], cstride * nsub, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaEventRecord(copied[s], st);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "prss_host H2D"));
-        rc = prss_launch(f, tab, (const uint8_t*)w->d_in[s], cstride, nsub, d, chunk_bytes, bound_bits, w->d_out[s], cn, st);
+        if (general) {
+            rc = prf_reduce_launch(*general, gf ? f->gf_poly : 0u, (const uint8_t*)w->d_in[s], cstride, nsub, cn * (size_t)d, chunk_bytes,
+                                   w->d_tmp[s], vstride, st);
+            if (rc == MPYC_B200_OK) rc = prss_launch(f, tab, (const uint8_t*)w->d_tmp[s], vstride, nsub, d, vbytes, 0, w->d_out[s], cn, st);
+        } else {
+            rc = prss_launch(f, tab, (const uint8_t*)w->d_in[s], cstride, nsub, d, chunk_bytes, bound_bits, w->d_out[s], cn, st);
+        }
         if (rc) return cleanup(rc);
         e = cudaMemcpyAsync((char*)h_out + c * ce * eb, w->d_out[s], cn * eb, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return cleanup(cuda_fail(e, "prss_host D2H"));
@@ -1402,4 +1524,22 @@ MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys
     workers.clear();
     for (int s = 0; s < kSlots; s++) cudaEventDestroy(copied[s]);
     return MPYC_B200_OK;
+}
+
+MPYC_API int mpyc_b200_prss_host(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                                   size_t uci_bytes, int nsub, int d, int chunk_bytes, int bound_bits, const uint64_t* h_coef,
+                                   const uint64_t* h_weights, void* h_out, size_t n, int device, int max_threads) {
+    return prss_host_impl(f, h_keys, key_bytes, h_uci, uci_bytes, nsub, d, chunk_bytes, bound_bits, nullptr, h_coef, h_weights, h_out, n,
+                          device, max_threads);
+}
+
+MPYC_API int mpyc_b200_prss_host_bound(const mpyc_b200_field* f, const uint8_t* h_keys, int key_bytes, const uint8_t* h_uci,
+                                         size_t uci_bytes, int nsub, int d, int chunk_bytes, const uint64_t* h_bound, int bound_nlimbs,
+                                         const uint64_t* h_coef, const uint64_t* h_weights, void* h_out, size_t n, int device,
+                                         int max_threads) {
+    BoundSpec b;
+    int rc = bound_spec(h_bound, bound_nlimbs, b);
+    if (rc) return rc;
+    return prss_host_impl(f, h_keys, key_bytes, h_uci, uci_bytes, nsub, d, chunk_bytes, 0, &b, h_coef, h_weights, h_out, n, device,
+                          max_threads);
 }

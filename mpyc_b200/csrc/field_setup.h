@@ -65,6 +65,19 @@ static inline void montgomery_constants(FieldParams& fp) {
     for (int i = 0; i < LL; i++) fp.r2[i] = get64(x, i);
 }
 
+// Barrett constants only, for a modulus that need not be prime or odd: the `bound` of a PRF (prf_reduce.cuh).
+// bound: nlimbs limbs (top limb non-zero), bound >= 3 and not a power of two (then 2^64 <= floor(2^(k+64)/bound) < 2^65).
+static inline void bound_params_init(const uint64_t* bound, int nlimbs, FieldParams* out) {
+    FieldParams& fp = *out;
+    memset(&fp, 0, sizeof fp);
+    for (int i = 0; i < nlimbs; i++) fp.p[i] = bound[i];
+    fp.L = nlimbs;
+    fp.k = bit_length(fp.p, nlimbs);
+    fp.s = fp.k & 63;
+    fp.kind = KIND_GENERIC;
+    barrett_constants(fp);
+}
+
 // modulus: nlimbs (already stripped of leading zero limbs, 1..4) limbs of an odd p >= 3
 static inline void field_params_init(const uint64_t* modulus, int nlimbs, FieldParams* out) {
     FieldParams& fp = *out;

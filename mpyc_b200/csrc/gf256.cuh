@@ -299,16 +299,18 @@ k_gf_recombine(unsigned poly, GfTab lam, GfRows rows, int k, int width, unsigned
     }
 }
 
-// ---- PRSS: out[h] = sum_S coef[S] * sum_j bytes[S][h*d+j] * w[j]; tab = coef | w ---------------------
+// ---- PRSS: out[h] = sum_S coef[S] * sum_j (bytes[S][h*d+j] & mask) * w[j]; tab = coef | w --------------
+// mask = 2^b - 1 for a PRF bound 2^b <= 256 (thresha.py:261: chunk % bound; b = 1 for runtime.random_bits on
+// characteristic-2 fields, runtime.py:4138,4218), 0xFF for the full byte.
 static __global__ void __launch_bounds__(GF_THREADS)
 k_gf_prss(unsigned poly, GfTab tab, const unsigned char* __restrict__ bytes, size_t subset_stride, int nsub, int d,
-          unsigned char* __restrict__ out, size_t n) {
+          unsigned mask, unsigned char* __restrict__ out, size_t n) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
         unsigned acc = 0;
         for (int S = 0; S < nsub; S++) {
             unsigned y = 0;
-            for (int j = 0; j < d; j++) y ^= gf_mul1(bytes[(size_t)S * subset_stride + h * d + j], tab.v[nsub + j], poly);
+            for (int j = 0; j < d; j++) y ^= gf_mul1(bytes[(size_t)S * subset_stride + h * d + j] & mask, tab.v[nsub + j], poly);
             acc ^= gf_mul1(y, tab.v[S], poly);
         }
         out[h] = (unsigned char)acc;
@@ -449,11 +451,11 @@ static inline cudaError_t gf256_recombine(unsigned poly, const unsigned char* co
     GF_LAUNCH(k_gf_recombine, (n + 7) / 8, st, poly, tab, r, k, width, out, ostride, n);
 }
 static inline cudaError_t gf256_prss(unsigned poly, const unsigned char* bytes, size_t subset_stride, int nsub, int d,
-                                     const unsigned char* coef_w, unsigned char* out, size_t n, cudaStream_t st) {
+                                     const unsigned char* coef_w, unsigned mask, unsigned char* out, size_t n, cudaStream_t st) {
     if ((size_t)nsub + d > GF_MAX_TAB) return cudaErrorNotSupported;
     GfTab tab;
     for (int i = 0; i < nsub + d; i++) tab.v[i] = coef_w[i];
-    GF_LAUNCH(k_gf_prss, n, st, poly, tab, bytes, subset_stride, nsub, d, out, n);
+    GF_LAUNCH(k_gf_prss, n, st, poly, tab, bytes, subset_stride, nsub, d, mask, out, n);
 }
 static inline cudaError_t gf256_fill(unsigned long long base, unsigned char* out, size_t n, cudaStream_t st) {
     GF_LAUNCH(k_gf_fill, n, st, base, out, n);

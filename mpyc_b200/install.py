@@ -8,7 +8,9 @@ PRSS helpers run on the GPU while runtime.py, sectypes.py and the demos stay byt
 Fields the engine does not cover (GF(2), GF(p^n) with n > 1, binary fields other than GF(2^8), primes
 wider than 256 bits) are NOT intercepted: for those the wrapper hands the call to the reference's own
 function, exactly as if install() had not been called (strict=True raises UnsupportedFieldError
-instead).  For covered fields there is no fallback of any kind: without a CUDA device the call raises.
+instead).  The same holds per call: an argument outside the kernels' range on a covered field (e.g. a PRF bound
+above 2^256) goes to the reference's function.  That hand-over is the only one: a covered call never runs on a CPU
+restatement of the kernels, and without a CUDA device it raises.
 """
 import functools
 
@@ -50,7 +52,16 @@ def _wrap(name, ours, theirs, strict, min_size=0):
                 n = _batch_size(name, args)
                 if n is not None and n < min_size:
                     return theirs(field, *args, **kwargs)     # the reference's own code, as without install()
-            return ours(field, *args, **kwargs)
+            if strict:
+                return ours(field, *args, **kwargs)
+            try:
+                return ours(field, *args, **kwargs)
+            except UnsupportedFieldError:
+                # coverage is decided per CALL, not per field: a covered field with an argument outside the kernels'
+                # range (a PRF bound above 2^256, more than 64 recombination points, a constant table beyond shared
+                # memory ...) is computed by the reference's own function, exactly as without install() -- never
+                # raise where the reference computes.  These functions are pure, so nothing is half-done.
+                return theirs(field, *args, **kwargs)
         if strict:
             raise UnsupportedFieldError(f'mpyc_b200 does not cover field {getattr(field, "__name__", field)}')
         return theirs(field, *args, **kwargs)

@@ -165,8 +165,21 @@ def _recombination_vector(field, xs, x_r):
     return list(_wrap_poly(field, ctx, lam)) if ctx.binary else lam
 
 
-def _recombine_limbs(ctx, xs, rows, pts):
+def _check_rows(ctx, rows):
+    """Every share row must hold the same number of elements in the field's limb layout: rows come from peers
+    (unpickled arrays or ShareRows whose length the sender chose), and the C ABI copies n elements from each
+    (the reference raises from field.array(shares) on ragged input, thresha.py:128)."""
     n = rows[0].shape[0]
+    want = (n,) if ctx.binary else (n, ctx.nlimbs)
+    dt = np.uint8 if ctx.binary else np.uint64
+    for r in rows:
+        if r.shape != want or r.dtype != dt:
+            raise ValueError(f'recombine: share rows must all have {n} elements (got shapes {[tuple(x.shape) for x in rows]})')
+    return n
+
+
+def _recombine_limbs(ctx, xs, rows, pts):
+    n = _check_rows(ctx, rows)
     width = len(pts)
     shape = (width, n) if ctx.binary else (width, n, ctx.nlimbs)
     out = np.empty(shape, dtype=np.uint8 if ctx.binary else np.uint64)
@@ -185,8 +198,8 @@ def np_recombine(field, points, x_rs=0):
     pts = [x_rs] if single else x_rs
     rows = [sh.limbs if isinstance(sh, ShareRow) and sh.ctx is ctx else codec.ints_to_limbs(_values_of(field, sh), ctx)
             for sh in shares]
+    n = _check_rows(ctx, rows)
     out = _recombine_limbs(ctx, xs, rows, pts)
-    n = rows[0].shape[0]
     vals = np.empty((len(pts), n), dtype=object)
     for r in range(len(pts)):
         vals[r] = _wrap_poly(field, ctx, codec.limbs_to_ints(out[r], ctx))
@@ -203,6 +216,7 @@ def recombine(field, points, x_rs=0):
     pts = [x_rs] if single else x_rs
     is_elt = len(shares[0]) > 0 and isinstance(shares[0][0], field)
     rows = [codec.ints_to_limbs(_values_of(field, sh), ctx) for sh in shares]
+    _check_rows(ctx, rows)
     out = _recombine_limbs(ctx, xs, rows, pts)
     sums = []
     for r in range(len(pts)):
@@ -265,12 +279,20 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
     width = subsets[0][1].byte_length
     if any(f.max != bound for _, f in subsets):
         raise ValueError('all PRFs of one call must share their bound')
+    # Which form of the bound the engine sees (thresha.py:257-261 computes chunk % bound for ANY bound):
+    #   the field order, or 2^b <= order  -> folded into the combine kernel (bound_bits)
+    #   anything else up to 2^256         -> reduced by its own kernel first (mpyc_b200_prss_host_bound):
+    #       runtime._convert's (1 << (k+l)) // comb(m,t) + 1 and a source field's order used on a smaller
+    #       target field (runtime.py:735-739,758-760)
+    general = None
     if bound == field.order:
         bound_bits = 0
-    elif bound & (bound - 1) == 0 and bound <= field.order:
+    elif bound >= 2 and bound & (bound - 1) == 0 and bound <= field.order:
         bound_bits = bound.bit_length() - 1
+    elif 2 <= bound <= 1 << 256:
+        bound_bits, general = 0, bound
     else:
-        raise _cabi.UnsupportedFieldError('PRF bound must be the field order or a power of two below it')
+        raise _cabi.UnsupportedFieldError('PRF bounds above 2^256 are not covered by mpyc_b200')
     nl = max(ctx.nlimbs, 1)
     if n == 0:
         return np.zeros((0,) if ctx.binary else (0, nl), dtype=np.uint8 if ctx.binary else np.uint64)
@@ -289,15 +311,22 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
     wl = []
     for w in weights:
         wl.extend(_cabi.int_to_limbs(int(w), nl))
-    return _prss_device(ctx, keys, bytes(uci), d, width, bound_bits if not ctx.binary else 0, coef, wl, n)
+    return _prss_device(ctx, keys, bytes(uci), d, width, bound_bits, coef, wl, n, general)
 
 
-def _prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n):
-    """The device round trip of a PRSS call (mpyc_b200_prss_host): keys / uci / constants in, limb array (n, L) out."""
+def _prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n, general=None):
+    """The device round trip of a PRSS call (mpyc_b200_prss_host[_bound]): keys / uci / constants in, limb array
+    (n, L) out.  general: the PRF bound as an int when it is neither the field order nor 2^bound_bits <= order."""
     nl = max(ctx.nlimbs, 1)
     out = np.empty((n,) if ctx.binary else (n, nl), dtype=np.uint8 if ctx.binary else np.uint64)
-    check(lib.mpyc_b200_prss_host(ctx.handle, b''.join(keys), len(keys[0]), uci, len(uci), len(keys), d, width, bound_bits,
-                                  _cabi.u64_array(coef), _cabi.u64_array(weights), _ptr(out), n, device, prss_threads))
+    if general is None:
+        check(lib.mpyc_b200_prss_host(ctx.handle, b''.join(keys), len(keys[0]), uci, len(uci), len(keys), d, width, bound_bits,
+                                      _cabi.u64_array(coef), _cabi.u64_array(weights), _ptr(out), n, device, prss_threads))
+    else:
+        bl = _cabi.int_to_limbs(general, 5)
+        check(lib.mpyc_b200_prss_host_bound(ctx.handle, b''.join(keys), len(keys[0]), uci, len(uci), len(keys), d, width,
+                                            _cabi.u64_array(bl), 5, _cabi.u64_array(coef), _cabi.u64_array(weights), _ptr(out),
+                                            n, device, prss_threads))
     return out
 
 

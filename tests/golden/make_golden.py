@@ -142,6 +142,46 @@ def prss_cases(primes):
     return out
 
 
+def prss_bound_cases():
+    """PRSS with PRF bounds other than the field order (thresha.py:257-261 reduces chunk % bound for ANY bound):
+    prfs(2) of runtime.random_bits / np_random_bits (runtime.py:4138,4218), also on GF(2^8); the power-of-two bounds of
+    _randoms / _np_randoms (runtime.py:4050-4056,4090-4098); runtime._convert's (1 << (k+l)) // comb(m,t) + 1 and the
+    source field's order applied to another (smaller or larger) target field (runtime.py:735-739,758-760)."""
+    from itertools import combinations
+    from math import comb
+    f283 = gfpx.GFpX(2)(283)
+    fields = [('gf', 283, finfields.GF(f283)), ('p', P61, finfields.GF(P61)), ('p', P64G, finfields.GF(P64G)),
+              ('p', P128, finfields.GF(P128)), ('p', 101, finfields.GF(101))]
+    out = []
+    for kind, mod, F in fields:
+        for (m, t) in ((1, 0), (3, 1), (5, 2)):
+            bounds = [2, 16, 256, 1 << 10, 1000, (1 << 62) // comb(m, t) + 1, P61, P69, 1 << 70, P256, (1 << 200) + 12345, 1 << 256]
+            if kind == 'p':
+                bounds.append(mod - 1)
+            for bound in bounds:
+                n = 5
+                uci = (777 + m).to_bytes(8, 'little')
+                keys = {}
+                for S in combinations(range(m), m - t):
+                    keys[S] = bytes((sum(S) * 29 + j * 5 + len(S) + 1) & 0xFF for j in range(16))
+                per_party = []
+                for i in range(m):
+                    prfs = {S: thresha.PRF(k, bound) for S, k in keys.items() if i in S}
+                    a_np = thresha.np_pseudorandom_share(F, m, i, prfs, uci, n)
+                    a_li = thresha.pseudorandom_share(F, m, i, prfs, uci, n)
+                    z_np = thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n) if t else None
+                    z_li = thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)
+                    per_party.append({'i': i,
+                                      'share_np': hx([int(v) for v in a_np.value]),
+                                      'share_list': hx([int(x.value) for x in a_li]),
+                                      'zero_np': hx([int(v) for v in z_np.value]) if z_np is not None else None,
+                                      'zero_list': hx([int(x.value) for x in z_li])})
+                out.append({'field': kind, 'modulus': hex(mod), 'bound': hex(bound), 'm': m, 't': t, 'n': n,
+                            'uci': uci.hex(), 'keys': {','.join(map(str, S)): k.hex() for S, k in keys.items()},
+                            'parties': per_party})
+    return out
+
+
 def ff_cases(primes):
     out = []
     for p in primes:
@@ -217,6 +257,7 @@ def main():
         'prss.json': {'meta': meta, 'cases': prss_cases([P61, P69, P128, P256, P64G])},
         'finfields.json': {'meta': meta, 'cases': ff_cases(primes_all)},
         'gf256.json': {'meta': meta, **gf256_cases()},
+        'prss_bounds.json': {'meta': meta, 'cases': prss_bound_cases()},
     }
     for name, obj in files.items():
         with open(os.path.join(HERE, name), 'w') as fh:

@@ -1,0 +1,101 @@
+"""Launcher: run an UNMODIFIED MPyC program (a demo of the reference, or any script using `from mpyc.runtime import mpc`)
+with the B200 engine installed behind mpyc.thresha / mpyc.finfields.
+
+    python tests/run_installed.py <program.py> [program and MPyC flags, e.g. -M3 -1]
+
+MPyC's multi-party mode re-executes sys.argv for the other parties (mpyc/runtime.py:5156-5189), so every party goes
+through this launcher and gets the same installation.  Configuration travels in the environment so that it reaches
+the child parties too:
+    MPYC_REFERENCE           path of the reference checkout / install (prepended to sys.path); default: importable mpyc
+    MPYC_B200_HARNESS        comma list: install (default), oracle (no GPU: device round trips answered by
+                             tests/oracle_device.py -- test infrastructure), limb_wire, finfields, ops, strict, off
+    MPYC_B200_MIN_SIZE       install(min_size=...)
+    MPYC_B200_FORCE_PRIME    hex prime: SecInt/SecFxp types are built over this prime (BASELINE configs[4]: 256-bit)
+    MPYC_B200_CALL_LOG       file: one line per engine call (name, field bits, elements), appended per process
+"""
+import os
+import runpy
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+sys.dont_write_bytecode = True
+ref = os.environ.get('MPYC_REFERENCE')
+if ref:
+    sys.path.insert(0, ref)
+
+
+def main():
+    if len(sys.argv) < 2:
+        raise SystemExit(__doc__)
+    flags = set(filter(None, os.environ.get('MPYC_B200_HARNESS', 'install').split(',')))
+    from mpyc.runtime import mpc   # noqa: F401  (parses sys.argv, spawns the other parties with this launcher)
+    import mpyc.thresha
+    import mpyc.finfields
+    if 'off' not in flags:
+        import mpyc_b200.install as inst
+        if 'oracle' in flags:
+            import oracle_device
+            oracle_device.patch()
+            if hasattr(oracle_device, 'patch_finfields'):
+                oracle_device.patch_finfields()
+        kwargs = {'strict': 'strict' in flags, 'limb_wire': 'limb_wire' in flags,
+                  'min_size': int(os.environ.get('MPYC_B200_MIN_SIZE', '0'))}
+        if 'finfields' in flags or 'ops' in flags:
+            kwargs['finfields_module'] = mpyc.finfields
+        if 'ops' in flags:
+            kwargs['operators'] = True
+        inst.install(mpyc.thresha, **kwargs)
+        log = os.environ.get('MPYC_B200_CALL_LOG')
+        if log:
+            _log_calls(mpyc.thresha, log)
+    prime = os.environ.get('MPYC_B200_FORCE_PRIME')
+    if prime:
+        _force_prime(mpc, int(prime, 16))
+    program = sys.argv[1]
+    sys.argv = [program] + sys.argv[2:]
+    runpy.run_path(program, run_name='__main__')
+
+
+def _force_prime(mpc, p):
+    """SecInt / SecFxp factories accept p= (mpyc/sectypes.py:685-718); the demos do not pass it."""
+    for name in ('SecInt', 'SecFxp'):
+        orig = getattr(mpc, name)
+
+        def factory(*args, _orig=orig, **kwargs):
+            kwargs.setdefault('p', p)
+            return _orig(*args, **kwargs)
+        setattr(mpc, name, factory)
+
+
+def _log_calls(module, path):
+    import functools
+    names = ('random_split', 'recombine', 'np_random_split', 'np_recombine', 'pseudorandom_share',
+             'pseudorandom_share_zero', 'np_pseudorandom_share', 'np_pseudorandom_share_0')
+    fh = open(path, 'a')
+
+    def wrap(name, fn):
+        @functools.wraps(fn)
+        def call(field, *args, **kwargs):
+            try:
+                if 'split' in name:
+                    n = len(args[0])
+                elif 'recombine' in name:
+                    n = len(args[0][0][1])
+                else:
+                    n = int(args[-1])
+            except Exception:   # noqa: BLE001
+                n = -1
+            fh.write(f'{os.getpid()} {name} {getattr(field, "order", 0).bit_length()} {n}\n')
+            fh.flush()
+            return fn(field, *args, **kwargs)
+        return call
+    for name in names:
+        setattr(module, name, wrap(name, getattr(module, name)))
+
+
+if __name__ == '__main__':
+    main()

@@ -131,11 +131,13 @@ def oracle_prss(monkeypatch):
     import ctypes
     from mpyc_b200 import _cabi
 
-    def prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n):
-        assert not ctx.binary
-        p, L = ctx.modulus, ctx.nlimbs
+    def prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n, general=None):
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        L = max(ctx.nlimbs, 1)
         cs = [_cabi.limbs_to_int(coef[i * L:(i + 1) * L]) for i in range(len(keys))]
         ws = [_cabi.limbs_to_int(weights[j * L:(j + 1) * L]) for j in range(d)]
+        full = 256 if ctx.binary else ctx.modulus
+        bound = general if general is not None else (1 << bound_bits if bound_bits else full)
         acc = [0] * n
         for key, c in zip(keys, cs):
             raw = ctypes.create_string_buffer(n * d * width)
@@ -144,11 +146,10 @@ def oracle_prss(monkeypatch):
             for h in range(n):
                 y = 0
                 for j in range(d):
-                    v = int.from_bytes(raw[(h * d + j) * width:(h * d + j + 1) * width], 'little')
-                    v = v % p if bound_bits == 0 else v & ((1 << bound_bits) - 1)
-                    y += v * ws[j]
-                acc[h] += c * y
-        return codec.ints_to_limbs([a % p for a in acc], ctx)
+                    v = int.from_bytes(raw[(h * d + j) * width:(h * d + j + 1) * width], 'little') % bound
+                    y = F.add(y, F.mul(v, ws[j]))
+                acc[h] = F.add(acc[h], F.mul(c, y))
+        return codec.ints_to_limbs([F.red(a) for a in acc], ctx)
 
     monkeypatch.setattr(thresha, '_prss_device', prss_device)
 
@@ -170,6 +171,64 @@ def test_golden_prss_through_the_adapter(case, oracle_prss):
         assert [x.value for x in thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)] == unhex(party['zero_list'])
         if t:
             assert thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n).value.tolist() == unhex(party['zero_np'])
+
+
+BOUNDS = load('prss_bounds.json')
+
+
+@pytest.mark.parametrize('case', BOUNDS['cases'],
+                         ids=lambda c: f"{c['field']}{int(c['modulus'], 16).bit_length()}_b{int(c['bound'], 16).bit_length()}_m{c['m']}t{c['t']}")
+def test_golden_prss_any_bound_through_the_adapter(case, oracle_prss):
+    """Host side of PRSS with PRF bounds other than the field order (which form of the bound reaches the device call,
+    chunk width, GF(2^8) polynomial wrapping), on the reference-generated cases."""
+    mod, bound, m, t, n = int(case['modulus'], 16), int(case['bound'], 16), case['m'], case['t'], case['n']
+    F = fakefield.make_gf256(mod) if case['field'] == 'gf' else fakefield.make_prime_field(mod)
+    uci = bytes.fromhex(case['uci'])
+    keys = {tuple(int(x) for x in k.split(',')): bytes.fromhex(v) for k, v in case['keys'].items()}
+    for party in case['parties']:
+        i = party['i']
+        prfs = {S: thresha.PRF(k, bound) for S, k in keys.items() if i in S}
+        a_np = thresha.np_pseudorandom_share(F, m, i, prfs, uci, n)
+        assert isinstance(a_np, F.array) and [int(v) for v in a_np.value] == unhex(party['share_np'])
+        assert [int(x.value) for x in thresha.pseudorandom_share(F, m, i, prfs, uci, n)] == unhex(party['share_list'])
+        assert [int(x.value) for x in thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)] == unhex(party['zero_list'])
+        if t:
+            assert [int(v) for v in thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n).value] == unhex(party['zero_np'])
+
+
+def test_bound_form_handed_to_the_device(monkeypatch):
+    """bound == order -> bound_bits 0; 2^b <= order -> bound_bits b (also GF(2^8): the bug of round 1 was dropping it);
+    anything else up to 2^256 -> general; wider -> UnsupportedFieldError (install() then defers to the reference)."""
+    import mpyc_b200
+    seen = []
+
+    def spy(ctx, keys, uci, d, width, bound_bits, coef, weights, n, general=None):
+        seen.append((width, bound_bits, general))
+        return np.zeros((n,) if ctx.binary else (n, ctx.nlimbs), dtype=np.uint8 if ctx.binary else np.uint64)
+    monkeypatch.setattr(thresha, '_prss_device', spy)
+    G, P = fakefield.make_gf256(283), fakefield.make_prime_field(2**61 - 1)
+    key = bytes(16)
+    for F, bound, want in ((G, 256, (1, 0, None)), (G, 2, (1, 1, None)), (G, 16, (1, 4, None)), (G, 1 << 9, (2, 0, 1 << 9)),
+                           (G, 1000, (2 + 16, 0, 1000)), (P, 2**61 - 1, (8 + 16, 0, None)), (P, 2, (1, 1, None)),
+                           (P, 1 << 60, (8, 60, None)), (P, 1 << 61, (8, 0, 1 << 61)), (P, 12345, (2 + 16, 0, 12345)),
+                           (P, 2**69 - 93, (9 + 16, 0, 2**69 - 93)), (P, 1 << 256, (32, 0, 1 << 256))):
+        thresha.np_pseudorandom_share(F, 1, 0, {(0,): thresha.PRF(key, bound)}, b'u', 3)
+        assert seen[-1] == want, (bound, seen[-1])
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):
+        thresha.np_pseudorandom_share(P, 1, 0, {(0,): thresha.PRF(key, (1 << 256) + 1)}, b'u', 3)
+
+
+def test_ragged_share_rows_are_rejected(oracle_device):
+    """A share row of another length (a buggy or malicious peer) must raise before the C ABI copies n elements from it."""
+    F = fakefield.make_prime_field(2**61 - 1)
+    good, short = np.array([1, 2, 3, 4], dtype=object), np.array([1, 2, 3], dtype=object)
+    with pytest.raises(ValueError):
+        thresha.np_recombine(F, [(1, good), (2, short)])
+    with pytest.raises(ValueError):
+        thresha.recombine(F, [(1, [1, 2, 3, 4]), (2, [1, 2, 3])])
+    G = fakefield.make_gf256(283)
+    with pytest.raises(ValueError):
+        thresha.np_recombine(G, [(1, np.array([fakefield.Poly(1)] * 4, dtype=object)), (2, np.array([fakefield.Poly(1)] * 5, dtype=object))])
 
 
 def test_small_integer_form_of_the_prss_coefficients():

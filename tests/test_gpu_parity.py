@@ -135,6 +135,48 @@ def test_golden_prss_dropin(case):
             assert z_np.value.tolist() == unhex(party['zero_np'])
 
 
+BOUNDS = load('prss_bounds.json')
+
+
+@pytest.mark.parametrize('case', BOUNDS['cases'],
+                         ids=lambda c: f"{c['field']}{int(c['modulus'], 16).bit_length()}_b{int(c['bound'], 16).bit_length()}_m{c['m']}t{c['t']}")
+def test_golden_prss_any_bound(case):
+    """Reference-generated PRSS cases whose PRF bound is NOT the field order: 2 (random bits, also on GF(2^8):
+    runtime.py:4138,4218), other powers of two below and above the order, runtime._convert's
+    (1 << (k+l)) // comb(m,t) + 1 and foreign field orders (runtime.py:735-739,758-760)."""
+    mod, bound, m, t, n = int(case['modulus'], 16), int(case['bound'], 16), case['m'], case['t'], case['n']
+    F = fakefield.make_gf256(mod) if case['field'] == 'gf' else fakefield.make_prime_field(mod)
+    uci = bytes.fromhex(case['uci'])
+    keys = {tuple(int(x) for x in k.split(',')): bytes.fromhex(v) for k, v in case['keys'].items()}
+    for party in case['parties']:
+        i = party['i']
+        prfs = {S: thresha.PRF(k, bound) for S, k in keys.items() if i in S}
+        a_np = thresha.np_pseudorandom_share(F, m, i, prfs, uci, n)
+        assert isinstance(a_np, F.array) and [int(v) for v in a_np.value] == unhex(party['share_np'])
+        assert [int(x.value) for x in thresha.pseudorandom_share(F, m, i, prfs, uci, n)] == unhex(party['share_list'])
+        assert [int(x.value) for x in thresha.pseudorandom_share_zero(F, m, i, prfs, uci, n)] == unhex(party['zero_list'])
+        if t:
+            assert [int(v) for v in thresha.np_pseudorandom_share_0(F, m, i, prfs, uci, n).value] == unhex(party['zero_np'])
+
+
+@pytest.mark.parametrize('mod,binary', [(283, True), (P61, False), (P128, False), (GEN['192'], False), (P256, False)])
+def test_prss_general_bound_pipeline_sizes(mod, binary):
+    """General-bound PRSS at multi-chunk sizes (reduction kernel + combine kernel per pipeline chunk) against the oracle."""
+    from itertools import combinations
+    from math import comb
+    F = fakefield.make_gf256(mod) if binary else fakefield.make_prime_field(mod)
+    Fo = orc.field_of(mod, binary=binary)
+    m, t, i = 5, 2, 1
+    for bound, n in (((1 << 62) // comb(m, t) + 1, 20011), (P256, 3001), ((1 << 77) + 1, 777), (1 << 90, 1500), (3, 40000)):
+        keys = {S: bytes([(sum(S) * 11 + 3) & 0xFF] * 16) for S in combinations(range(m), m - t) if i in S}
+        prfs = {S: thresha.PRF(k, bound) for S, k in keys.items()}
+        got = [int(v) for v in thresha.np_pseudorandom_share(F, m, i, prfs, b'uci-gen!', n).value]
+        assert got == orc.prss_share(Fo, m, i, {S: orc.prf_values(k, bound, b'uci-gen!', n) for S, k in keys.items()}, n)
+        n0 = max(n // 7, 1)
+        got0 = [int(v) for v in thresha.np_pseudorandom_share_0(F, m, i, prfs, b'uci-gen0', n0).value]
+        assert got0 == orc.prss_share_zero_np_order(Fo, m, i, {S: orc.prf_values(k, bound, b'uci-gen0', n0 * t) for S, k in keys.items()}, n0)
+
+
 def test_prss_power_of_two_bound_and_prf():
     """bounded PRSS (runtime.py:4076: bound = power of two) and the PRF class itself."""
     key = bytes.fromhex(load('prf.json')['key'])

@@ -155,3 +155,29 @@ def test_numpy_object_variants_agree_with_scalar_oracle():
     assert got.tolist() == ref
     rec = orc.np_recombine(p, (1, 2, 3), got[:3])
     assert rec.tolist() == s
+
+
+BOUNDS = load('prss_bounds.json')
+
+
+def _bound_id(c):
+    return f"{c['field']}{int(c['modulus'], 16).bit_length()}_b{int(c['bound'], 16).bit_length()}_m{c['m']}t{c['t']}"
+
+
+@pytest.mark.parametrize('case', BOUNDS['cases'], ids=_bound_id)
+def test_prss_with_any_prf_bound(case):
+    """PRF bounds other than the field order (thresha.py:257-261 reduces chunk % bound for any bound; callers
+    runtime.py:735-739,758-760,4138,4218), prime fields and GF(2^8), reference-generated."""
+    mod, bound, m, t, n = int(case['modulus'], 16), int(case['bound'], 16), case['m'], case['t'], case['n']
+    F = orc.field_of(mod, binary=case['field'] == 'gf')
+    uci = bytes.fromhex(case['uci'])
+    keys = {tuple(int(x) for x in k.split(',')): bytes.fromhex(v) for k, v in case['keys'].items()}
+    for party in case['parties']:
+        i = party['i']
+        mine = {S: k for S, k in keys.items() if i in S}
+        prl = {S: orc.prf_values(k, bound, uci, n) for S, k in mine.items()}
+        assert orc.prss_share(F, m, i, prl, n) == unhex(party['share_np']) == unhex(party['share_list'])
+        prl0 = {S: orc.prf_values(k, bound, uci, n * t) for S, k in mine.items()}
+        assert orc.prss_share_zero_list_order(F, m, i, prl0, n) == unhex(party['zero_list'])
+        if t:
+            assert orc.prss_share_zero_np_order(F, m, i, prl0, n) == unhex(party['zero_np'])
