@@ -102,15 +102,77 @@ def _install_finfields(finfields_module, min_size):
 
 
 _saved_ff = {}
+_saved_ops = {}
+
+
+def _install_operators(finfields_module, min_size):
+    """FiniteFieldArray.__init__ and + - * neg @ (mpyc/finfields.py:717-725,1056-1146): limb-backed operands, and plain
+    object arrays of at least `min_size` elements, are combined by the K1 / K1c kernels (mpyc_b200.resident); everything
+    else -- scalars with small arrays, broadcasting, uncovered fields -- runs the reference's own method unchanged."""
+    from mpyc_b200 import _cabi, resident
+    resident.min_size = int(min_size)
+    cls = finfields_module.FiniteFieldArray
+    names = ('__init__', '__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__neg__', '__matmul__',
+             '__rmatmul__')
+    orig = {name: cls.__dict__[name] for name in names}
+    _saved_ops.update({'cls': cls, 'module': finfields_module, **orig})
+    MISS = resident._MISS
+    value_property = resident.make_value_property(finfields_module)
+    slot_set = resident._slot.__set__
+
+    def __init__(self, value, check=True, copy=False):
+        lv = resident.as_limb_value(value)
+        if lv is not None:
+            slot_set(self, lv)         # canonical residues by construction: nothing to check, nothing to copy
+            return
+        if type(value) is resident.LimbValue:
+            value = value._ints
+        orig['__init__'](self, value, check=check, copy=copy)
+
+    def make(op, name, reflected=False):
+        def method(self, other):
+            r = resident.binop(self, other, op, reflected)
+            return orig[name](self, other) if r is MISS else r
+        method.__name__ = name
+        method.__doc__ = orig[name].__doc__
+        return method
+
+    def __neg__(self):
+        r = resident.negate(self)
+        return orig['__neg__'](self) if r is MISS else r
+
+    def __matmul__(self, other):
+        r = resident.matmul(self, other)
+        return orig['__matmul__'](self, other) if r is MISS else r
+
+    def __rmatmul__(self, other):
+        r = resident.matmul(self, other, reflected=True)
+        return orig['__rmatmul__'](self, other) if r is MISS else r
+
+    cls.value = value_property
+    cls.__init__ = __init__
+    cls.__add__ = make(_cabi.OP_ADD, '__add__')
+    cls.__radd__ = make(_cabi.OP_ADD, '__radd__')
+    cls.__sub__ = make(_cabi.OP_SUB, '__sub__')
+    cls.__rsub__ = make(_cabi.OP_SUB, '__rsub__', reflected=True)
+    cls.__mul__ = make(_cabi.OP_MUL, '__mul__')
+    cls.__rmul__ = make(_cabi.OP_MUL, '__rmul__')
+    cls.__neg__ = __neg__
+    cls.__matmul__ = __matmul__
+    cls.__rmatmul__ = __rmatmul__
 
 
 def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256,
-            limb_wire=False, min_size=0):
+            limb_wire=False, min_size=0, operators=False, operators_min_size=1024, resident=False):
     """Patch `mpyc.thresha` (or the module passed in); with finfields_module also the batched
     inverse/pow/sqrt/is_sqr of PrimeFieldArray.  limb_wire=True: shares travel between parties as limb
     buffers (mpyc_b200.wire; every party must run mpyc_b200).  min_size > 0: calls on fewer elements are left to
     the reference's own functions -- a GPU round trip costs ~35 us per call, which the reference beats below a few
     dozen 64-bit elements; the default 0 sends every covered call to the GPU.
+    operators=True: FiniteFieldArray's + - * neg @ (finfields.py:1056-1146) run on the K1 / K1c kernels for operands
+    of at least operators_min_size elements (mpyc_b200.resident).  resident=True (implies operators and limb_wire):
+    recombined / pseudorandom shares stay limb-backed in HBM between protocol steps; Python ints are created only
+    where a value is actually looked at (input, output, raw-value arithmetic).
     Returns the list of patched names."""
     if thresha_module is None:
         import mpyc.thresha as thresha_module
@@ -118,8 +180,15 @@ def install(thresha_module=None, strict=False, device=0, finfields_module=None, 
         uninstall()
     if finfields_module is not None:
         _install_finfields(finfields_module, finfields_min_size)
+    if operators or resident:
+        if finfields_module is None:
+            import mpyc.finfields as finfields_module
+        _install_operators(finfields_module, operators_min_size)
+    from mpyc_b200 import resident as res
+    res.resident = bool(resident)
+    res.backend.device = device
     engine.device = device
-    engine.limb_wire = bool(limb_wire)
+    engine.limb_wire = bool(limb_wire or resident)
     for name in _NAMES:
         theirs = getattr(thresha_module, name)
         _saved[name] = (thresha_module, theirs)
@@ -138,6 +207,14 @@ def uninstall():
         setattr(module, name, theirs)
     _saved.clear()
     engine.limb_wire = False
+    from mpyc_b200 import resident as res
+    res.resident = False
+    if _saved_ops:
+        cls = _saved_ops.pop('cls')
+        res.restore_value_slot(_saved_ops.pop('module'))
+        for name, member in _saved_ops.items():
+            setattr(cls, name, member)
+        _saved_ops.clear()
     if _saved_ff:
         cls = _saved_ff.pop('cls')
         for name, member in _saved_ff.items():

@@ -32,6 +32,7 @@ from mpyc_b200 import _cabi, codec
 from mpyc_b200._cabi import lib, check
 from mpyc_b200.field import context_of_field
 from mpyc_b200.wire import ShareRow, ShareRows
+from mpyc_b200 import resident as _res
 
 __all__ = ['random_split', 'recombine', 'pseudorandom_share', 'pseudorandom_share_zero',
            'np_random_split', 'np_recombine', 'np_pseudorandom_share', 'np_pseudorandom_share_0', 'PRF']
@@ -54,8 +55,8 @@ def _values_of(field, s):
         s = s.value
     if isinstance(s, np.ndarray):
         return s.reshape(-1)
-    if isinstance(s, ShareRow):
-        return s.__array__()
+    if isinstance(s, (ShareRow, _res.LimbValue)):
+        return s.__array__().reshape(-1)
     s = list(s)
     if s and isinstance(s[0], field):
         s = [a.value for a in s]
@@ -118,18 +119,39 @@ def _use_generate(ctx, t, n):
     return coefficient_source is None and not ctx.binary and 1 <= t <= 4 and n > 0
 
 
+def _limb_secrets(field, s):
+    """(store, n) when the secrets arrive limb-backed (a resident field array, its .value, or a ShareRow)."""
+    arr_t = getattr(field, 'array', None)
+    if arr_t is not None and isinstance(s, arr_t):
+        s = _res.raw_value(s)
+    lv = _res.as_limb_value(s)
+    if lv is None or lv.ctx is not context_of_field(field):
+        return None
+    return lv.store, lv.size
+
+
 def np_random_split(field, s, t, m):
     """Split each secret in s into m Shamir shares of degree t (0 <= t < m): object ndarray (m, n)."""
     ctx = context_of_field(field)
-    s = _values_of(field, s)
-    n = len(s)
-    sec = codec.ints_to_limbs(s, ctx)
-    if _use_generate(ctx, t, n):
-        shares = _split_generate(ctx, sec, t, m)
+    limb = _limb_secrets(field, s)
+    if limb is not None:
+        # resident secrets (mpyc_b200.resident): no Python ints on the way in
+        store, n = limb
+        C = None
+        if coefficient_source is not None or ctx.binary or not 1 <= t <= 4:
+            C = _draw(ctx, field.order, t * n).reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
+        shares = _split_store(ctx, store, C, t, m) if n else np.zeros((m, 0) if ctx.binary else (m, 0, ctx.nlimbs),
+                                                                  dtype=np.uint8 if ctx.binary else np.uint64)
     else:
-        C = _draw(ctx, field.order, t * n)
-        C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
-        shares = _split_limbs(ctx, sec, C, t, m)
+        s = _values_of(field, s)
+        n = len(s)
+        sec = codec.ints_to_limbs(s, ctx)
+        if _use_generate(ctx, t, n):
+            shares = _split_generate(ctx, sec, t, m)
+        else:
+            C = _draw(ctx, field.order, t * n)
+            C = C.reshape((t, n) if ctx.binary else (t, n, ctx.nlimbs))
+            shares = _split_limbs(ctx, sec, C, t, m)
     if limb_wire:
         return ShareRows(ctx, shares, type(field.modulus) if ctx.binary else None)
     if not ctx.binary:
@@ -138,6 +160,13 @@ def np_random_split(field, s, t, m):
     for i in range(m):
         out[i] = _wrap_poly(field, ctx, codec.limbs_to_ints(shares[i], ctx))
     return out
+
+
+def _split_store(ctx, store, C, t, m):
+    """Device round trip of a split whose secrets are already limbs (possibly in HBM): host limb rows (m, n, L)."""
+    if isinstance(store, np.ndarray):      # host limbs (they came over the wire): the pipelined host-buffer entry points
+        return _split_generate(ctx, store, t, m) if C is None else _split_limbs(ctx, store, C, t, m)
+    return _res.backend.split(ctx, store, t, m, C)
 
 
 def random_split(field, s, t, m):
@@ -169,12 +198,17 @@ def _check_rows(ctx, rows):
     """Every share row must hold the same number of elements in the field's limb layout: rows come from peers
     (unpickled arrays or ShareRows whose length the sender chose), and the C ABI copies n elements from each
     (the reference raises from field.array(shares) on ragged input, thresha.py:128)."""
-    n = rows[0].shape[0]
+    n = len(rows[0])
     want = (n,) if ctx.binary else (n, ctx.nlimbs)
     dt = np.uint8 if ctx.binary else np.uint64
     for r in rows:
-        if r.shape != want or r.dtype != dt:
-            raise ValueError(f'recombine: share rows must all have {n} elements (got shapes {[tuple(x.shape) for x in rows]})')
+        if isinstance(r, np.ndarray):
+            ok = r.shape == want and r.dtype == dt
+        else:                                     # a store in HBM (mpyc_b200.device.DeviceArray of this field)
+            ok = len(r) == n and getattr(r, 'ctx', None) is ctx
+        if not ok:
+            raise ValueError(f'recombine: share rows must all have {n} elements of this field '
+                             f'(got lengths {[len(x) for x in rows]})')
     return n
 
 
@@ -190,20 +224,40 @@ def _recombine_limbs(ctx, xs, rows, pts):
     return out
 
 
+def _row_limbs(field, ctx, sh):
+    """One share row as limbs: ShareRow / resident values as they are, anything else through the codec."""
+    if isinstance(sh, ShareRow) and sh.ctx is ctx and sh._ints is None:
+        return sh.limbs
+    arr_t = getattr(field, 'array', None)
+    lv = _res.as_limb_value(_res.raw_value(sh) if arr_t is not None and isinstance(sh, arr_t) else sh)
+    if lv is not None and lv.ctx is ctx:
+        return lv.store
+    return codec.ints_to_limbs(_values_of(field, sh), ctx)
+
+
 def np_recombine(field, points, x_rs=0):
     """Recombine shares given by points [(x_i, share_i), ...] at x_rs: field.array (n,) or (width, n)."""
     ctx = context_of_field(field)
     xs, shares = zip(*points)
     single = not isinstance(x_rs, list)
     pts = [x_rs] if single else x_rs
-    rows = [sh.limbs if isinstance(sh, ShareRow) and sh.ctx is ctx else codec.ints_to_limbs(_values_of(field, sh), ctx)
-            for sh in shares]
+    rows = [_row_limbs(field, ctx, sh) for sh in shares]
     n = _check_rows(ctx, rows)
+    if _res.resident and single and n:
+        # the result stays limb-backed (in HBM): the next local operation / split consumes it without Python ints
+        store = _recombine_store(ctx, xs, rows, pts)
+        return field.array(_res.LimbValue(ctx, store, (n,), type(field.modulus) if ctx.binary else None), check=False)
+    rows = [_res.backend.to_host(ctx, r) for r in rows]
     out = _recombine_limbs(ctx, xs, rows, pts)
     vals = np.empty((len(pts), n), dtype=object)
     for r in range(len(pts)):
         vals[r] = _wrap_poly(field, ctx, codec.limbs_to_ints(out[r], ctx))
     return field.array(vals[0] if single else vals, check=False)
+
+
+def _recombine_store(ctx, xs, rows, pts):
+    """Device round trip of a resident recombination: one store (DeviceArray) for the single point pts[0]."""
+    return _res.backend.recombine(ctx, xs, rows, pts)[0]
 
 
 def recombine(field, points, x_rs=0):
@@ -285,7 +339,7 @@ def _prss(field, m, i, prfs, uci, n, d, weights):
     #       runtime._convert's (1 << (k+l)) // comb(m,t) + 1 and a source field's order used on a smaller
     #       target field (runtime.py:735-739,758-760)
     general = None
-    if bound == field.order:
+    if bound == field.order or bound == 1:      # bound 1: width 0, all values 0 (handled below)
         bound_bits = 0
     elif bound >= 2 and bound & (bound - 1) == 0 and bound <= field.order:
         bound_bits = bound.bit_length() - 1
@@ -330,11 +384,18 @@ def _prss_device(ctx, keys, uci, d, width, bound_bits, coef, weights, n, general
     return out
 
 
+def _array_from_limbs(field, ctx, limbs):
+    """field.array over a host limb array: limb-backed in resident mode, else unpacked to Python ints."""
+    if _res.resident and len(limbs):
+        return field.array(_res.LimbValue(ctx, limbs, (len(limbs),), type(field.modulus) if ctx.binary else None), check=False)
+    return field.array(_wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx)), check=False)
+
+
 def np_pseudorandom_share(field, m, i, prfs, uci, n):
     """Pseudorandom Shamir shares of n random values for party i: field.array (n,)."""
     ctx = context_of_field(field)
     limbs = _prss(field, m, i, prfs, uci, n, 1, [1])
-    return field.array(_wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx)), check=False)
+    return _array_from_limbs(field, ctx, limbs)
 
 
 def pseudorandom_share(field, m, i, prfs, uci, n):
@@ -375,7 +436,7 @@ def np_pseudorandom_share_0(field, m, i, prfs, uci, n):
     limbs = _prss(field, m, i, prfs, uci, n, d, _powers(field, ctx, i, d, horner=False)) if d else None
     if limbs is None:
         return field.array(np.zeros(n, dtype=object), check=False)
-    return field.array(_wrap_poly(field, ctx, codec.limbs_to_ints(limbs, ctx)), check=False)
+    return _array_from_limbs(field, ctx, limbs)
 
 
 def pseudorandom_share_zero(field, m, i, prfs, uci, n):

@@ -81,3 +81,106 @@ def patch(monkeypatch=None):
             monkeypatch.setattr(thresha, name, fn)
         else:
             setattr(thresha, name, fn)
+
+
+# ---- mpyc_b200.resident backend on host limb arrays (oracle arithmetic) -------------------------------------------
+
+class OracleBackend:
+    """Stand-in for resident.CudaBackend: stores are host limb arrays, the arithmetic is the oracle's."""
+
+    device = 0
+
+    def _ints(self, ctx, a):
+        return [int(v) for v in codec.limbs_to_ints(np.ascontiguousarray(a), ctx)]
+
+    def to_store(self, ctx, limbs):
+        return limbs
+
+    def to_host(self, ctx, store):
+        return store
+
+    def _op(self, ctx, op, x, y):
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        f = {_cabi.OP_ADD: F.add, _cabi.OP_SUB: F.sub, _cabi.OP_MUL: F.mul}[op]
+        return codec.ints_to_limbs([F.red(f(a, b)) for a, b in zip(x, y)], ctx)
+
+    def binop(self, ctx, op, a, b):
+        return self._op(ctx, op, self._ints(ctx, a), self._ints(ctx, b))
+
+    def binop_scalar(self, ctx, op, a, scalar):
+        x = self._ints(ctx, a)
+        s = int(scalar) if ctx.binary else int(scalar) % ctx.modulus
+        return self._op(ctx, op, x, [s] * len(x))
+
+    def neg(self, ctx, a):
+        x = self._ints(ctx, a)
+        return self._op(ctx, _cabi.OP_SUB, [0] * len(x), x)
+
+    def matmul(self, ctx, a, b, r, k, c):
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        A, B = self._ints(ctx, a), self._ints(ctx, b)
+        out = []
+        for i in range(r):
+            for j in range(c):
+                acc = 0
+                for l in range(k):
+                    acc = F.add(acc, F.mul(A[i * k + l], B[l * c + j]))
+                out.append(F.red(acc))
+        return codec.ints_to_limbs(out, ctx)
+
+    def split(self, ctx, sec, t, m, coeffs=None):
+        return split_generate(ctx, sec, t, m) if coeffs is None else split_limbs(ctx, sec, coeffs, t, m)
+
+    def recombine(self, ctx, xs, rows, pts):
+        out = recombine_limbs(ctx, xs, rows, pts)
+        return [out[r] for r in range(len(pts))]
+
+
+def patch_resident(monkeypatch=None):
+    from mpyc_b200 import resident
+    if monkeypatch is not None:
+        monkeypatch.setattr(resident, 'backend', OracleBackend())
+    else:
+        resident.backend = OracleBackend()
+
+
+def patch_finfields(monkeypatch=None):
+    """mpyc_b200.finfields' batched inverse / pow / sqrt / is_sqr / matmul answered by the oracle."""
+    from mpyc_b200 import finfields as ff
+
+    def shaped(fn):
+        def call(cls, a, *args, **kwargs):
+            a = np.asarray(a, dtype=object)
+            p = cls.field.modulus
+            vals = fn(p, [int(v) for v in a.reshape(-1)], *args, **kwargs)
+            out = np.empty(len(vals), dtype=object)
+            out[:] = vals
+            return out.reshape(a.shape)
+        return call
+
+    def recip(p, vals):
+        if any(v % p == 0 for v in vals):
+            raise ZeroDivisionError('inverse of zero')
+        return orc.ff_inv(p, vals)
+
+    def power(cls, a, b, _fallback=None):
+        if not isinstance(b, (int, np.integer)):
+            return _fallback(a, b)
+        return shaped(lambda p, vals: orc.ff_pow(p, vals, int(b)))(cls, a)
+
+    def sqrt(cls, a, INV=False, _fallback=None):
+        if cls.field.modulus & 3 != 3:
+            return _fallback(a, INV=INV)
+        return shaped(lambda p, vals: orc.ff_sqrt(p, vals, INV=INV))(cls, a)
+
+    def is_sqr(cls, a):
+        a = np.asarray(a, dtype=object)
+        p = cls.field.modulus
+        return np.array(orc.ff_is_sqr(p, [int(v) for v in a.reshape(-1)]), dtype=bool).reshape(a.shape)
+
+    repl = {'reciprocal': shaped(recip), 'power': power, 'sqrt': sqrt, 'is_sqr': is_sqr}
+    for name, fn in repl.items():
+        if monkeypatch is not None:
+            monkeypatch.setattr(ff, name, fn)
+        else:
+            setattr(ff, name, fn)

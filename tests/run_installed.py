@@ -8,7 +8,9 @@ through this launcher and gets the same installation.  Configuration travels in 
 the child parties too:
     MPYC_REFERENCE           path of the reference checkout / install (prepended to sys.path); default: importable mpyc
     MPYC_B200_HARNESS        comma list: install (default), oracle (no GPU: device round trips answered by
-                             tests/oracle_device.py -- test infrastructure), limb_wire, finfields, ops, strict, off
+                             tests/oracle_device.py -- test infrastructure), limb_wire, finfields, ops (operator hooks),
+                             resident (limb-resident arrays), spread (party i on GPU i mod #GPUs), strict, off
+    MPYC_B200_OPS_MIN_SIZE   install(operators_min_size=...)
     MPYC_B200_MIN_SIZE       install(min_size=...)
     MPYC_B200_FORCE_PRIME    hex prime: SecInt/SecFxp types are built over this prime (BASELINE configs[4]: 256-bit)
     MPYC_B200_CALL_LOG       file: one line per engine call (name, field bits, elements), appended per process
@@ -40,14 +42,26 @@ def main():
         if 'oracle' in flags:
             import oracle_device
             oracle_device.patch()
-            if hasattr(oracle_device, 'patch_finfields'):
-                oracle_device.patch_finfields()
+            oracle_device.patch_finfields()
+            oracle_device.patch_resident()
         kwargs = {'strict': 'strict' in flags, 'limb_wire': 'limb_wire' in flags,
                   'min_size': int(os.environ.get('MPYC_B200_MIN_SIZE', '0'))}
         if 'finfields' in flags or 'ops' in flags:
             kwargs['finfields_module'] = mpyc.finfields
-        if 'ops' in flags:
+        if 'ops' in flags or 'resident' in flags:
             kwargs['operators'] = True
+            kwargs['operators_min_size'] = int(os.environ.get('MPYC_B200_OPS_MIN_SIZE', '1024'))
+        if 'resident' in flags:
+            kwargs['resident'] = True
+            kwargs['finfields_module'] = mpyc.finfields
+        if os.environ.get('MPYC_B200_DEVICE'):
+            kwargs['device'] = int(os.environ['MPYC_B200_DEVICE'])
+        elif 'spread' in flags:           # co-located parties: party i on GPU i mod #GPUs
+            import mpyc_b200
+            import ctypes
+            cnt = ctypes.c_int(0)
+            mpyc_b200._cabi.lib.mpyc_b200_device_count(ctypes.byref(cnt))
+            kwargs['device'] = mpc.pid % max(cnt.value, 1)
         inst.install(mpyc.thresha, **kwargs)
         log = os.environ.get('MPYC_B200_CALL_LOG')
         if log:

@@ -6,8 +6,9 @@ Two device modes, same tests:
     by tests/oracle_device.py, everything above them is the product code.  Needs the reference checkout
     (/root/reference or $MPYC_REFERENCE); skipped where it is absent.
   * 'cuda'    (-m gpu): the real kernels through the C ABI.  On the GPU box the reference is importable from
-    baseline/_ref (the `mpyc` package only: pip install --target of the unmodified checkout, git-ignored) or
-    $MPYC_REFERENCE; tests that need the reference's tests/ or demos/ directories skip when only the package is there.
+    baseline/_ref (pip install --target of the unmodified checkout plus its demos/ and tests/ under _checkout/,
+    git-ignored, written by tools/install_reference.sh) or $MPYC_REFERENCE; tests that need the reference's tests/
+    or demos/ directories skip when only the package is there.
 
 Every run goes through tests/run_installed.py in a child process (MPyC parses sys.argv and builds its runtime at import;
 -M3 re-executes the command line for the other parties, mpyc/runtime.py:5156-5189).
@@ -37,8 +38,21 @@ def _find_reference():
 
 
 REF = _find_reference()
-HAVE_TESTS = bool(REF) and os.path.isdir(os.path.join(REF, 'tests'))
-HAVE_DEMOS = bool(REF) and os.path.isfile(os.path.join(REF, 'demos', 'np_aes.py'))
+
+
+def _checkout_dir(name):
+    """The reference's tests/ or demos/ directory: in the checkout, or next to a package-only install
+    (baseline/_ref/_checkout, written by tools/install_reference.sh)."""
+    for base in (REF, os.path.join(REF or '', '_checkout')):
+        if base and os.path.isdir(os.path.join(base, name)):
+            return os.path.join(base, name)
+    return None
+
+
+TESTS_DIR = _checkout_dir('tests')
+DEMOS_DIR = _checkout_dir('demos')
+HAVE_TESTS = TESTS_DIR is not None
+HAVE_DEMOS = DEMOS_DIR is not None and os.path.isfile(os.path.join(DEMOS_DIR, 'np_aes.py'))
 _ports = itertools.count(13000 + (os.getpid() % 400) * 40, 8)
 
 
@@ -75,26 +89,35 @@ def run(mode, program, args=(), flags=('install',), cwd=None, timeout=900, parti
     return r.stdout
 
 
-@pytest.mark.parametrize('flags', [('install',), ('install', 'limb_wire'), ('install', 'ops')], ids=lambda f: '+'.join(f))
-@pytest.mark.parametrize('name', ['test_thresha', 'test_finfields', 'test_runtime'])
+EVERYTHING = {'MPYC_B200_OPS_MIN_SIZE': '1'}    # every array operator call goes through the hooks, whatever its size
+
+
+@pytest.mark.parametrize('flags', [('install',), ('install', 'limb_wire'), ('install', 'ops'), ('install', 'resident')],
+                         ids=lambda f: '+'.join(f))
+@pytest.mark.parametrize('name', ['test_thresha', 'test_finfields', 'test_runtime', 'test_sectypes', 'test_secpols',
+                                  'test_statistics'])
 def test_reference_unittests_under_install(mode, name, flags):
-    """The reference's own unit tests, all green with the engine behind mpyc.thresha (and, with 'ops', behind the
-    FiniteFieldArray operators and batched inverse/pow/sqrt)."""
+    """The reference's own unit tests, all green with the engine behind mpyc.thresha (and, with 'ops' / 'resident', behind
+    the FiniteFieldArray operators, the batched inverse/pow/sqrt and the limb-resident `.value`, with the size
+    threshold at 1 so that every operator call takes the hooked path)."""
     if not HAVE_TESTS:
         pytest.skip('reference tests/ directory not available (package-only reference)')
-    out = run(mode, os.path.join(HERE, 'ref_unittest.py'), [os.path.join(REF, 'tests', name + '.py')], flags)
+    if name in ('test_sectypes', 'test_secpols', 'test_statistics') and flags != ('install', 'resident'):
+        pytest.skip('the wider suites run once, in the most invasive configuration')
+    out = run(mode, os.path.join(HERE, 'ref_unittest.py'), [os.path.join(TESTS_DIR, name + '.py')], flags,
+              env_extra=EVERYTHING)
     assert 'failures=0 errors=0' in out, out[-2000:]
     if name == 'test_runtime':
         assert 'REFTESTS run=20 ' in out
 
 
-@pytest.mark.parametrize('flags', [('install',), ('install', 'limb_wire', 'ops')], ids=lambda f: '+'.join(f))
+@pytest.mark.parametrize('flags', [('install',), ('install', 'resident')], ids=lambda f: '+'.join(f))
 @pytest.mark.parametrize('parties', [1, 3])
 def test_np_aes_fips197(mode, parties, flags):
     """BASELINE configs[3]: demos/np_aes.py unchanged; AES-128 of the FIPS-197 example block."""
     if not HAVE_DEMOS:
         pytest.skip('reference demos/ not available (package-only reference)')
-    out = run(mode, 'np_aes.py', ['-1'], flags, cwd=os.path.join(REF, 'demos'), parties=parties)
+    out = run(mode, 'np_aes.py', ['-1'], flags, cwd=DEMOS_DIR, parties=parties, env_extra=EVERYTHING)
     assert f'Ciphertext:  {FIPS197}' in out, out
 
 
@@ -104,20 +127,37 @@ def test_np_cnnmnist_logits_identical(mode, parties):
     without the engine."""
     if not HAVE_DEMOS:
         pytest.skip('reference demos/ not available (package-only reference)')
-    cwd = os.path.join(REF, 'demos')
+    cwd = DEMOS_DIR
     want = run(mode, 'np_cnnmnist.py', ['1', '0'], ('off',), cwd=cwd, parties=parties)
-    got = run(mode, 'np_cnnmnist.py', ['1', '0'], ('install', 'ops'), cwd=cwd, parties=parties)
+    got = run(mode, 'np_cnnmnist.py', ['1', '0'], ('install', 'resident'), cwd=cwd, parties=parties,
+              env_extra={'MPYC_B200_OPS_MIN_SIZE': '64'})
     tail = lambda s: s[s.index('Image #0'):]   # noqa: E731
     assert 'with label 7: 7 predicted' in got
     assert tail(got) == tail(want)
 
 
-@pytest.mark.parametrize('flags', [('install',), ('install', 'limb_wire', 'ops')], ids=lambda f: '+'.join(f))
+@pytest.mark.parametrize('flags', [('install',), ('install', 'resident')], ids=lambda f: '+'.join(f))
 @pytest.mark.parametrize('parties', [1, 3])
 def test_secure_ops_program_installed_equals_reference(mode, parties, flags):
     """tests/programs/secure_ops.py (input, output, multiply, matmul, comparisons, random bits, fixed-point truncation,
     convert, GF(2^8) inversion, field division): opened results identical with and without the engine."""
     want = run(mode, PROGRAM, ['48'], ('off',), parties=parties)
-    got = run(mode, PROGRAM, ['48'], flags, parties=parties)
+    got = run(mode, PROGRAM, ['48'], flags, parties=parties, env_extra=EVERYTHING)
     assert 'field division' in got
     assert got == want
+
+
+@pytest.mark.parametrize('parties', [1, 3])
+def test_resident_chain_creates_no_python_ints_between_input_and_output(mode, parties):
+    """input -> a*b -> _reshare -> (a*b)*a -> _reshare -> output over a 128-bit prime with install(resident=True):
+    the product code performs no int <-> limb conversion between the arrival of the input shares and output()
+    (and on a GPU box the C codec is not called at all in between); result equal to NumPy's."""
+    import json
+    out = run(mode, os.path.join(HERE, 'programs', 'resident_chain.py'), ['3000'], ('install', 'resident'), parties=parties)
+    rec = json.loads(out.strip().splitlines()[-1])
+    assert rec['ok'] and rec['n'] == 3000 and rec['parties'] == parties
+    between = rec['conversions_between']
+    assert between['materialised'] == 0 and between['packed'] == 0
+    assert between['limb_ops'] == 2                      # the two local products ran on limbs
+    if mode == 'cuda':
+        assert between['pycodec'] == 0                   # (the oracle stand-in converts internally; the kernels do not)
