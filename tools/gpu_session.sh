@@ -1,0 +1,60 @@
+#!/bin/bash
+# One parameterised GPU session script (replaces the per-session scripts of round 1).  Run through gpurun from the
+# repo root:   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh <step> [<step> ...]'
+# Every step writes its artefacts to gpurun_out/ (merged back into the build container); summaries that matter are
+# copied to profiles/ by hand afterwards.  Steps:
+#   tests        python -m pytest tests -m gpu            -> r02_pytest_gpu.log
+#   bench        the default bench line + the reference arm   -> r02_bench.json, r02_bench_reference.json
+#   chain        tests/programs/resident_chain.py, 3 parties, n = 10^6: off / install / resident   -> r02_chain.jsonl
+#   demos        np_aes / np_cnnmnist timings with and without the engine                          -> r02_demos.txt
+#   ncu_<cfg>    launch list + one --set full capture of the split/recombine kernels of a bench config
+#   sass         per-kernel SASS / ptxas summary (no GPU needed, also runs in the build container)
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+export PYTHONDONTWRITEBYTECODE=1
+REFDIR=$PWD/baseline/_ref
+launcher() { MPYC_REFERENCE=$REFDIR python tests/run_installed.py "$@"; }
+
+for step in "$@"; do
+  echo "=== step $step"
+  case $step in
+    tests)
+      python -m pytest tests -m gpu -q -x 2>&1 | tail -60 > $OUT/r02_pytest_gpu.log; tail -3 $OUT/r02_pytest_gpu.log ;;
+    bench)
+      python bench.py > $OUT/r02_bench.json 2> $OUT/r02_bench.err; tail -c 1500 $OUT/r02_bench.json
+      python bench.py --impl reference --steps 3 --warmup 1 > $OUT/r02_bench_reference.json 2>> $OUT/r02_bench.err; tail -c 600 $OUT/r02_bench_reference.json ;;
+    chain)
+      : > $OUT/r02_chain.jsonl
+      for n in 100000 1000000; do
+        for h in off install install,limb_wire install,resident; do
+          echo "# harness=$h n=$n" >> $OUT/r02_chain.jsonl
+          MPYC_B200_HARNESS=$h launcher tests/programs/resident_chain.py $n -M3 -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 1 >> $OUT/r02_chain.jsonl
+        done
+      done
+      cat $OUT/r02_chain.jsonl ;;
+    demos)
+      : > $OUT/r02_demos.txt
+      cd $REFDIR/_checkout/demos
+      for h in off install install,resident; do
+        for prog in "np_aes.py -1" "np_aes.py -1 -M3" "np_cnnmnist.py 1 0" "np_cnnmnist.py 1 0 -M3"; do
+          s=$(date +%s.%N)
+          MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h MPYC_REFERENCE=$REFDIR python $OLDPWD/tests/run_installed.py $prog -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 2 | tr '\n' ' ' >> $OLDPWD/$OUT/r02_demos.txt
+          e=$(date +%s.%N)
+          echo " | harness=$h prog=$prog wall=$(echo "$e - $s" | bc)" >> $OLDPWD/$OUT/r02_demos.txt
+        done
+      done
+      cd $OLDPWD; cat $OUT/r02_demos.txt ;;
+    ncu_*)
+      cfg=${step#ncu_}
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/r02_launches_$cfg.csv \
+          python bench.py --config $cfg --steps 2 --warmup 1 --no-cpu > $OUT/r02_ncu_$cfg.log 2>&1
+      for k in k_split k_recombine k_prss k_binop; do
+        ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o $OUT/r02_ncu_${cfg}_$k -f \
+            python bench.py --config $cfg --steps 1 --warmup 1 --no-cpu >> $OUT/r02_ncu_$cfg.log 2>&1 || true
+      done ;;
+    sass)
+      python tools/sass_summary.py > $OUT/r02_sass_summary.txt 2>&1; tail -5 $OUT/r02_sass_summary.txt ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
