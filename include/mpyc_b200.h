@@ -198,6 +198,13 @@ int mpyc_b200_prss_host_bound(const mpyc_b200_field* f, const uint8_t* h_keys, i
  * thresha.PRF (mpyc/thresha.py:257).  Host only; no GPU involved. */
 int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, size_t outlen);
 
+/* The XOF streams of one PRSS call: `count` sponges SHAKE128(key_i || suffix) (thresha.py:257: key_i of each key subset,
+ * suffix = the unique call identifier), each squeezed to outlen bytes at out + i * out_stride.  On hosts with AVX-512F the
+ * sponges advance eight at a time in lock step on one core (csrc/shake128_x8.h; *used_wide = 1), which is what a PRSS
+ * worker thread that owns several key subsets does inside mpyc_b200_prss_host.  Host only; no GPU involved. */
+int mpyc_b200_shake128_multi(const uint8_t* keys, int key_bytes, const uint8_t* suffix, size_t suffix_len, int count,
+                             uint8_t* out, size_t out_stride, size_t outlen, int* used_wide);
+
 /* Lets kernels launched on `device` load/store memory of `peer_device` (cudaDeviceEnablePeerAccess; idempotent).
  * Needed once per pair before mpyc_b200_shamir_split_generate_rows is given rows on another GPU. */
 int mpyc_b200_enable_peer_access(int device, int peer_device);

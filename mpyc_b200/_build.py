@@ -11,6 +11,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libmpyc_b200.so')
 SOURCES = ['api.cu', 'inst_L1.cu', 'inst_L2.cu', 'inst_L3.cu', 'inst_L4.cu']
+HOST_SOURCES = ['shake128_x8.cpp']   # host compiler only (AVX-512 through per-function target attributes)
 PUBLIC_HEADER = os.path.join('..', '..', 'include', 'mpyc_b200.h')
 
 
@@ -31,7 +32,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
-    for name in SOURCES + _headers():
+    for name in SOURCES + HOST_SOURCES + _headers():
         with open(os.path.join(CSRC, name), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -97,8 +98,17 @@ def build(force=False, verbose=False, defines=(), lib=None):
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout[-4000:], r.stderr[-8000:]))
         return obj, r.stderr
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    def compile_host(src):
+        obj = os.path.join(OBJ, src.replace('.cpp', '.o'))
+        r = subprocess.run(['g++', '-std=c++17', '-O3', '-fPIC', '-fvisibility=hidden', '-c', os.path.join(CSRC, src), '-o', obj],
+                           capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError('g++ failed for %s:\n%s' % (src, r.stderr[-4000:]))
+        return obj, r.stderr
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES) + len(HOST_SOURCES)) as ex:
+        host_jobs = [ex.submit(compile_host, src) for src in HOST_SOURCES]
+        results = list(ex.map(compile_one, SOURCES)) + [j.result() for j in host_jobs]
     objs = [o for o, _ in results]
     if verbose:
         with open(os.path.join(OBJ, 'ptxas.log'), 'w') as fh:

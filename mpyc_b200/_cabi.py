@@ -83,6 +83,7 @@ _SIGNATURES = {
     'mpyc_b200_peer_close': (c_int, [c_void_p]),
     'mpyc_b200_peer_free': (c_int, [c_void_p]),
     'mpyc_b200_shake128': (c_int, [c_char_p, c_size_t, c_void_p, c_size_t]),
+    'mpyc_b200_shake128_multi': (c_int, [c_char_p, c_int, c_char_p, c_size_t, c_int, c_void_p, c_size_t, c_size_t, POINTER(c_int)]),
     'mpyc_b200_fill_random': (c_int, [_field_p, c_void_p, c_size_t, c_uint64, c_uint64, c_void_p]),
     'mpyc_b200_count_mismatch': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     'mpyc_b200_shamir_split_host': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,

@@ -4,6 +4,7 @@
 // table preparation and caching, argument checking, and the chunked host-buffer pipelines.
 // Kernels live in kernels.cuh / gf256.cuh and are instantiated per limb count in inst_L*.cu.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,6 +26,7 @@
 #include "launch.h"
 #include "prf_reduce.cuh"
 #include "shake128.h"
+#include "shake128_x8.h"
 
 #define MPYC_API extern "C" __attribute__((visibility("default")))
 
@@ -278,6 +280,12 @@ static int get_table(mpyc_b200_field* f, const std::string& key, DevTable* out, 
     t.full = full;
     CU(cudaMalloc(&t.d, t.bytes));
     cudaError_t e = cudaMemcpy(t.d, host.data(), t.bytes, cudaMemcpyHostToDevice);
+    // cudaMemcpy from PAGEABLE host memory returns once the data sits in the driver's staging buffer -- the DMA into
+    // t.d may still be in flight -- and it runs on the legacy default stream, which the library's non-blocking
+    // streams do not order against: a kernel launched right after could stage a half-written table.  With the GPU to
+    // itself the DMA always won that race; with three MPyC parties time-slicing one GPU it lost it on the first use
+    // of a table (round 2: wrong reshare results in real -M3 runs).  Wait for the copy before publishing the table.
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         cudaFree(t.d);
         return cuda_fail(e, "table upload");
@@ -1092,7 +1100,11 @@ struct Workspace {
     std::mutex mu;
 };
 
-Workspace g_ws[16];
+// Two independent workspaces (streams + staging buffers + lock) per device: set 0 serves the split / elementwise / PRSS
+// entry points, set 1 mpyc_b200_shamir_recombine_host.  A caller that pipelines batches -- split of batch j+1 from one
+// thread while batch j is recombined from another -- keeps both PCIe directions busy at once: the split is
+// D2H-heavy (m rows out for 1 + t in), the recombination H2D-heavy (k rows in for one out).
+Workspace g_ws[16][2];
 std::mutex g_ws_mu;
 
 // Restores the calling thread's current CUDA device when it goes out of scope: the host-buffer entry points select
@@ -1113,10 +1125,10 @@ struct DeviceGuard {
 
 // creates the per-device workspace (streams) on first use; the caller then locks w->mu and calls reserve().
 // Callers hold a DeviceGuard: the current device is switched here and restored when the entry point returns.
-int acquire_workspace(int device, Workspace** out) {
+int acquire_workspace(int device, Workspace** out, int set = 0) {
     if (device < 0 || device >= 16) return fail(MPYC_B200_EINVAL, "device ordinal out of range");
     CU(cudaSetDevice(device));
-    Workspace& w = g_ws[device];
+    Workspace& w = g_ws[device][set];
     {
         std::lock_guard<std::mutex> g(g_ws_mu);
         if (w.device < 0) {
@@ -1258,7 +1270,7 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
     const size_t ch = chunk_elems(n, eb * (size_t)(k + width));
     DeviceGuard guard;
     Workspace* w;
-    int rc = acquire_workspace(device, &w);
+    int rc = acquire_workspace(device, &w, 1);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(w->mu);
     rc = reserve(*w, ch * eb * (size_t)k, ch * eb * (size_t)width);
@@ -1344,6 +1356,7 @@ MPYC_API int mpyc_b200_peer_alloc(size_t bytes, void** d_ptr, uint8_t handle[64]
     void* p = nullptr;
     CU(cudaMalloc(&p, bytes));
     cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the memset is asynchronous with respect to the host
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
@@ -1381,6 +1394,42 @@ MPYC_API int mpyc_b200_shake128(const uint8_t* in, size_t inlen, uint8_t* out, s
     return MPYC_B200_OK;
 }
 
+// count sponges SHAKE128(key_i || suffix), i < count, squeezed to outlen bytes each at out + i * out_stride: the XOF
+// streams of one PRSS call (thresha.py:257 with key_i per subset and suffix = uci).  Sponges are processed eight at a
+// time in the AVX-512 lock-step form when the host has it (*used_wide = 1), else one by one.  Host only.
+MPYC_API int mpyc_b200_shake128_multi(const uint8_t* keys, int key_bytes, const uint8_t* suffix, size_t suffix_len, int count,
+                                        uint8_t* out, size_t out_stride, size_t outlen, int* used_wide) {
+    if (count < 0 || key_bytes < 0 || (count && key_bytes && !keys) || (suffix_len && !suffix) || (count && outlen && !out))
+        return fail(MPYC_B200_EINVAL, "shake128_multi: bad arguments");
+    const bool wide = mpyc_shake::x8_available();
+    if (used_wide) *used_wide = wide ? 1 : 0;
+    for (int b = 0; b < count;) {
+        const int take = (wide && count - b >= 2) ? std::min(count - b, 8) : 1;
+        if (take >= 2) {
+            mpyc_shake::Shake128x8 g;
+            g.reset(take);
+            const uint8_t* kp[8] = {};
+            const uint8_t* sp[8] = {};
+            uint8_t* op[8] = {};
+            for (int q = 0; q < take; q++) {
+                kp[q] = keys + (size_t)(b + q) * key_bytes;
+                sp[q] = suffix;
+                op[q] = out + (size_t)(b + q) * out_stride;
+            }
+            g.absorb(kp, (size_t)key_bytes);
+            g.absorb(sp, suffix_len);
+            g.squeeze(op, outlen);
+        } else {
+            mpyc_shake::Shake128 x;
+            x.absorb(keys + (size_t)b * key_bytes, (size_t)key_bytes);
+            x.absorb(suffix, suffix_len);
+            x.squeeze(out + (size_t)b * out_stride, outlen);
+        }
+        b += take;
+    }
+    return MPYC_B200_OK;
+}
+
 namespace {
 
 struct PinnedStage {   // pinned host staging for the PRF byte streams, one buffer per pipeline slot, per device
@@ -1402,6 +1451,28 @@ int reserve_pinned(PinnedStage& p, size_t bytes) {
 }
 
 }   // namespace
+
+// CPUs this process may actually use: hardware threads, capped by the scheduler affinity mask and by a cgroup CPU quota
+// (a container that sees 128 hardware threads but is limited to 8 CPUs' worth of time -- the round-1 GPU box)
+static int usable_cpus() {
+    int n = (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        const int a = CPU_COUNT(&set);
+        if (a >= 1 && a < n) n = a;
+    }
+    if (FILE* fh = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char quota[32] = "";
+        long period = 0;
+        if (fscanf(fh, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+            const long q = (atol(quota) + period - 1) / period;
+            if (q >= 1 && q < n) n = (int)q;
+        }
+        fclose(fh);
+    }
+    return n;
+}
 
 // general: PRF bound given by `general` (two kernels per chunk: k_prf_reduce, then K4 on the reduced values);
 // otherwise bound_bits as in mpyc_b200_prss_combine
@@ -1444,16 +1515,58 @@ static int prss_host_impl(const mpyc_b200_field* f, const uint8_t* h_keys, int k
                  : prss_prepare(f, nsub, d, chunk_bytes, bound_bits, h_coef, h_weights, w->streams[0], tab);
     if (rc) return rc;
 
-    // one sponge per key subset (thresha.py:257: shake_128(key + s)); subsets are dealt round-robin to the workers
-    std::vector<mpyc_shake::Shake128> sponge(nsub);
-    for (int S = 0; S < nsub; S++) {
-        sponge[S].absorb(h_keys + (size_t)S * key_bytes, (size_t)key_bytes);
-        sponge[S].absorb(h_uci, uci_bytes);
-    }
-    int hw = (int)std::thread::hardware_concurrency();
-    if (hw < 1) hw = 1;
+    // One sponge per key subset (thresha.py:257: shake_128(key + s)), dealt round-robin to the worker threads.  A worker
+    // that owns several sponges squeezes them in lock step, eight at a time, with the AVX-512 form (shake128_x8.h)
+    // when the host has it; a worker with a single sponge, or a host without AVX-512, uses the scalar sponge.
+    const int hw = usable_cpus();
     int nthreads = std::min(nsub, max_threads > 0 ? max_threads : hw);
     if ((size_t)nsub * n * per_elem < (64u << 10)) nthreads = 1;       // tiny calls: thread start-up costs more than it saves
+    struct Unit {
+        std::vector<int> subs;             // key subsets of this unit (1 for scalar, 2..8 for the wide form)
+        mpyc_shake::Shake128 scalar;
+        mpyc_shake::Shake128x8 wide;
+        bool is_wide = false;
+    };
+    const bool use_x8 = mpyc_shake::x8_available();
+    std::vector<std::vector<Unit>> units(nthreads);
+    for (int wk = 0; wk < nthreads; wk++) {
+        std::vector<int> mine;
+        for (int S = wk; S < nsub; S += nthreads) mine.push_back(S);
+        for (size_t b = 0; b < mine.size();) {
+            const size_t left = mine.size() - b;
+            const size_t take = (use_x8 && left >= 2) ? std::min<size_t>(left, 8) : 1;
+            units[wk].emplace_back();
+            Unit& u = units[wk].back();
+            u.subs.assign(mine.begin() + b, mine.begin() + b + take);
+            if (take >= 2) {
+                u.is_wide = true;
+                u.wide.reset((int)take);
+                const uint8_t* kp[8] = {};
+                const uint8_t* up[8] = {};
+                for (size_t q = 0; q < take; q++) {
+                    kp[q] = h_keys + (size_t)u.subs[q] * key_bytes;
+                    up[q] = h_uci;
+                }
+                u.wide.absorb(kp, (size_t)key_bytes);
+                u.wide.absorb(up, uci_bytes);
+            } else {
+                u.scalar.absorb(h_keys + (size_t)u.subs[0] * key_bytes, (size_t)key_bytes);
+                u.scalar.absorb(h_uci, uci_bytes);
+            }
+            b += take;
+        }
+    }
+    auto squeeze_worker = [&](int wk, uint8_t* base, size_t len) {
+        for (Unit& u : units[wk]) {
+            if (u.is_wide) {
+                uint8_t* outs[8] = {};
+                for (size_t q = 0; q < u.subs.size(); q++) outs[q] = base + (size_t)u.subs[q] * cstride;
+                u.wide.squeeze(outs, len);
+            } else {
+                u.scalar.squeeze(base + (size_t)u.subs[0] * cstride, len);
+            }
+        }
+    };
     std::vector<std::atomic<int>> produced(nchunks);
     for (auto& p : produced) p.store(0, std::memory_order_relaxed);
     std::atomic<size_t> consumed{0};                                  // chunks whose pinned slot may be overwritten
@@ -1465,8 +1578,7 @@ static int prss_host_impl(const mpyc_b200_field* f, const uint8_t* h_keys, int k
                 std::this_thread::sleep_for(std::chrono::microseconds(50));   // do not burn a core the sponges could use
             }
             const size_t cn = std::min(ce, n - c * ce);
-            uint8_t* base = (uint8_t*)pin.h[c % kSlots];
-            for (int S = worker; S < nsub; S += nthreads) sponge[S].squeeze(base + (size_t)S * cstride, cn * per_elem);
+            squeeze_worker(worker, (uint8_t*)pin.h[c % kSlots], cn * per_elem);
             produced[c].fetch_add(1, std::memory_order_release);
         }
     };
@@ -1493,8 +1605,7 @@ static int prss_host_impl(const mpyc_b200_field* f, const uint8_t* h_keys, int k
             if (c >= kSlots) {                                        // slot reuse: its H2D copy must have left the host buffer
                 if (cudaEventSynchronize(copied[s]) != cudaSuccess) return cleanup(cuda_fail(cudaGetLastError(), "prss_host event"));
             }
-            uint8_t* base = (uint8_t*)pin.h[s];
-            for (int S = 0; S < nsub; S++) sponge[S].squeeze(base + (size_t)S * cstride, cn * per_elem);
+            squeeze_worker(0, (uint8_t*)pin.h[s], cn * per_elem);
         } else {
             while (produced[c].load(std::memory_order_acquire) < nthreads) std::this_thread::sleep_for(std::chrono::microseconds(50));
         }

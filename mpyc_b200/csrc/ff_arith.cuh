@@ -58,7 +58,9 @@ struct FieldParams {
     u64 pn2[5];  //   2 pn
     u64 muf[4];  //   floor(2^(128L) / pn) - 2^(64L)        (full-width quotients: products)
     u32 nsh;     //   64L - k
-    u32 pad_;
+    u32 mus32;   //   floor(2^(k+32) / p) - 2^32            (32-bit quotients: values < 2^(k+31), barrett_small32)
+    u32 q32;     //   per launch (set by the launcher, 0 in the field handle): every value handed to reduce_small is
+    u32 pad_;    //   < 2^(k+31), so the 32-bit-quotient step applies
 };
 
 // 32-bit view of a little-endian u64 array (kernel parameters and tables are stored as u64)
@@ -470,6 +472,22 @@ struct Fp {
         barrett_fix(r, d, as32(f.p), as32(f.p2));
     }
 
+    // x < 2^(k+31) in WSM limbs -> x mod p, with a ONE-limb quotient: x1 = floor(x / 2^k) < 2^31,
+    // q^ = x1 + floor(x1 * mus32 / 2^32) with 2^32 + mus32 = floor(2^(k+32) / p):  q - 3 <= q^ <= q < 2^32
+    // (x/p - q^ = frac(x1 M / 2^32) + x1 eps / 2^32 + x0 / p < 1 + 1 + 2).  One IMAD.HI for the estimate and N
+    // IMAD.WIDE for q^ p, against 4 + 3N for barrett_small: share generation multiplies by (i+1)^j only, so its
+    // sums are < (1 + m + ... + m^t) p and the quotient is tiny (launch_impl.cuh: split_q32).
+    static FF_HD void barrett_small32(u32* r, const u32* x, const FieldParams& f) {
+        const u64 lo = get64(x, L - 1), hi = get64(x, L);
+        const u32 x1 = (u32)(f.s ? ((lo >> f.s) | (hi << (64 - f.s))) : hi);
+        const u32 q = x1 + (u32)(((u64)x1 * f.mus32) >> 32);        // q^ <= q = floor(x / p) < 2^(k+31) / 2^(k-1) = 2^32
+        u32 T[N + 2], d[N + 1];
+        zero_n<N + 2>(T);
+        mac_small<N, N + 2>(T, as32(f.p), q);
+        sub_n<N + 1>(d, x, T);                          // x - q^ p in [0, 4p), exact mod 2^(32(N+1))
+        barrett_fix(r, d, as32(f.p), as32(f.p2));
+    }
+
     // canonical a, b -> a b mod p.  The product is taken against b << nsh so that the modulus is the
     // normalised pn = p << nsh (top bit of N limbs set): x' = a b 2^nsh < 2^(32N) pn, x1 = its high N
     // limbs, q^ = x1 + floor(x1 * muf / 2^(32N)) with 2^(32N) + muf = floor(2^(64N) / pn);
@@ -508,6 +526,30 @@ struct Fp {
     static FF_HD void reduce_small(u32* r, const u32* x, const FieldParams& f) {
         if constexpr (KIND == KIND_GENERIC) barrett_small(r, x, f);
         else pm_reduce<WSM>(r, x, f);
+    }
+
+    // the same when the launcher has established x < 2^(k+31) for every value of this launch (f.q32, warp-uniform)
+    static FF_HD void reduce_small_q32(u32* r, const u32* x, const FieldParams& f) {
+        if constexpr (KIND == KIND_GENERIC) {
+            if (f.q32) barrett_small32(r, x, f);
+            else barrett_small(r, x, f);
+        } else if constexpr (KIND == KIND_PM_ALIGNED && L == 1) {
+            if (f.q32) {
+                // p = 2^64 - c, x = lo + hi 2^64 with hi < 2^31: x = lo + hi c (mod p), hi c < 2^47 -- one IMAD.WIDE,
+                // one 64-bit add, a rare second fold of the carry, one conditional subtraction (the general fold
+                // multiplies the two-limb top part by c and folds twice)
+                const u64 lo = get64(x, 0);
+                const u64 t = (u64)x[2] * (u32)f.c;
+                u64 v = lo + t;
+                if (v < t) v += f.c;                     // carry: 2^64 = c (mod p); cannot carry again (v < 2^48 + c)
+                set64(r, 0, v);
+                csub(r, 0, f);
+            } else {
+                pm_reduce<WSM>(r, x, f);
+            }
+        } else {
+            pm_reduce<WSM>(r, x, f);
+        }
     }
 
     // r = a^e in the domain; e = little-endian 64-bit limbs, ebits = bit length of e (>= 0).

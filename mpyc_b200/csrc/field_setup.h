@@ -47,6 +47,8 @@ static inline void barrett_constants(FieldParams& fp) {
     for (int i = 0; i <= L; i++) fp.p2[i] = ((i < L ? fp.p[i] : 0) << 1) | (i ? fp.p[i - 1] >> 63 : 0);
     pow2_div((int)fp.k + 64, fp.p, L, q);           // 2^64 <= quotient < 2^65
     fp.mus = q[0];
+    pow2_div((int)fp.k + 32, fp.p, L, q);           // 2^32 <= quotient < 2^33
+    fp.mus32 = (u32)q[0];
     for (int i = L - 1; i >= 0; i--)
         fp.pn[i] = fp.nsh ? ((fp.p[i] << fp.nsh) | (i ? fp.p[i - 1] >> (64 - fp.nsh) : 0)) : fp.p[i];
     for (int i = 0; i <= L; i++) fp.pn2[i] = ((i < L ? fp.pn[i] : 0) << 1) | (i ? fp.pn[i - 1] >> 63 : 0);

@@ -381,7 +381,7 @@ __device__ __forceinline__ void split_compute(const FieldParams& f, const u32 (*
                 acc[N] = acc[N + 1] = 0;
 #pragma unroll
                 for (int j = 1; j < TP1; j++) F::mac_const(acc, M[j] + e * N, tab[i * TP1 + j]);
-                if constexpr (TP1 > 1) F::reduce_small(r + e * N, acc, f);
+                if constexpr (TP1 > 1) F::reduce_small_q32(r + e * N, acc, f);
                 else copy_n<N>(r + e * N, acc);
             }
         }

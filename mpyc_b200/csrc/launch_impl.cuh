@@ -113,6 +113,24 @@ cudaError_t Launch<L>::inv_batch(const FieldParams& fp, const ExpParams& ex, con
 
 // ---- split ----------------------------------------------------------------------------------
 
+// Small-table share generation sums M[0] + sum_{j>=1} M[j] (i+1)^j < (1 + m + ... + m^t) p.  When that factor is
+// at most 2^31 every value handed to the per-share reduction is < 2^(k+31): generic fields may use the one-limb
+// quotient (Fp::barrett_small32) and 2^64 - c the single-multiply fold (Fp::reduce_small_q32).  Returns fp with q32
+// set accordingly (the copy travels as the kernel parameter).
+static inline FieldParams split_q32(const FieldParams& fp, bool full, int t, int m) {
+    FieldParams f = fp;
+    f.q32 = 0;
+    if (!full && (fp.kind == KIND_GENERIC || (fp.kind == KIND_PM_ALIGNED && fp.L == 1)) && m >= 1 && t >= 0 && t <= 16 && getenv("MPYC_B200_NO_Q32") == nullptr) {
+        unsigned __int128 sum = 0, pw = 1;             // m <= 255, t <= 16: m^t < 2^128
+        for (int j = 0; j <= t; j++) {
+            sum += pw;
+            pw *= (unsigned)m;
+        }
+        f.q32 = sum <= ((unsigned __int128)1 << 31) ? 1u : 0u;
+    }
+    return f;
+}
+
 template <int L, int KIND, bool FULL, bool VEC>
 static cudaError_t split_k(const FieldParams& fp, const u64* secrets, const u64* coeffs, size_t cstride, u64* shares,
                            size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
@@ -157,9 +175,10 @@ static cudaError_t split_kind(const FieldParams& fp, const u64* secrets, const u
 }
 
 template <int L>
-cudaError_t Launch<L>::split(const FieldParams& fp, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
+cudaError_t Launch<L>::split(const FieldParams& fp0, bool full, const u64* secrets, const u64* coeffs, size_t cstride,
                              u64* shares, size_t sstride, size_t n, int t, int m, const u64* gtab, u32 tab_bytes,
                              cudaStream_t st) {
+    const FieldParams fp = split_q32(fp0, full, t, m);
     const bool vec = L != 3 && aligned32(secrets) && aligned32(shares) && (t == 0 || aligned32(coeffs)) &&
                      (cstride % 4 == 0 || t <= 1) && (sstride % 4 == 0 || m <= 1);   // strides in limbs
     const int maxt = full ? 5 : 9;
@@ -214,8 +233,9 @@ static cudaError_t split_gen_k(const FieldParams& fp, const ChaChaKey& key, cons
 }
 
 template <int L>
-cudaError_t Launch<L>::split_gen(const FieldParams& fp, bool full, const ChaChaKey& key, const u64* secrets,
+cudaError_t Launch<L>::split_gen(const FieldParams& fp0, bool full, const ChaChaKey& key, const u64* secrets,
                                  const ShareDst& dst, size_t n, int t, int m, const u64* gtab, u32 tab_bytes, cudaStream_t st) {
+    const FieldParams fp = split_q32(fp0, full, t, m);
     const bool vec = L != 3 && aligned32(secrets) && dst_aligned32(dst, m);
 #define GEN_GO(V)                                                                                                  \
     do {                                                                                                           \

@@ -46,6 +46,13 @@ def commands(p, lazy_sizes=(1, 2, 3, 7, 17, 64, 1000)):
     for x in [0, 1, p, p - 1, (1 << (k + 64)) - 1, (p << 64) - 1] + [rnd.randrange(1 << (k + 64)) for _ in range(16)]:
         lines.append(f'redsmall {x:x}')
         want.append(x % p)
+    # share-generation sums (1 + m + ... + m^t) p <= 2^31 p: the 32-bit-quotient Barrett step of generic fields and
+    # the single-multiply fold of 2^64 - c (Fp::reduce_small_q32 with q32 set)
+    for x in [0, 1, p, p - 1, 2 * p - 1, 2 * p, 3 * p + 5, (1 << (k + 31)) - 1, (p << 31) - 1, ((1 << 31) - 1) * p, 31 * (p - 1), 400 * (p - 1)] \
+            + [rnd.randrange(1 << (k + 31)) for _ in range(24)] + [rnd.randrange(1 << 9) * p + rnd.randrange(p) for _ in range(24)]:
+        if x < 1 << (k + 31):
+            lines.append(f'redsmall32 {x:x}')
+            want.append(x % p)
     for a in vals[:12]:
         for e in (0, 1, 2, 5, p - 2, (p - 1) // 2, (3 * p - 5) // 4 if p > 3 else 1, rnd.randrange(1 << 300)):
             lines.append(f'pow {a:x} {e:x}')

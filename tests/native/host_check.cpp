@@ -6,6 +6,7 @@
 //   lazy <K> a1 b1 ... aK bK          -> sum a_i*b_i mod p via mac (b in table form) + finish
 //   small <K> <s> a1 v1 ... aK vK     -> (s + sum a_i*v_i) mod p via mac_const + reduce_small
 //   redsmall <x>                      -> x mod p for x < 2^(k+64) via reduce_small
+//   redsmall32 <x>                    -> x mod p for x < 2^(k+31) via reduce_small_q32 with q32 set
 //   pow <a> <e>
 // TEST INFRASTRUCTURE: not part of the shipped library.
 #include <stdio.h>
@@ -89,6 +90,14 @@ static std::string run(const std::string& cmd, std::istringstream& in) {
             F::mac_const(acc, a, (u64)v[0] | ((u64)v[1] << 32));
         }
         F::reduce_small(r, acc, fp);
+        return to_hex(r, N);
+    }
+    if (cmd == "redsmall32") {           // x < 2^(k+31): the one-limb-quotient / single-fold forms (f.q32 set)
+        u32 x[N + 2];
+        in >> t; parse_hex(t, x, N + 2);
+        FieldParams f2 = fp;
+        f2.q32 = 1;
+        F::reduce_small_q32(r, x, f2);
         return to_hex(r, N);
     }
     if (cmd == "redsmall") {

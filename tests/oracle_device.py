@@ -184,3 +184,63 @@ def patch_finfields(monkeypatch=None):
             monkeypatch.setattr(ff, name, fn)
         else:
             setattr(ff, name, fn)
+
+
+# ---- cross-check mode: the REAL device calls run, and every result is compared with the oracle ------------------------
+
+def verify(log_path):
+    """Wrap the adapter's device round trips so that each real result is checked against the oracle on the same limb
+    arrays (split: the shares must lie on one polynomial of degree <= t through the secret; recombine and PRSS: equal
+    to the oracle's output).  Mismatches are appended to log_path and raise."""
+    real = {name: getattr(thresha, name) for name in ('_split_limbs', '_split_generate', '_recombine_limbs', '_prss_device')}
+
+    def fail(msg):
+        with open(log_path, 'a') as fh:
+            fh.write(f'{os.getpid()} {msg}\n')
+        raise AssertionError(msg)
+
+    def ints(ctx, a):
+        return [int(v) for v in codec.limbs_to_ints(np.ascontiguousarray(a), ctx)]
+
+    def check_sharing(ctx, sec, shares, t, m, what):
+        F = orc.field_of(ctx.modulus, binary=ctx.binary)
+        s = ints(ctx, sec)
+        rows = [ints(ctx, shares[i]) for i in range(m)]
+        if t + 1 <= m:
+            xs = list(range(1, t + 2))
+            if orc.recombine(F, xs, [rows[x - 1] for x in xs], [0])[0] != s:
+                fail(f'{what}: shares 1..t+1 do not recombine to the secrets (n={len(s)}, bits={ctx.bits})')
+            for i in range(t + 1, m):            # every further share lies on the same polynomial
+                if orc.recombine(F, xs, [rows[x - 1] for x in xs], [i + 1])[0] != rows[i]:
+                    fail(f'{what}: share {i + 1} is not on the polynomial through shares 1..t+1 (n={len(s)}, bits={ctx.bits})')
+
+    def split_limbs_v(ctx, sec, C, t, m):
+        out = real['_split_limbs'](ctx, sec, C, t, m)
+        want = split_limbs(ctx, sec, C, t, m)
+        if not np.array_equal(out, want):
+            fail(f'_split_limbs differs from the oracle (n={sec.shape[0]}, bits={ctx.bits}, t={t}, m={m})')
+        return out
+
+    def split_generate_v(ctx, sec, t, m):
+        out = real['_split_generate'](ctx, sec, t, m)
+        check_sharing(ctx, sec, out, t, m, '_split_generate')
+        return out
+
+    def recombine_limbs_v(ctx, xs, rows, pts):
+        out = real['_recombine_limbs'](ctx, xs, rows, pts)
+        want = recombine_limbs(ctx, xs, rows, pts)
+        if not np.array_equal(out, want):
+            fail(f'_recombine_limbs differs from the oracle (n={rows[0].shape[0]}, bits={ctx.bits}, xs={list(xs)}, pts={list(pts)})')
+        return out
+
+    def prss_device_v(*args, **kwargs):
+        out = real['_prss_device'](*args, **kwargs)
+        want = prss_device(*args, **kwargs)
+        if not np.array_equal(out, want):
+            fail(f'_prss_device differs from the oracle (n={args[-1] if not kwargs else "?"}, bits={args[0].bits})')
+        return out
+
+    thresha._split_limbs = split_limbs_v
+    thresha._split_generate = split_generate_v
+    thresha._recombine_limbs = recombine_limbs_v
+    thresha._prss_device = prss_device_v

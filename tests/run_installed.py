@@ -9,7 +9,8 @@ the child parties too:
     MPYC_REFERENCE           path of the reference checkout / install (prepended to sys.path); default: importable mpyc
     MPYC_B200_HARNESS        comma list: install (default), oracle (no GPU: device round trips answered by
                              tests/oracle_device.py -- test infrastructure), limb_wire, finfields, ops (operator hooks),
-                             resident (limb-resident arrays), spread (party i on GPU i mod #GPUs), strict, off
+                             resident (limb-resident arrays), spread (party i on GPU i mod #GPUs), verify (real device calls, every
+                             result cross-checked against the oracle; mismatches logged and raised), strict, off
     MPYC_B200_OPS_MIN_SIZE   install(operators_min_size=...)
     MPYC_B200_MIN_SIZE       install(min_size=...)
     MPYC_B200_FORCE_PRIME    hex prime: SecInt/SecFxp types are built over this prime (BASELINE configs[4]: 256-bit)
@@ -44,6 +45,9 @@ def main():
             oracle_device.patch()
             oracle_device.patch_finfields()
             oracle_device.patch_resident()
+        if 'verify' in flags:            # real device calls, each result cross-checked against the oracle
+            import oracle_device
+            oracle_device.verify(os.environ.get('MPYC_B200_VERIFY_LOG', '/tmp/mpyc_b200_verify.log'))
         kwargs = {'strict': 'strict' in flags, 'limb_wire': 'limb_wire' in flags,
                   'min_size': int(os.environ.get('MPYC_B200_MIN_SIZE', '0'))}
         if 'finfields' in flags or 'ops' in flags:
