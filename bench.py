@@ -583,11 +583,13 @@ def measure_device(w, n, steps, warmup, seed_rank=0, sustain_s=0.0, keep=False):
                 'split_ms': sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(count)) / count,
                 'rec_ms': 0.0 if is_mul else sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(count)) / count,
                 'launches': mpyc_b200.launch_count() - launches0, 'window': (t_start, t_end), 'count': count}
+    common = dict(ctx=ctx, is_mul=is_mul, eb=ctx.elem_bytes, L=max(ctx.nlimbs, 1))
     res = timed(steps)
+    res.update(common)
     if sustain_s > 0:
         per = max(res['total_ms'] / steps, 1e-3)
         res['sustained'] = timed(max(steps, int(sustain_s * 1e3 / per) + 1))
-    res.update(ctx=ctx, is_mul=is_mul, eb=ctx.elem_bytes, L=max(ctx.nlimbs, 1))
+        res['sustained'].update(common)
     if keep:
         res['buffers'] = dict(S=S, B=B, OUT=OUT) if is_mul else dict(S=S, C=C, SH=SH, REC=REC, rows=rows, xs=xs)
     return res

@@ -11,7 +11,7 @@
 #include "../../mpyc_b200/csrc/field_setup.h"
 
 struct Cmd {
-    int op;            // 0 mul 1 add 2 sub 3 neg 4 lazy 5 small 6 redsmall 7 pow
+    int op;            // 0 mul 1 add 2 sub 3 neg 4 lazy 5 small 6 redsmall 7 pow 8 redsmall32
     int cnt;
     u32 a[64][8];      // operands (up to 64 terms)
     u32 b[64][8];
@@ -48,6 +48,10 @@ __global__ void run(FieldParams fp, const Cmd* cmd, u32* out) {
         F::reduce_small(r, acc, fp);
     } else if (c.op == 6) {
         F::reduce_small(r, c.x, fp);
+    } else if (c.op == 8) {                 // x < 2^(k+31): one-limb-quotient Barrett / single-multiply fold
+        FieldParams f2 = fp;
+        f2.q32 = 1;
+        F::reduce_small_q32(r, c.x, f2);
     } else if (c.op == 7) {
         u32 x[N], r2[N];
         F::to_dom(x, c.a[0], fp);
@@ -148,6 +152,9 @@ int main() {
             }
         } else if (cmd == "redsmall") {
             c.op = 6;
+            in >> t; parse_hex(t, c.x, N + 2);
+        } else if (cmd == "redsmall32") {
+            c.op = 8;
             in >> t; parse_hex(t, c.x, N + 2);
         } else if (cmd == "pow") {
             c.op = 7;
