@@ -723,6 +723,34 @@ def time_gather(REC_row, n, world):
             'algbw_GBps': out_bytes / (ms * 1e-3) / 1e9, 'busbw_GBps': out_bytes * (world - 1) / world / (ms * 1e-3) / 1e9}
 
 
+def pcie_probe(nbytes=1 << 29, reps=3):
+    """What the host link gives this rank: pinned cudaMemcpyAsync H2D alone, D2H alone, and both directions at once
+    (GB/s per direction).  The e2e step moves h2d_bytes + d2h_bytes per step through exactly this link, so the
+    bidirectional figure is its ceiling."""
+    import torch
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * nbytes / (time.perf_counter() - t0) / 1e9
+    run(True, True)
+    return {'h2d_alone_GBps': run(True, False), 'd2h_alone_GBps': run(False, True), 'bidirectional_GBps_per_direction': run(True, True),
+            'bytes_per_copy': nbytes}
+
+
 def run_gpu_arm(a, w):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     numa = bind_to_gpu_numa(local)       # before CUDA initialisation and any pinned allocation
@@ -878,10 +906,18 @@ def run_gpu_arm(a, w):
             dt = float(td.item())
         if not is_mul:
             assert torch.equal(hout[0], hs), 'e2e: recombined secrets differ from inputs'
+        if world > 1:
+            dist.barrier()
+        probe = pcie_probe()                      # all ranks at once: what the shared host links give concurrently
+        if world > 1:
+            tp = torch.tensor([probe['bidirectional_GBps_per_direction']], device='cuda', dtype=torch.float64)
+            dist.all_reduce(tp, op=dist.ReduceOp.MIN)
+            probe['bidirectional_GBps_per_direction_min_over_ranks'] = float(tp.item())
         e2e = {'value': world * ne * a.steps / dt, 'unit': 'pairs/s' if not is_mul else 'elem/s', 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': d2h, 'n_per_step': ne, 'ms_per_step': 1e3 * dt / a.steps, 'path': path,
                'serial_two_call_ms_per_step': serial_ms,
                'pcie_GBps_per_direction': {'h2d': h2d / (dt / a.steps) / 1e9, 'd2h': d2h / (dt / a.steps) / 1e9},
+               'pcie_probe': probe,
                'note': 'all ranks concurrently, max over ranks of the host wall clock around the blocking C-ABI calls'}
         del hs
 

@@ -1489,9 +1489,16 @@ static int prss_host_impl(const mpyc_b200_field* f, const uint8_t* h_keys, int k
     size_t eb;
     mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
     const size_t per_elem = (size_t)d * chunk_bytes;
-    // elements per pipeline chunk: ~384 KiB of XOF output per sponge (about a millisecond of squeezing),
-    // a multiple of the kernel's 256-element tiles
+    // elements per pipeline chunk: a multiple of the kernel's 256-element tiles; at least ~384 KiB of XOF output per
+    // sponge (about a millisecond of squeezing) and, for long calls, about a sixth of the call (at most 4 MiB per
+    // sponge): every chunk boundary is a rendezvous of all sponge threads with the copy/launch thread, and with
+    // ~1 ms chunks the scheduling jitter of 20 threads cost a third of the throughput (round 2: 26 chunks per
+    // np_cnnmnist-sized call, 164 MB/s per sponge thread against 367 MB/s for a free-running sponge)
     size_t ce = std::max<size_t>((384u << 10) / per_elem / 256 * 256, 256);
+    const size_t sixth = round_up((n + 5) / 6, 256);
+    const size_t cap = std::max<size_t>((4u << 20) / per_elem / 256 * 256, 256);
+    ce = std::max(ce, std::min(sixth, cap));
+    if (getenv("MPYC_B200_PRSS_CHUNK")) ce = std::max<size_t>(round_up((size_t)atol(getenv("MPYC_B200_PRSS_CHUNK")), 256), 256);
     ce = std::min(ce, round_up(n, 256));
     const size_t cstride = round_up(ce * per_elem, 16);               // bytes per subset per chunk
     const size_t nchunks = (n + ce - 1) / ce;

@@ -612,6 +612,14 @@ def test_prss_pipeline_in_library(p, m, t, monkeypatch):
     monkeypatch.setenv('MPYC_B200_PRSS_NO_SIMPLE', '1')  # general small form instead of the compile-time plain-share variant
     general = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
     monkeypatch.delenv('MPYC_B200_PRSS_NO_SIMPLE')
+    monkeypatch.setenv('MPYC_B200_PRSS_CHUNK', '2048')   # ~100 pipeline chunks: slot reuse, events, producer hand-off
+    monkeypatch.setattr(thresha, 'prss_threads', 3)      # several sponges per thread: the AVX-512 lock-step form where available
+    many = thresha.np_pseudorandom_share(F, m, i, prfs(p), uci, big).value
+    monkeypatch.setenv('MPYC_B200_NO_AVX512', '1')       # (read once per process: only effective if set before the first PRSS call)
+    monkeypatch.delenv('MPYC_B200_PRSS_CHUNK')
+    monkeypatch.delenv('MPYC_B200_NO_AVX512')
+    monkeypatch.setattr(thresha, 'prss_threads', 0)
+    assert many.tolist() == ref.tolist()
     assert general.tolist() == ref.tolist()
     assert zero_full == got0
     assert ref.tolist() == one.tolist() == flat.tolist() == flat_full.tolist() == tiled_full.tolist()

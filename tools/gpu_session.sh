@@ -47,11 +47,13 @@ for step in "$@"; do
       cd $OLDPWD; cat $OUT/r02_demos.txt ;;
     ncu_*)
       cfg=${step#ncu_}
+      QUICK="--no-cpu --no-e2e --no-extras --sustain 0"
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/r02_launches_$cfg.csv \
-          python bench.py --config $cfg --steps 2 --warmup 1 --no-cpu > $OUT/r02_ncu_$cfg.log 2>&1
-      for k in k_split k_recombine k_prss k_binop; do
-        ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o $OUT/r02_ncu_${cfg}_$k -f \
-            python bench.py --config $cfg --steps 1 --warmup 1 --no-cpu >> $OUT/r02_ncu_$cfg.log 2>&1 || true
+          python bench.py --config $cfg --steps 2 --warmup 3 $QUICK > $OUT/r02_ncu_$cfg.log 2>&1
+      case $cfg in prss) kernels="k_prss";; modmul*) kernels="k_binop";; *) kernels="k_split k_recombine";; esac
+      for k in $kernels; do
+        ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o $OUT/r02_ncu_${cfg}_$k -f \
+            python bench.py --config $cfg --steps 1 --warmup 3 $QUICK >> $OUT/r02_ncu_$cfg.log 2>&1 || true
       done ;;
     sass)
       python tools/sass_summary.py > $OUT/r02_sass_summary.txt 2>&1; tail -5 $OUT/r02_sass_summary.txt ;;
