@@ -244,6 +244,15 @@ int mpyc_b200_shamir_split_generate_host(const mpyc_b200_field* f, const void* h
 int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const void* const* h_share_rows,
                                     const int64_t* xs, int k, const int64_t* x_rs, int width,
                                     void* h_out, size_t out_stride, size_t n, int device);
+/* A party's steady state in a stream of resharing rounds (mpyc/runtime.py:660-680): recombine the rows received for batch
+ * j (mpyc_b200_shamir_recombine_host's arguments, n_rec elements) WHILE dealing the shares of batch j+1
+ * (mpyc_b200_shamir_split_host's arguments, n_split elements).  One host thread issues the pipeline chunks of both jobs
+ * alternately on two independent stream sets, so the D2H-heavy split and the H2D-heavy recombination keep both PCIe
+ * directions busy.  Either job may be empty.  Results are identical to the two separate calls. */
+int mpyc_b200_shamir_reshare_step_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
+                                       size_t coeff_stride, void* h_shares, size_t share_stride, size_t n_split, int t, int m,
+                                       const void* const* h_share_rows, const int64_t* xs, int k, const int64_t* x_rs,
+                                       int width, void* h_out, size_t out_stride, size_t n_rec, int device);
 int mpyc_b200_ff_binop_host(const mpyc_b200_field* f, int op, const void* h_a, const void* h_b,
                             void* h_out, size_t n, int device);
 

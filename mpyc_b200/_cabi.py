@@ -93,6 +93,9 @@ _SIGNATURES = {
     'mpyc_b200_shamir_recombine_host': (c_int, [_field_p, POINTER(c_void_p), POINTER(c_int64), c_int,
                                                 POINTER(c_int64), c_int, c_void_p, c_size_t, c_size_t, c_int]),
     'mpyc_b200_ff_binop_host': (c_int, [_field_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    'mpyc_b200_shamir_reshare_step_host': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_int,
+                                                   POINTER(c_void_p), POINTER(c_int64), c_int, POINTER(c_int64), c_int, c_void_p,
+                                                   c_size_t, c_size_t, c_int]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _fn = getattr(lib, _name)   # AttributeError here = library does not export the declared ABI

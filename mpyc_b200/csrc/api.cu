@@ -1186,6 +1186,42 @@ size_t chunk_elems(size_t n, size_t bytes_per_elem_total) {
 
 }   // namespace
 
+// one pipeline chunk of a split with explicit coefficients: H2D of the t+1 input rows, K2, D2H of the m share rows,
+// all on slot `s` of workspace `w` (ch = chunk capacity in elements, eb = bytes per element)
+static int split_chunk(const mpyc_b200_field* f, Workspace* w, int s, size_t ch, size_t eb, const void* h_secrets,
+                       const void* h_coeffs, size_t coeff_stride, void* h_shares, size_t share_stride, size_t off, size_t cn,
+                       int t, int m) {
+    cudaStream_t st = w->streams[s];
+    char* din = (char*)w->d_in[s];
+    char* dout = (char*)w->d_out[s];
+    CU(cudaMemcpyAsync(din, (const char*)h_secrets + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+    if (t > 0)
+        CU(cudaMemcpy2DAsync(din + ch * eb, ch * eb, (const char*)h_coeffs + off * eb, coeff_stride * eb, cn * eb, t,
+                             cudaMemcpyHostToDevice, st));
+    int rc = mpyc_b200_shamir_split(f, din, din + ch * eb, ch, dout, ch, cn, t, m, st);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m, cudaMemcpyDeviceToHost, st));
+    return MPYC_B200_OK;
+}
+
+// one pipeline chunk of a recombination: H2D of the k share rows, K3, D2H of the `width` result rows
+static int recombine_chunk(const mpyc_b200_field* f, Workspace* w, int s, size_t ch, size_t eb, const void* const* h_share_rows,
+                           const int64_t* xs, int k, const int64_t* x_rs, int width, void* h_out, size_t out_stride, size_t off,
+                           size_t cn) {
+    cudaStream_t st = w->streams[s];
+    char* din = (char*)w->d_in[s];
+    char* dout = (char*)w->d_out[s];
+    const void* rows[MPYC_B200_MAX_POINTS];
+    for (int i = 0; i < k; i++) {
+        CU(cudaMemcpyAsync(din + (size_t)i * ch * eb, (const char*)h_share_rows[i] + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
+        rows[i] = din + (size_t)i * ch * eb;
+    }
+    int rc = mpyc_b200_shamir_recombine(f, rows, xs, k, x_rs, width, dout, ch, cn, st);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync((char*)h_out + off * eb, out_stride * eb, dout, ch * eb, cn * eb, width, cudaMemcpyDeviceToHost, st));
+    return MPYC_B200_OK;
+}
+
 MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
                                            size_t coeff_stride, void* h_shares, size_t share_stride, size_t n, int t, int m,
                                            int device) {
@@ -1205,19 +1241,9 @@ MPYC_API int mpyc_b200_shamir_split_host(const mpyc_b200_field* f, const void* h
     if (rc) return rc;
     size_t c = 0;
     for (size_t off = 0; off < n; off += ch, c++) {
-        const int s = (int)(c % kSlots);
-        const size_t cn = std::min(ch, n - off);
-        cudaStream_t st = w->streams[s];
-        char* din = (char*)w->d_in[s];
-        char* dout = (char*)w->d_out[s];
-        CU(cudaMemcpyAsync(din, (const char*)h_secrets + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
-        if (t > 0)
-            CU(cudaMemcpy2DAsync(din + ch * eb, ch * eb, (const char*)h_coeffs + off * eb, coeff_stride * eb, cn * eb, t,
-                                 cudaMemcpyHostToDevice, st));
-        rc = mpyc_b200_shamir_split(f, din, din + ch * eb, ch, dout, ch, cn, t, m, st);
+        rc = split_chunk(f, w, (int)(c % kSlots), ch, eb, h_secrets, h_coeffs, coeff_stride, h_shares, share_stride, off,
+                         std::min(ch, n - off), t, m);
         if (rc) return rc;
-        CU(cudaMemcpy2DAsync((char*)h_shares + off * eb, share_stride * eb, dout, ch * eb, cn * eb, m,
-                             cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
     return MPYC_B200_OK;
@@ -1277,21 +1303,64 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
     if (rc) return rc;
     size_t c = 0;
     for (size_t off = 0; off < n; off += ch, c++) {
-        const int s = (int)(c % kSlots);
-        const size_t cn = std::min(ch, n - off);
-        cudaStream_t st = w->streams[s];
-        char* din = (char*)w->d_in[s];
-        char* dout = (char*)w->d_out[s];
-        const void* rows[MPYC_B200_MAX_POINTS];
-        for (int i = 0; i < k; i++) {
-            CU(cudaMemcpyAsync(din + (size_t)i * ch * eb, (const char*)h_share_rows[i] + off * eb, cn * eb, cudaMemcpyHostToDevice, st));
-            rows[i] = din + (size_t)i * ch * eb;
-        }
-        rc = mpyc_b200_shamir_recombine(f, rows, xs, k, x_rs, width, dout, ch, cn, st);
+        rc = recombine_chunk(f, w, (int)(c % kSlots), ch, eb, h_share_rows, xs, k, x_rs, width, h_out, out_stride, off,
+                             std::min(ch, n - off));
         if (rc) return rc;
-        CU(cudaMemcpy2DAsync((char*)h_out + off * eb, out_stride * eb, dout, ch * eb, cn * eb, width, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < kSlots && (size_t)s < c; s++) CU(cudaStreamSynchronize(w->streams[s]));   // only the slots this call used
+    return MPYC_B200_OK;
+}
+
+// A party's steady state in a stream of resharing rounds (runtime.py:660-680): while it recombines the 2t+1 rows it
+// received for batch j (H2D-heavy: k rows in, one out) it already deals its shares of batch j+1 (D2H-heavy: t+1 rows in,
+// m out).  This entry point runs both jobs from ONE host thread with their pipeline chunks issued alternately on the
+// two workspaces' streams, so that both PCIe directions carry traffic all the time.  Either job may be empty
+// (n_split == 0 / n_rec == 0); the two jobs are independent (different buffers).
+MPYC_API int mpyc_b200_shamir_reshare_step_host(const mpyc_b200_field* f, const void* h_secrets, const void* h_coeffs,
+                                                  size_t coeff_stride, void* h_shares, size_t share_stride, size_t n_split, int t,
+                                                  int m, const void* const* h_share_rows, const int64_t* xs, int k,
+                                                  const int64_t* x_rs, int width, void* h_out, size_t out_stride, size_t n_rec,
+                                                  int device) {
+    if (!f) return fail(MPYC_B200_EINVAL, "field is null");
+    if (n_split) {
+        if (m < 1 || t < 0 || t >= m) return fail(MPYC_B200_EINVAL, "shamir_split: need 0 <= t < m");
+        if (!h_secrets || !h_shares || (t > 0 && !h_coeffs)) return fail(MPYC_B200_EINVAL, "reshare_step_host: null split buffer");
+    }
+    if (n_rec) {
+        if (!h_share_rows || !xs || !x_rs || !h_out) return fail(MPYC_B200_EINVAL, "reshare_step_host: null recombine argument");
+        if (k < 1 || width < 1 || k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EINVAL, "reshare_step_host: bad k/width");
+    }
+    if (n_split == 0 && n_rec == 0) return MPYC_B200_OK;
+    size_t eb;
+    mpyc_b200_field_info(f, nullptr, nullptr, nullptr, &eb);
+    // half-size chunks: twice as many interleaving points between the two jobs for the same staging memory
+    const size_t chs = n_split ? std::max<size_t>(chunk_elems(n_split, 2 * eb * (size_t)(t + 1 + m)), 16) : 16;
+    const size_t chr = n_rec ? std::max<size_t>(chunk_elems(n_rec, 2 * eb * (size_t)(k + width)), 16) : 16;
+    DeviceGuard guard;
+    Workspace *ws, *wr;
+    int rc = acquire_workspace(device, &ws, 0);
+    if (rc == MPYC_B200_OK) rc = acquire_workspace(device, &wr, 1);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g0(ws->mu);          // always set 0 before set 1
+    std::lock_guard<std::mutex> g1(wr->mu);
+    if (n_split) rc = reserve(*ws, chs * eb * (size_t)(t + 1), chs * eb * (size_t)m);
+    if (rc == MPYC_B200_OK && n_rec) rc = reserve(*wr, chr * eb * (size_t)k, chr * eb * (size_t)width);
+    if (rc) return rc;
+    const size_t cs = n_split ? (n_split + chs - 1) / chs : 0, cr = n_rec ? (n_rec + chr - 1) / chr : 0;
+    for (size_t c = 0; c < std::max(cs, cr); c++) {
+        if (c < cs) {
+            rc = split_chunk(f, ws, (int)(c % kSlots), chs, eb, h_secrets, h_coeffs, coeff_stride, h_shares, share_stride, c * chs,
+                             std::min(chs, n_split - c * chs), t, m);
+            if (rc) return rc;
+        }
+        if (c < cr) {
+            rc = recombine_chunk(f, wr, (int)(c % kSlots), chr, eb, h_share_rows, xs, k, x_rs, width, h_out, out_stride, c * chr,
+                                 std::min(chr, n_rec - c * chr));
+            if (rc) return rc;
+        }
+    }
+    for (int s = 0; s < kSlots && (size_t)s < cs; s++) CU(cudaStreamSynchronize(ws->streams[s]));
+    for (int s = 0; s < kSlots && (size_t)s < cr; s++) CU(cudaStreamSynchronize(wr->streams[s]));
     return MPYC_B200_OK;
 }
 

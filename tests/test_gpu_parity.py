@@ -624,3 +624,35 @@ def test_prss_pipeline_in_library(p, m, t, monkeypatch):
     assert zero_full == got0
     assert ref.tolist() == one.tolist() == flat.tolist() == flat_full.tolist() == tiled_full.tolist()
     assert ref[:n].tolist() == got               # a longer call extends the same streams (XOF prefix property)
+
+
+@pytest.mark.parametrize('p,m,t,k', [(P128, 5, 2, 3), (P64, 3, 1, 3), (P256, 7, 3, 7), (GEN['128'], 5, 2, 5)], ids=['p128', 'p64', 'p256', 'generic128'])
+def test_reshare_step_host_equals_the_two_calls(p, m, t, k):
+    """mpyc_b200_shamir_reshare_step_host (recombine batch j while dealing batch j+1, chunks of both jobs interleaved on
+    two stream sets) gives exactly what mpyc_b200_shamir_split_host and mpyc_b200_shamir_recombine_host give, for
+    multi-chunk and ragged sizes and with either job empty; the recombined values are checked against the oracle."""
+    import ctypes
+    from mpyc_b200 import _cabi
+    from mpyc_b200._cabi import lib, check
+    ctx = mpyc_b200.context_for(p)
+    L = ctx.nlimbs
+    Fo = orc.field_of(p)
+    xs = list(range(1, k + 1))
+    for n_split, n_rec in ((1_000_003, 700_001), (5, 3), (0, 1000), (4099, 0), (300_000, 2_000_000)):
+        rng = np.random.default_rng(n_split + n_rec)
+        sec = codec.ints_to_limbs(orc.synth_elements(p, n_split, 5), ctx)
+        C = np.stack([codec.ints_to_limbs(orc.synth_elements(p, n_split, 6 + j), ctx) for j in range(t)]) if n_split else np.zeros((t, 0, L), np.uint64)
+        rows = [codec.ints_to_limbs(orc.synth_elements(p, n_rec, 20 + i), ctx) for i in range(k)]
+        sh_a, out_a = np.zeros((m, n_split, L), np.uint64), np.zeros((1, n_rec, L), np.uint64)
+        sh_b, out_b = np.zeros((m, n_split, L), np.uint64), np.zeros((1, n_rec, L), np.uint64)
+        rowp = _cabi.ptr_array([r.ctypes.data for r in rows])
+        xs_c, xr_c = _cabi.i64_array(xs), _cabi.i64_array([0])
+        ptr = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
+        check(lib.mpyc_b200_shamir_split_host(ctx.handle, ptr(sec), ptr(C), n_split, ptr(sh_a), n_split, n_split, t, m, 0))
+        check(lib.mpyc_b200_shamir_recombine_host(ctx.handle, rowp, xs_c, k, xr_c, 1, ptr(out_a), n_rec, n_rec, 0))
+        check(lib.mpyc_b200_shamir_reshare_step_host(ctx.handle, ptr(sec), ptr(C), n_split, ptr(sh_b), n_split, n_split, t, m,
+                                                     rowp, xs_c, k, xr_c, 1, ptr(out_b), n_rec, n_rec, 0))
+        assert np.array_equal(sh_a, sh_b) and np.array_equal(out_a, out_b)
+        if 0 < n_rec <= 1000:
+            want = orc.recombine(Fo, xs, [[int(v) for v in codec.limbs_to_ints(r, ctx)] for r in rows], [0])[0]
+            assert [int(v) for v in codec.limbs_to_ints(out_b[0], ctx)] == want

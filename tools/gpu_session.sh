@@ -52,9 +52,22 @@ for step in "$@"; do
           python bench.py --config $cfg --steps 2 --warmup 3 $QUICK > $OUT/r02_ncu_$cfg.log 2>&1
       case $cfg in prss) kernels="k_prss";; modmul*) kernels="k_binop";; *) kernels="k_split k_recombine";; esac
       for k in $kernels; do
-        ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o $OUT/r02_ncu_${cfg}_$k -f \
+        ncu --set full --clock-control none -k regex:$k -s 3 -c 1 -o $OUT/r02_ncu_${cfg}_$k -f \
             python bench.py --config $cfg --steps 1 --warmup 3 $QUICK >> $OUT/r02_ncu_$cfg.log 2>&1 || true
+        python tools/ncu_summary.py $OUT/r02_ncu_${cfg}_$k.ncu-rep $OUT/r02_ncu_${k#k_}_$cfg.txt > /dev/null 2>&1 || true
+        ncu -i $OUT/r02_ncu_${cfg}_$k.ncu-rep --page details --csv > $OUT/r02_ncu_${cfg}_${k}_details.csv 2>/dev/null || true
+        ncu -i $OUT/r02_ncu_${cfg}_$k.ncu-rep --page raw --csv > $OUT/r02_ncu_${cfg}_${k}_raw.csv 2>/dev/null || true
+        rm -f $OUT/r02_ncu_${cfg}_$k.ncu-rep      # 35-55 MB each: only the extracted pages travel back (gpurun_out is capped at 64 MiB)
       done ;;
+    overlap)
+      python tools/time_e2e_overlap.py > $OUT/r02_e2e_overlap.json 2>&1; cat $OUT/r02_e2e_overlap.json ;;
+    variants_*)
+      cfg=${step#variants_}
+      for lib in libmpyc_b200.so libmpyc_b200_u2.so libmpyc_b200_minb2.so libmpyc_b200_u2minb2.so; do
+        [ -f mpyc_b200/$lib ] || continue
+        echo "# $lib" >> $OUT/r02_variants_$cfg.txt
+        MPYC_B200_LIB=$lib python bench.py --config $cfg --steps 10 --no-cpu --no-e2e --no-extras --sustain 0 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print(r['kernel'], round(r['frac'],4), round(r['ms'],4), 'rec', round(r.get('recombine',{}).get('frac',0),4), 'value', d['value'])" >> $OUT/r02_variants_$cfg.txt 2>&1
+      done; cat $OUT/r02_variants_$cfg.txt ;;
     sass)
       python tools/sass_summary.py > $OUT/r02_sass_summary.txt 2>&1; tail -5 $OUT/r02_sass_summary.txt ;;
     *) echo "unknown step $step" ;;
