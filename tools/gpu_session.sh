@@ -8,6 +8,9 @@
 #   chain        tests/programs/resident_chain.py, 3 parties, n = 10^6: off / install / resident   -> r02_chain.jsonl
 #   demos        np_aes / np_cnnmnist timings with and without the engine                          -> r02_demos.txt
 #   ncu_<cfg>    launch list + one --set full capture of the split/recombine kernels of a bench config
+#   scale_N      (gpurun --gpus N) the driver's N-GPU launch line: multi_selftest, gather timing, e2e over all ranks; N=2 also tests/test_gpu_multi.py
+#   overlap      tools/time_e2e_overlap.py at three pipeline chunk sizes
+#   variants_<cfg>  bench a config with every libmpyc_b200_*.so tuning build present
 #   sass         per-kernel SASS / ptxas summary (no GPU needed, also runs in the build container)
 set -u
 OUT=gpurun_out
@@ -44,7 +47,7 @@ for step in "$@"; do
         s=$(date +%s.%N)
         res=$(env $extra MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h MPYC_REFERENCE=$REFDIR timeout 1500 python $OLDPWD/tests/run_installed.py "$@" -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 2 | tr '\n' ' ')
         e=$(date +%s.%N)
-        echo "$label | harness=$h | wall=$(echo "$e - $s" | bc) s | $res" >> $OLDPWD/$OUT/r02_demos.txt
+        echo "$label | harness=$h | wall=$(python -c "print(round($e - $s, 2))") s | $res" >> $OLDPWD/$OUT/r02_demos.txt
       }
       for h in off install install,resident; do
         run_demo "np_aes 1 party" $h "X=1" np_aes.py -1
@@ -69,6 +72,14 @@ for step in "$@"; do
         ncu -i $OUT/r02_ncu_${cfg}_$k.ncu-rep --page raw --csv > $OUT/r02_ncu_${cfg}_${k}_raw.csv 2>/dev/null || true
         rm -f $OUT/r02_ncu_${cfg}_$k.ncu-rep      # 35-55 MB each: only the extracted pages travel back (gpurun_out is capped at 64 MiB)
       done ;;
+    scale_*)
+      # gpurun --gpus N -- 'bash tools/gpu_session.sh scale_N': the driver's launch line for N > 1, plus the 2-GPU tests
+      N=${step#scale_}
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py \
+          --gpus $N --steps 20 --warmup 5 > $OUT/r02_scale_n$N.json 2> $OUT/r02_scale_n$N.err
+      tail -c 2500 $OUT/r02_scale_n$N.json; tail -5 $OUT/r02_scale_n$N.err
+      python bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $OUT/r02_scale_n${N}_reference.json 2>> $OUT/r02_scale_n$N.err
+      if [ "$N" = "2" ]; then python -m pytest tests/test_gpu_multi.py -q -m gpu 2>&1 | tail -3 | tee $OUT/r02_pytest_multi.log; fi ;;
     overlap)
       : > $OUT/r02_e2e_overlap.jsonl
       for mb in 32 8 128; do MPYC_B200_CHUNK_MB=$mb python tools/time_e2e_overlap.py $mb >> $OUT/r02_e2e_overlap.jsonl 2>&1; done
