@@ -232,6 +232,9 @@ __device__ __forceinline__ void gf_split_group(const GfW2& s0, const GfW2* c, un
     }
 }
 
+#ifndef GF_SPLIT_PREFETCH
+#define GF_SPLIT_PREFETCH 1   // software-pipelined main loop (0: GF_SPLIT_U groups per trip, all loads first)
+#endif
 #ifndef GF_SPLIT_U
 #define GF_SPLIT_U 2   // 16-byte groups in flight per thread (ncu round 1: long-scoreboard bound at one group, 0.84-0.86 of peak)
 #endif
@@ -242,8 +245,28 @@ k_gf_split_vec(unsigned poly, const unsigned char* __restrict__ secrets, const u
                size_t cstride, unsigned char* __restrict__ shares, size_t sstride, size_t ngroups, int m) {
     const size_t nth = (size_t)gridDim.x * blockDim.x;
     const unsigned long long red = poly & 0xFFu;
-    constexpr int U = GF_SPLIT_U;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if GF_SPLIT_PREFETCH
+    // software pipeline (as k_split for 1-limb prime fields): the T+1 input vectors of group g+nth are requested before
+    // the shares of group g are computed and stored
+    GfW2 s0 = {0ull, 0ull}, c[T > 0 ? T : 1];
+    auto fetch = [&](GfW2& s, GfW2* cc, size_t grp) {
+        s = gf_ld16(secrets + 16 * grp);
+#pragma unroll
+        for (int j = 0; j < T; j++) cc[j] = gf_ld16(coeffs + (size_t)j * cstride + 16 * grp);
+    };
+    if (g < ngroups) fetch(s0, c, g);
+    for (; g < ngroups; g += nth) {
+        const bool more = g + nth < ngroups;
+        GfW2 s1 = {0ull, 0ull}, c1[T > 0 ? T : 1];
+        if (more) fetch(s1, c1, g + nth);
+        gf_split_group<T>(s0, c, shares, sstride, g, m, red);
+        s0 = s1;
+#pragma unroll
+        for (int j = 0; j < T; j++) c[j] = c1[j];
+    }
+#else
+    constexpr int U = GF_SPLIT_U;
     for (; g + (U - 1) * nth < ngroups; g += U * nth) {      // all loads of the U groups are issued before the first xtime
         GfW2 s0[U];
         GfW2 c[U][T > 0 ? T : 1];
@@ -263,6 +286,7 @@ k_gf_split_vec(unsigned poly, const unsigned char* __restrict__ secrets, const u
         for (int j = 0; j < T; j++) c[j] = gf_ld16(coeffs + (size_t)j * cstride + 16 * g);
         gf_split_group<T>(s0, c, shares, sstride, g, m, red);
     }
+#endif
 }
 
 // ---- recombine, vector form (width 1): 16 bytes per thread and access ----------------------------------

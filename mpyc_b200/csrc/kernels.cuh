@@ -409,6 +409,11 @@ __device__ __forceinline__ void split_items(const FieldParams& f, const u64* sec
         split_compute<L, KIND, TP1, FULL, E, VEC>(f, M[u], dst, m, tab, limb_off + u * limb_step);
 }
 
+#ifndef MPYC_SPLIT_PREFETCH
+// software-pipelined main loop of k_split for fields of at most this many limbs (0 = off).  Measured on B200, ns64
+// (1 limb, 160 bytes per thread and trip, long-scoreboard bound at 46 % warps active): K2 0.874 -> 0.937 of the copy peak
+#define MPYC_SPLIT_PREFETCH 1
+#endif
 #ifndef MPYC_SPLIT_MINB
 #define MPYC_SPLIT_MINB 1   // min resident CTAs per SM requested from ptxas for k_split (register cap)
 #endif
@@ -429,12 +434,37 @@ k_split(FieldParams f, const u64* __restrict__ secrets, const u64* __restrict__ 
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n_items = n / E;
     size_t it = tid;
-    for (; it + (U - 1) * nth < n_items; it += U * nth)
-        split_items<L, KIND, TP1, FULL, E, VEC, U>(f, secrets, coeffs, cstride, dst, m, stab,
-                                                   it * (size_t)(E * L), nth * (size_t)(E * L));
-    for (; it < n_items; it += nth)
-        split_items<L, KIND, TP1, FULL, E, VEC, 1>(f, secrets, coeffs, cstride, dst, m, stab,
-                                                   it * (size_t)(E * L), 0);
+    if constexpr (L <= MPYC_SPLIT_PREFETCH && !FULL && TP1 <= 3) {
+        // software pipeline for the narrow fields (few bytes per item, latency-bound at one item per trip): the t+1
+        // input vectors of item it+nth are requested before the shares of item it are computed and stored
+        constexpr int N = 2 * L;
+        u32 cur[TP1][E * N], nxt[TP1][E * N];
+        auto fetch = [&](u32 (*M)[E * N], size_t item) {
+            const size_t off = item * (size_t)(E * L);
+            load_limbs<E * L, VEC>(M[0], secrets + off);
+#pragma unroll
+            for (int j = 1; j < TP1; j++) load_limbs<E * L, VEC>(M[j], coeffs + (size_t)(j - 1) * cstride + off);
+        };
+        if (it < n_items) fetch(cur, it);
+        for (; it < n_items; it += nth) {
+            const bool more = it + nth < n_items;
+            if (more) fetch(nxt, it + nth);
+            split_compute<L, KIND, TP1, FULL, E, VEC>(f, cur, dst, m, stab, it * (size_t)(E * L));
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < TP1; j++)
+#pragma unroll
+                    for (int q = 0; q < E * N; q++) cur[j][q] = nxt[j][q];
+            }
+        }
+    } else {
+        for (; it + (U - 1) * nth < n_items; it += U * nth)
+            split_items<L, KIND, TP1, FULL, E, VEC, U>(f, secrets, coeffs, cstride, dst, m, stab,
+                                                       it * (size_t)(E * L), nth * (size_t)(E * L));
+        for (; it < n_items; it += nth)
+            split_items<L, KIND, TP1, FULL, E, VEC, 1>(f, secrets, coeffs, cstride, dst, m, stab,
+                                                       it * (size_t)(E * L), 0);
+    }
     if constexpr (E > 1) {
         for (size_t h = n_items * E + tid; h < n; h += nth)
             split_items<L, KIND, TP1, FULL, 1, false, 1>(f, secrets, coeffs, cstride, dst, m, stab,
