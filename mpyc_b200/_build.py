@@ -83,11 +83,29 @@ def build(force=False, verbose=False, defines=(), lib=None):
         finally:
             OBJ, LIB = saved
     os.makedirs(OBJ, exist_ok=True)
-    build_codec(force=False)
     stamp = LIB + '.digest'   # next to the library: travels with it to the GPU box, where nothing is rebuilt
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest
+    if not force and fresh():
+        build_codec(force=False)
         return LIB
+    # several processes may import the package at once (torchrun ranks, MPyC parties): one of them builds, the others wait
+    # on the lock and then find the fresh stamp
+    import fcntl
+    with open(os.path.join(OBJ, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            build_codec(force=False)
+            if not force and fresh():
+                return LIB
+            return _build_locked(verbose, defines, stamp, digest)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose, defines, stamp, digest):
     nvcc = _nvcc()
 
     def compile_one(src):

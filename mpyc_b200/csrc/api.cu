@@ -1317,7 +1317,8 @@ MPYC_API int mpyc_b200_shamir_recombine_host(const mpyc_b200_field* f, const voi
                                                int k, const int64_t* x_rs, int width, void* h_out, size_t out_stride,
                                                size_t n, int device) {
     if (!f || !h_share_rows || !xs || !x_rs) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: null argument");
-    if (k < 1 || width < 1 || k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: bad k/width");
+    if (k < 1 || width < 1) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: bad k/width");
+    if (k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EUNSUPPORTED, "shamir_recombine_host: more than MPYC_B200_MAX_POINTS shares");
     if (n == 0) return MPYC_B200_OK;
     if (!h_out) return fail(MPYC_B200_EINVAL, "shamir_recombine_host: null output");
     size_t eb;
@@ -1357,7 +1358,8 @@ MPYC_API int mpyc_b200_shamir_reshare_step_host(const mpyc_b200_field* f, const 
     }
     if (n_rec) {
         if (!h_share_rows || !xs || !x_rs || !h_out) return fail(MPYC_B200_EINVAL, "reshare_step_host: null recombine argument");
-        if (k < 1 || width < 1 || k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EINVAL, "reshare_step_host: bad k/width");
+        if (k < 1 || width < 1) return fail(MPYC_B200_EINVAL, "reshare_step_host: bad k/width");
+        if (k > MPYC_B200_MAX_POINTS) return fail(MPYC_B200_EUNSUPPORTED, "reshare_step_host: more than MPYC_B200_MAX_POINTS shares");
     }
     if (n_split == 0 && n_rec == 0) return MPYC_B200_OK;
     size_t eb;

@@ -198,6 +198,8 @@ def _check_rows(ctx, rows):
     """Every share row must hold the same number of elements in the field's limb layout: rows come from peers
     (unpickled arrays or ShareRows whose length the sender chose), and the C ABI copies n elements from each
     (the reference raises from field.array(shares) on ragged input, thresha.py:128)."""
+    if len(rows) > _cabi.MAX_POINTS:
+        raise _cabi.UnsupportedFieldError(f'recombination of more than {_cabi.MAX_POINTS} shares is not covered by mpyc_b200')
     n = len(rows[0])
     want = (n,) if ctx.binary else (n, ctx.nlimbs)
     dt = np.uint8 if ctx.binary else np.uint64

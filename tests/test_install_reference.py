@@ -151,3 +151,37 @@ def test_install_sets_and_clears_the_limb_wire_flag(mpyc_thresha):
     finally:
         inst.uninstall()
     assert engine.limb_wire is False
+
+
+def test_coverage_is_decided_per_call_never_raises_where_the_reference_computes(mpyc_thresha, monkeypatch):
+    """A covered field with an argument outside the kernels' range -- a PRF bound above 2^256, more than 64 recombination
+    points -- is computed by the reference's own function (round 1 raised UnsupportedFieldError in the middle of
+    runtime._convert).  strict=True keeps raising.  The device round trips are answered by the oracle here."""
+    thresha, finfields, gfpx = mpyc_thresha
+    import mpyc_b200
+    from mpyc_b200 import install as inst
+    import oracle_device
+    oracle_device.patch(monkeypatch)
+    F = finfields.GF(2**61 - 1)
+    key = bytes(range(16))
+    big = (1 << 300) + 7
+    prfs = {(0,): thresha.PRF(key, big)}
+    want = thresha.np_pseudorandom_share(F, 1, 0, prfs, b'uci', 9).value.tolist()
+    want_l = [a.value for a in thresha.pseudorandom_share(F, 1, 0, prfs, b'uci', 9)]
+    xs = list(range(1, 71))                                   # 70 points > MPYC_B200_MAX_POINTS
+    rows = [[(x * 7 + h) % F.modulus for h in range(5)] for x in xs]
+    want_rec = thresha.recombine(F, list(zip(xs, rows)))
+    inst.install(thresha)
+    try:
+        assert thresha.np_pseudorandom_share(F, 1, 0, prfs, b'uci', 9).value.tolist() == want
+        assert [a.value for a in thresha.pseudorandom_share(F, 1, 0, prfs, b'uci', 9)] == want_l
+        got = thresha.recombine(F, list(zip(xs, rows)))
+        assert [int(v) % F.modulus for v in got] == [int(v) % F.modulus for v in want_rec]
+    finally:
+        inst.uninstall()
+    inst.install(thresha, strict=True)
+    try:
+        with pytest.raises(mpyc_b200.UnsupportedFieldError):
+            thresha.np_pseudorandom_share(F, 1, 0, prfs, b'uci', 9)
+    finally:
+        inst.uninstall()
