@@ -877,10 +877,11 @@ def run_gpu_arm(a, w):
             def e2e_run(count):
                 # software pipeline over successive batches: while batch j's shares are recombined (H2D-heavy), batch
                 # j+1 is split from a second host thread (D2H-heavy); the two entry points use separate workspaces in
-                # the library.  `count` splits and `count` recombinations in total.  (Measured on the B200 box: this,
-                # the serial two-call form and the single-thread mpyc_b200_shamir_reshare_step_host are within 4 % of
-                # each other -- 41.3 / 42.4 / 44.3 ms: the step is bound by the aggregate PCIe throughput of the
-                # chunked copy pattern, ~78 GB/s over both directions, not by a lack of overlap; see pcie_probe.)
+                # the library.  `count` splits and `count` recombinations in total.  (Measured on the B200 box with
+                # 32 MiB pipeline chunks this, the serial two-call form and the single-thread
+                # mpyc_b200_shamir_reshare_step_host were within 4 % of each other -- 41.3 / 42.4 / 44.3 ms; with
+                # call-sized chunks (128 MiB here) 37.6 / 42.3 ms: the step is bound by the PCIe throughput the
+                # chunked bidirectional copy pattern reaches, see pcie_probe.)
                 for j in range(count + 1):
                     th = None
                     if j < count:

@@ -638,11 +638,16 @@ def test_reshare_step_host_equals_the_two_calls(p, m, t, k):
     L = ctx.nlimbs
     Fo = orc.field_of(p)
     xs = list(range(1, k + 1))
+    def rand_limbs(n, seed):
+        """n canonical residues as a host limb array (generated on the device: no Python-int loops)."""
+        if n == 0:
+            return np.zeros((0, L), np.uint64)
+        return np.ascontiguousarray(DeviceArray.random(ctx, n, seed=seed, stream_id=4).to_limbs())
+
     for n_split, n_rec in ((1_000_003, 700_001), (5, 3), (0, 1000), (4099, 0), (300_000, 2_000_000)):
-        rng = np.random.default_rng(n_split + n_rec)
-        sec = codec.ints_to_limbs(orc.synth_elements(p, n_split, 5), ctx)
-        C = np.stack([codec.ints_to_limbs(orc.synth_elements(p, n_split, 6 + j), ctx) for j in range(t)]) if n_split else np.zeros((t, 0, L), np.uint64)
-        rows = [codec.ints_to_limbs(orc.synth_elements(p, n_rec, 20 + i), ctx) for i in range(k)]
+        sec = rand_limbs(n_split, 5)
+        C = np.stack([rand_limbs(n_split, 6 + j) for j in range(t)]) if n_split else np.zeros((t, 0, L), np.uint64)
+        rows = [rand_limbs(n_rec, 20 + i) for i in range(k)]
         sh_a, out_a = np.zeros((m, n_split, L), np.uint64), np.zeros((1, n_rec, L), np.uint64)
         sh_b, out_b = np.zeros((m, n_split, L), np.uint64), np.zeros((1, n_rec, L), np.uint64)
         rowp = _cabi.ptr_array([r.ctypes.data for r in rows])

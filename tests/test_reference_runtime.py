@@ -75,6 +75,14 @@ def mode(request):
     return request.param
 
 
+def trim_for_gpu(mode, keep):
+    """The cuda variants run a subset (the driver's GPU test slot is minutes, and every run pays interpreter start + CUDA
+    context creation per party): multi-party runs and the most invasive configurations.  MPYC_B200_FULL_GPU_HARNESS=1
+    runs everything."""
+    if mode == 'cuda' and not keep and os.environ.get('MPYC_B200_FULL_GPU_HARNESS') != '1':
+        pytest.skip('not in the GPU subset (MPYC_B200_FULL_GPU_HARNESS=1 runs it)')
+
+
 def run(mode, program, args=(), flags=('install',), cwd=None, timeout=900, parties=1, env_extra=None):
     flags = list(flags)
     if mode == 'oracle' and 'off' not in flags:
@@ -104,6 +112,7 @@ def test_reference_unittests_under_install(mode, name, flags):
         pytest.skip('reference tests/ directory not available (package-only reference)')
     if name in ('test_sectypes', 'test_secpols', 'test_statistics') and flags != ('install', 'resident'):
         pytest.skip('the wider suites run once, in the most invasive configuration')
+    trim_for_gpu(mode, flags in (('install',), ('install', 'resident')) and name in ('test_thresha', 'test_finfields', 'test_runtime', 'test_secpols'))
     out = run(mode, os.path.join(HERE, 'ref_unittest.py'), [os.path.join(TESTS_DIR, name + '.py')], flags,
               env_extra=EVERYTHING)
     assert 'failures=0 errors=0' in out, out[-2000:]
@@ -117,6 +126,7 @@ def test_np_aes_fips197(mode, parties, flags):
     """BASELINE configs[3]: demos/np_aes.py unchanged; AES-128 of the FIPS-197 example block."""
     if not HAVE_DEMOS:
         pytest.skip('reference demos/ not available (package-only reference)')
+    trim_for_gpu(mode, parties == 3)
     out = run(mode, 'np_aes.py', ['-1'], flags, cwd=DEMOS_DIR, parties=parties, env_extra=EVERYTHING)
     assert f'Ciphertext:  {FIPS197}' in out, out
 
@@ -128,6 +138,7 @@ def test_np_cnnmnist_logits_identical(mode, parties):
     if not HAVE_DEMOS:
         pytest.skip('reference demos/ not available (package-only reference)')
     cwd = DEMOS_DIR
+    trim_for_gpu(mode, parties == 3)
     want = run(mode, 'np_cnnmnist.py', ['1', '0'], ('off',), cwd=cwd, parties=parties)
     got = run(mode, 'np_cnnmnist.py', ['1', '0'], ('install', 'resident'), cwd=cwd, parties=parties,
               env_extra={'MPYC_B200_OPS_MIN_SIZE': '64'})
@@ -141,6 +152,7 @@ def test_np_cnnmnist_logits_identical(mode, parties):
 def test_secure_ops_program_installed_equals_reference(mode, parties, flags):
     """tests/programs/secure_ops.py (input, output, multiply, matmul, comparisons, random bits, fixed-point truncation,
     convert, GF(2^8) inversion, field division): opened results identical with and without the engine."""
+    trim_for_gpu(mode, parties == 3)
     want = run(mode, PROGRAM, ['48'], ('off',), parties=parties)
     got = run(mode, PROGRAM, ['48'], flags, parties=parties, env_extra=EVERYTHING)
     assert 'field division' in got
