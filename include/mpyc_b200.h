@@ -108,6 +108,41 @@ int mpyc_b200_ff_is_sqr(const mpyc_b200_field* f, const void* d_a, uint8_t* d_ou
 int mpyc_b200_ff_matmul(const mpyc_b200_field* f, const void* d_a, const void* d_b, void* d_c,
                         size_t r, size_t k, size_t c, void* stream);
 
+/* ---- protocol-local algebra on raw share values (prime fields) -------------
+ * Between two openings MPyC's protocols compute on the RAW share values in NumPy object loops and reduce when
+ * the result enters a field array (finfields.py:717-725).  These entry points are those steps mod p (reduction is
+ * a ring homomorphism, so the field array that results is the same bit for bit); `&` and `>>` are applied to
+ * canonical residues, as the reference applies them to the canonical result of Runtime.output. */
+
+/* out = a*b + c; d_b == NULL: a*a + c -- np_random_bits' `_r.value**2 + z.value` (runtime.py:4252) */
+int mpyc_b200_ff_fma(const mpyc_b200_field* f, const void* d_a, const void* d_b, const void* d_c, void* d_out,
+                     size_t n, void* stream);
+/* out = a*s + t for canonical host scalars s, t (L limbs each) -- np_random_bits' tail `bits += 1; bits *= (p+1)>>1;
+ * bits <<= f` (runtime.py:4267-4271) is one call with s = 2^f (p+1)/2, t = s; `x << l`, `(x << 1) - 1`, `x + (1 << l)` alike */
+int mpyc_b200_ff_axpb(const mpyc_b200_field* f, const void* d_a, const uint64_t* h_s, const uint64_t* h_t,
+                      void* d_out, size_t n, void* stream);
+/* out = a & (2^nbits - 1) -- `c.value & ((1<<f) - 1)` on an opened value (runtime.py:870,3657) */
+int mpyc_b200_ff_low_bits(const mpyc_b200_field* f, const void* d_a, int nbits, void* d_out, size_t n, void* stream);
+/* d_out_u8[h] = a[h] != 0 (d_out_u8 may be NULL), *d_count = number of non-zero elements --
+ * `mask = _r2.value != 0; np.count_nonzero(mask)` (runtime.py:4254-4255) */
+int mpyc_b200_ff_nonzero(const mpyc_b200_field* f, const void* d_a, uint8_t* d_out_u8, uint64_t* d_count, size_t n,
+                         void* stream);
+/* out[i] = sum_j bits[i*nbits + j] * 2^e(j) mod p over the (n, nbits) row-major matrix d_bits of arbitrary residues
+ * (shares of bits); e(j) = j (descending == 0) or nbits-1-j --
+ * `np.sum(r_bits.value.reshape((n, f)) << np.arange(f), axis=1)` (runtime.py:860, 4415) and np_sgn's
+ * `np.sum(r_bits << np.arange(l-1, -1, -1), axis=1)` (runtime.py:3650-3651).  d_bits / d_out 16-byte aligned. */
+int mpyc_b200_ff_bits_compose(const mpyc_b200_field* f, const void* d_bits, size_t n, int nbits, int descending,
+                              void* d_out, void* stream);
+/* out[j*out_stride + i] = bit e(j) of the canonical residue c[i], as a field element 0 / 1 (out_stride in elements) --
+ * `np.right_shift.outer(c, shifts).T & 1` (runtime.py:3660, 4423) */
+int mpyc_b200_ff_bits_decompose(const mpyc_b200_field* f, const void* d_c, size_t n, int nbits, int descending,
+                                void* d_out, size_t out_stride, void* stream);
+/* Y[k][v][m][n] = B[v] + 'same' 2-D correlation of X[k][r][m][n] with W[v][r][s][s] summed over the r input channels,
+ * mod p, s odd -- demos/np_cnnmnist.py:69-81 (convolvetensor's np.correlate loops followed by field.array(Y)).
+ * All arrays contiguous, row-major. */
+int mpyc_b200_ff_conv2d(const mpyc_b200_field* f, const void* d_x, const void* d_w, const void* d_b, void* d_y,
+                        int k, int r, int m, int n, int v, int s, void* stream);
+
 /* ---- Shamir share generation ---------------------------------------------------------------
  * thresha.np_random_split (mpyc/thresha.py:47-64) with the coefficient matrix C given explicitly:
  *   shares[i][h] = sum_{j=0..t} (i+1)^j * M[j][h] mod p,   M[0] = secrets, M[j] = coeffs row j-1

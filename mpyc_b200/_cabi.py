@@ -56,6 +56,14 @@ _SIGNATURES = {
     'mpyc_b200_ff_sqrt': (c_int, [_field_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_ff_is_sqr': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_ff_matmul': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    'mpyc_b200_ff_fma': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_axpb': (c_int, [_field_p, c_void_p, POINTER(c_uint64), POINTER(c_uint64), c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_low_bits': (c_int, [_field_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_nonzero': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_bits_compose': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
+    'mpyc_b200_ff_bits_decompose': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_conv2d': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
     'mpyc_b200_shamir_split': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,
                                        c_int, c_int, c_void_p]),
     'mpyc_b200_shamir_split_generate': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,

@@ -610,6 +610,115 @@ MPYC_API int mpyc_b200_ff_matmul(const mpyc_b200_field* f, const void* d_a, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// K6: protocol-local algebra on raw share values (local.cuh; prime fields)
+// ---------------------------------------------------------------------------------------
+
+static int prime_only(const mpyc_b200_field* f, const char* what) {
+    if (!f) return fail(MPYC_B200_EINVAL, what);
+    if (f->kind == MPYC_B200_KIND_GF256) return fail(MPYC_B200_EUNSUPPORTED, "protocol-local kernels cover prime fields only");
+    return MPYC_B200_OK;
+}
+
+static bool canonical(const mpyc_b200_field* f, const uint64_t* x) {
+    for (int i = (int)f->fp.L - 1; i >= 0; i--) {
+        if (x[i] < f->fp.p[i]) return true;
+        if (x[i] > f->fp.p[i]) return false;
+    }
+    return false;
+}
+
+MPYC_API int mpyc_b200_ff_fma(const mpyc_b200_field* f, const void* d_a, const void* d_b, const void* d_c, void* d_out,
+                              size_t n, void* stream) {
+    if (int rc = prime_only(f, "ff_fma: field is null")) return rc;
+    if (n && (!d_a || !d_c || !d_out)) return fail(MPYC_B200_EINVAL, "ff_fma: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::fma(f->fp, d_b == nullptr, (const u64*)d_a, (const u64*)d_b, (const u64*)d_c,
+                                            (u64*)d_out, n, st), "ff_fma launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_axpb(const mpyc_b200_field* f, const void* d_a, const uint64_t* h_s, const uint64_t* h_t,
+                               void* d_out, size_t n, void* stream) {
+    if (int rc = prime_only(f, "ff_axpb: field is null")) return rc;
+    if (!h_s || !h_t || (n && (!d_a || !d_out))) return fail(MPYC_B200_EINVAL, "ff_axpb: null argument");
+    if (!canonical(f, h_s) || !canonical(f, h_t)) return fail(MPYC_B200_EINVAL, "ff_axpb: scalars must be canonical residues");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::axpb(f->fp, (const u64*)d_a, (const u64*)h_s, (const u64*)h_t, (u64*)d_out, n, st),
+                             "ff_axpb launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_low_bits(const mpyc_b200_field* f, const void* d_a, int nbits, void* d_out, size_t n, void* stream) {
+    if (int rc = prime_only(f, "ff_low_bits: field is null")) return rc;
+    if (nbits < 0 || (n && (!d_a || !d_out))) return fail(MPYC_B200_EINVAL, "ff_low_bits: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::low_bits(f->fp, (const u64*)d_a, nbits, (u64*)d_out, n, st), "ff_low_bits launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_nonzero(const mpyc_b200_field* f, const void* d_a, uint8_t* d_out_u8, uint64_t* d_count, size_t n,
+                                  void* stream) {
+    if (int rc = prime_only(f, "ff_nonzero: field is null")) return rc;
+    if (!d_count || (n && !d_a)) return fail(MPYC_B200_EINVAL, "ff_nonzero: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::nonzero(f->fp, (const u64*)d_a, d_out_u8, (unsigned long long*)d_count, n, st),
+                             "ff_nonzero launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_bits_compose(const mpyc_b200_field* f, const void* d_bits, size_t n, int nbits, int descending,
+                                       void* d_out, void* stream) {
+    if (int rc = prime_only(f, "ff_bits_compose: field is null")) return rc;
+    if (nbits < 1 || nbits > 4096 || (n && (!d_bits || !d_out))) return fail(MPYC_B200_EINVAL, "ff_bits_compose: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::bits_compose(f->fp, (const u64*)d_bits, (u64*)d_out, n, nbits, descending != 0, st),
+                             "ff_bits_compose launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_bits_decompose(const mpyc_b200_field* f, const void* d_c, size_t n, int nbits, int descending,
+                                         void* d_out, size_t out_stride, void* stream) {
+    if (int rc = prime_only(f, "ff_bits_decompose: field is null")) return rc;
+    if (nbits < 0 || out_stride < n || (n && nbits && (!d_c || !d_out)))
+        return fail(MPYC_B200_EINVAL, "ff_bits_decompose: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nbits == 0) return MPYC_B200_OK;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::bits_decompose(f->fp, (const u64*)d_c, (u64*)d_out, out_stride, n, nbits, descending != 0, st),
+                             "ff_bits_decompose launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_conv2d(const mpyc_b200_field* f, const void* d_x, const void* d_w, const void* d_b, void* d_y,
+                                 int k, int r, int m, int n, int v, int s, void* stream) {
+    if (int rc = prime_only(f, "ff_conv2d: field is null")) return rc;
+    if (k < 0 || r < 1 || m < 1 || n < 1 || v < 1 || s < 1) return fail(MPYC_B200_EINVAL, "ff_conv2d: bad shape");
+    if (s % 2 == 0) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: even filter sizes are not covered");
+    if ((size_t)r * s * s > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: too many taps for one lazy sum");
+    if ((size_t)r * s * s * f->fp.L * 8 > 200u * 1024u) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: filter does not fit shared memory");
+    if (k == 0) return MPYC_B200_OK;
+    if (!d_x || !d_w || !d_b || !d_y) return fail(MPYC_B200_EINVAL, "ff_conv2d: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::conv2d(f->fp, (const u64*)d_x, (const u64*)d_w, (const u64*)d_b, (u64*)d_y, k, r, m, n, v, s, st),
+                             "ff_conv2d launch");
+    });
+}
+
+// ---------------------------------------------------------------------------------------
 // Shamir split
 // ---------------------------------------------------------------------------------------
 

@@ -1207,3 +1207,5 @@ k_count_mismatch(const u64* __restrict__ a, const u64* __restrict__ b, size_t n_
     for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
+
+#include "local.cuh"

@@ -46,6 +46,25 @@ struct Launch {
     static cudaError_t matmul(const FieldParams& fp, const u64* A, const u64* B, u64* C, size_t r, size_t k, size_t c,
                               cudaStream_t st);
     static cudaError_t fill_random(const FieldParams& fp, u64* out, size_t n, u64 base, cudaStream_t st);
+    // ---- K6: protocol-local algebra on raw share values (local.cuh) ----
+    // out = a*b + c (square: a*a + c, b ignored)
+    static cudaError_t fma(const FieldParams& fp, bool square, const u64* a, const u64* b, const u64* c, u64* out, size_t n,
+                           cudaStream_t st);
+    // out = a*s + t for canonical host scalars s, t
+    static cudaError_t axpb(const FieldParams& fp, const u64* a, const u64* s, const u64* t, u64* out, size_t n, cudaStream_t st);
+    // out = a & (2^nbits - 1)
+    static cudaError_t low_bits(const FieldParams& fp, const u64* a, int nbits, u64* out, size_t n, cudaStream_t st);
+    // out8[h] = a[h] != 0 (out8 may be null); *count (device, zeroed by the caller) += non-zero elements
+    static cudaError_t nonzero(const FieldParams& fp, const u64* a, unsigned char* out8, unsigned long long* count, size_t n,
+                               cudaStream_t st);
+    // out[i] = sum_j bits[i*f + j] 2^e(j), e(j) = j or f-1-j
+    static cudaError_t bits_compose(const FieldParams& fp, const u64* bits, u64* out, size_t n, int f, bool descending, cudaStream_t st);
+    // out[j*ostride + i] = bit e(j) of c[i]   (ostride in elements)
+    static cudaError_t bits_decompose(const FieldParams& fp, const u64* c, u64* out, size_t ostride, size_t n, int l, bool descending,
+                                      cudaStream_t st);
+    // Y (k, v, m, n) = 'same' correlation of X (k, r, m, n) with W (v, r, s, s) over the r input channels + B (v); s odd
+    static cudaError_t conv2d(const FieldParams& fp, const u64* X, const u64* W, const u64* B, u64* Y, int k, int r, int m, int n,
+                              int v, int s, cudaStream_t st);
 };
 
 extern template struct Launch<1>;

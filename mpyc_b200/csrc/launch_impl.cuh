@@ -398,3 +398,116 @@ cudaError_t Launch<L>::matmul(const FieldParams& fp, const u64* A, const u64* B,
     if (part) cudaFreeAsync(part, st);
     return e;
 }
+
+// ---- K6: protocol-local algebra (local.cuh) ---------------------------------------------------
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int L>
+cudaError_t Launch<L>::fma(const FieldParams& fp, bool square, const u64* a, const u64* b, const u64* c, u64* out, size_t n,
+                           cudaStream_t st) {
+    const bool vec = L != 3 && aligned32(a) && aligned32(c) && aligned32(out) && (square || aligned32(b));
+    constexpr int E = VecItem<L>::E;
+#define M(K)                                                                                                             \
+    if constexpr (L != 3) {                                                                                              \
+        if (vec) {                                                                                                       \
+            if (square) return launch_kernel(k_fma<L, K, true, true>, (n + E - 1) / E, 0, st, fp, a, b, c, out, n);      \
+            return launch_kernel(k_fma<L, K, false, true>, (n + E - 1) / E, 0, st, fp, a, b, c, out, n);                 \
+        }                                                                                                                \
+    }                                                                                                                    \
+    if (square) return launch_kernel(k_fma<L, K, true, false>, n, 0, st, fp, a, b, c, out, n);                           \
+    return launch_kernel(k_fma<L, K, false, false>, n, 0, st, fp, a, b, c, out, n)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::axpb(const FieldParams& fp, const u64* a, const u64* s, const u64* t, u64* out, size_t n, cudaStream_t st) {
+    AffineParams ap = {};
+    bool unit = s[0] == 1;
+    for (int i = 0; i < L; i++) {
+        ap.s[i] = s[i];
+        ap.t[i] = t[i];
+        if (i && s[i]) unit = false;
+    }
+    const bool vec = L != 3 && aligned32(a) && aligned32(out);
+    constexpr int E = VecItem<L>::E;
+#define M(K)                                                                                                             \
+    if constexpr (L != 3) {                                                                                              \
+        if (vec) return launch_kernel(k_axpb<L, K, true>, (n + E - 1) / E, 0, st, fp, ap, (int)unit, a, out, n);         \
+    }                                                                                                                    \
+    return launch_kernel(k_axpb<L, K, false>, n, 0, st, fp, ap, (int)unit, a, out, n)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::low_bits(const FieldParams& fp, const u64* a, int nbits, u64* out, size_t n, cudaStream_t st) {
+    ScalarParam mask = {};
+    for (int i = 0; i < L; i++) {
+        const int lo = 64 * i;
+        mask.v[i] = nbits >= lo + 64 ? ~0ull : (nbits > lo ? ((1ull << (nbits - lo)) - 1) : 0ull);
+    }
+    constexpr int E = VecItem<L>::E;
+    if constexpr (L != 3) {
+        if (aligned32(a) && aligned32(out)) return launch_kernel(k_low_bits<L, true>, (n + E - 1) / E, 0, st, mask, a, out, n);
+    }
+    return launch_kernel(k_low_bits<L, false>, n, 0, st, mask, a, out, n);
+}
+
+template <int L>
+cudaError_t Launch<L>::nonzero(const FieldParams& fp, const u64* a, unsigned char* out8, unsigned long long* count, size_t n,
+                               cudaStream_t st) {
+    if (L % 2 == 0 && !aligned16(a)) return cudaErrorMisalignedAddress;
+    return launch_kernel(k_nonzero<L>, n, 0, st, a, out8, count, n);
+}
+
+template <int L>
+cudaError_t Launch<L>::bits_compose(const FieldParams& fp, const u64* bits, u64* out, size_t n, int f, bool descending,
+                                    cudaStream_t st) {
+    if (L % 2 == 0 && (!aligned16(bits) || !aligned16(out))) return cudaErrorMisalignedAddress;
+    constexpr size_t smem = ComposeCfg<L>::SMEM;
+#define M(K)                                                                                                  \
+    {                                                                                                         \
+        auto kernel = k_bits_compose<L, K>;                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                       \
+        return launch_kernel(kernel, n, smem, st, fp, bits, out, n, f, (int)descending);                      \
+    }
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::bits_decompose(const FieldParams& fp, const u64* c, u64* out, size_t ostride, size_t n, int l,
+                                      bool descending, cudaStream_t st) {
+    constexpr int E = VecItem<L>::E;
+    if constexpr (L != 3) {
+        if (aligned32(c) && aligned32(out) && (ostride * L) % 4 == 0)
+            return launch_kernel(k_bits_decompose<L, true>, (n + E - 1) / E, 0, st, c, out, ostride, n, l, (int)descending);
+    }
+    return launch_kernel(k_bits_decompose<L, false>, n, 0, st, c, out, ostride, n, l, (int)descending);
+}
+
+template <int L>
+cudaError_t Launch<L>::conv2d(const FieldParams& fp, const u64* X, const u64* W, const u64* B, u64* Y, int k, int r, int m,
+                              int n, int v, int s, cudaStream_t st) {
+    const size_t smem = (size_t)r * s * s * 2 * L * sizeof(u32);
+    const size_t ptiles = ((size_t)m * n + MPYC_THREADS - 1) / MPYC_THREADS;
+    const size_t items = (size_t)k * v * ptiles;
+#define M(K)                                                                                                      \
+    {                                                                                                             \
+        auto kernel = k_conv2d<L, K>;                                                                             \
+        if (smem > 48u * 1024u) {                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                       \
+        }                                                                                                         \
+        return launch_kernel(kernel, items * MPYC_THREADS, smem, st, fp, X, W, B, Y, k, r, m, n, v, s);           \
+    }
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}

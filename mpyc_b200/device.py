@@ -323,3 +323,84 @@ def matmul(ctx, A, B, r, k, c):
     out = DeviceArray.empty(ctx, r * c, A.t.device)
     check(lib.mpyc_b200_ff_matmul(ctx.handle, A.ptr, B.ptr, out.ptr, r, k, c, _stream_ptr()))
     return out
+
+
+# ---- protocol-local algebra on raw share values (csrc/local.cuh) -----------------------------
+
+def fma(a: DeviceArray, b, c: DeviceArray):
+    """a*b + c, or a*a + c when b is None -- np_random_bits' `_r.value**2 + z.value` (mpyc/runtime.py:4252)."""
+    if c.ctx is not a.ctx or c.n != a.n or (b is not None and (b.ctx is not a.ctx or b.n != a.n)):
+        raise ValueError('operands must share field and length')
+    for x in (a, b, c):
+        if x is not None:
+            x._check_contiguous()
+    out = a._like()
+    check(lib.mpyc_b200_ff_fma(a.ctx.handle, a.ptr, b.ptr if b is not None else ctypes.c_void_p(0), c.ptr, out.ptr, a.n,
+                               _stream_ptr()))
+    return out
+
+
+def axpb(a: DeviceArray, s, t):
+    """a*s + t for public integers s, t (reduced here) -- the affine steps on raw values: `bits += 1; bits *= (p+1)>>1;
+    bits <<= f` (mpyc/runtime.py:4267-4271), `(r_bits << 1) - 1` (:3646), `x + (1 << l)` (:3656)."""
+    a._check_contiguous()
+    q = a.ctx.order
+    out = a._like()
+    check(lib.mpyc_b200_ff_axpb(a.ctx.handle, a.ptr, a.ctx.scalar_limbs(int(s) % q), a.ctx.scalar_limbs(int(t) % q), out.ptr,
+                                a.n, _stream_ptr()))
+    return out
+
+
+def low_bits(a: DeviceArray, nbits):
+    """a & (2^nbits - 1) on canonical residues -- `c.value & ((1<<f) - 1)` (mpyc/runtime.py:870, 3657)."""
+    a._check_contiguous()
+    out = a._like()
+    check(lib.mpyc_b200_ff_low_bits(a.ctx.handle, a.ptr, int(nbits), out.ptr, a.n, _stream_ptr()))
+    return out
+
+
+def nonzero(a: DeviceArray, want_mask=True):
+    """(bool tensor a != 0 or None, number of non-zero elements) -- `_r2.value != 0` (mpyc/runtime.py:4254-4255)."""
+    a._check_contiguous()
+    mask = torch.empty(a.n, dtype=torch.uint8, device=a.t.device) if want_mask else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=a.t.device)
+    check(lib.mpyc_b200_ff_nonzero(a.ctx.handle, a.ptr, ctypes.c_void_p(mask.data_ptr() if want_mask else 0),
+                                   ctypes.c_void_p(cnt.data_ptr()), a.n, _stream_ptr()))
+    return (mask.bool() if want_mask else None), int(cnt.item())
+
+
+def bits_compose(bits: DeviceArray, n, f, descending=False):
+    """out[i] = sum_j bits[i*f + j] << e(j) mod p, e(j) = j or f-1-j: `np.sum(r_bits.reshape((n, f)) << shifts, axis=1)`
+    (mpyc/runtime.py:860, 3650-3651, 4415).  bits: n*f residues, row-major."""
+    if bits.n != n * f:
+        raise ValueError('bits_compose: buffer does not hold n*f elements')
+    bits._check_contiguous()
+    out = DeviceArray.empty(bits.ctx, n, bits.t.device)
+    if n and f:
+        check(lib.mpyc_b200_ff_bits_compose(bits.ctx.handle, bits.ptr, n, f, 1 if descending else 0, out.ptr, _stream_ptr()))
+    elif n:
+        out.t.zero_()
+    return out
+
+
+def bits_decompose(c: DeviceArray, l, descending=False):
+    """DeviceMatrix (l, n): row j = bit e(j) of every c[i] as a field element: `np.right_shift.outer(c, shifts).T & 1`
+    (mpyc/runtime.py:3659-3660, 4422-4423)."""
+    c._check_contiguous()
+    out = DeviceMatrix.empty(c.ctx, l, c.n, c.t.device)
+    if l and c.n:
+        check(lib.mpyc_b200_ff_bits_decompose(c.ctx.handle, c.ptr, c.n, l, 1 if descending else 0, out.ptr, out.stride,
+                                              _stream_ptr()))
+    return out
+
+
+def conv2d(X: DeviceArray, W: DeviceArray, B: DeviceArray, k, r, m, n, v, s):
+    """np_cnnmnist's convolvetensor body (demos/np_cnnmnist.py:69-81) mod p: X (k,r,m,n), W (v,r,s,s), B (v) row-major
+    -> Y (k,v,m,n)."""
+    if X.n != k * r * m * n or W.n != v * r * s * s or B.n != v:
+        raise ValueError('conv2d: shapes do not match the buffers')
+    for x in (X, W, B):
+        x._check_contiguous()
+    out = DeviceArray.empty(X.ctx, k * v * m * n, X.t.device)
+    check(lib.mpyc_b200_ff_conv2d(X.ctx.handle, X.ptr, W.ptr, B.ptr, out.ptr, k, r, m, n, v, s, _stream_ptr()))
+    return out

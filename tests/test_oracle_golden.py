@@ -181,3 +181,38 @@ def test_prss_with_any_prf_bound(case):
         assert orc.prss_share_zero_list_order(F, m, i, prl0, n) == unhex(party['zero_list'])
         if t:
             assert orc.prss_share_zero_np_order(F, m, i, prl0, n) == unhex(party['zero_np'])
+
+
+# ---- protocol-local algebra: oracle vs the reference's own expressions -----------------------
+
+LOCAL = load('local.json')
+
+
+@pytest.mark.parametrize('case', LOCAL['algebra'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_{c['p'][-4:]}")
+def test_local_algebra(case):
+    p = int(case['p'], 16)
+    a, b, c = unhex(case['a']), unhex(case['b']), unhex(case['c'])
+    assert orc.local_fma(p, a, a, c) == unhex(case['square_add'])
+    assert orc.local_fma(p, a, b, c) == unhex(case['mul_add'])
+    assert orc.local_nonzero(a) == case['nonzero']
+    for f in (0, 6):
+        s = ((p + 1) >> 1 << f) % p
+        assert orc.local_axpb(p, a, s, s) == unhex(case[f'bits_tail_f{f}'])
+    assert orc.local_axpb(p, a, 2, -1) == unhex(case['s_sign'])
+    for key in case:
+        if key.startswith('low_bits_'):
+            assert orc.local_low_bits(c, int(key[9:])) == unhex(case[key])
+    for comp in case['compose']:
+        bits = unhex(comp['bits'])
+        assert orc.local_bits_compose(p, bits, comp['n'], comp['f']) == unhex(comp['ascending'])
+        assert orc.local_bits_compose(p, bits, comp['n'], comp['f'], descending=True) == unhex(comp['descending'])
+    for dec in case['decompose']:
+        assert orc.local_bits_decompose(c, dec['l']) == unhex(dec['ascending'])
+        assert orc.local_bits_decompose(c, dec['l'], descending=True) == unhex(dec['descending'])
+
+
+@pytest.mark.parametrize('case', LOCAL['conv'], ids=lambda c: f"p{int(c['p'],16).bit_length()}_{'x'.join(map(str, c['shape']))}")
+def test_local_conv2d(case):
+    p = int(case['p'], 16)
+    k, r, m, n, v, s = case['shape']
+    assert orc.local_conv2d(p, unhex(case['X']), unhex(case['W']), unhex(case['B']), k, r, m, n, v, s) == unhex(case['Y'])
