@@ -73,6 +73,7 @@ def _install_finfields(finfields_module, min_size):
     """PrimeFieldArray._reciprocal/_pow/_sqrt/_is_sqr -> batched kernels for covered primes and arrays of
     at least `min_size` elements (below that the per-call overhead of a launch outweighs the gain)."""
     from mpyc_b200 import finfields as ours
+    from mpyc_b200 import resident as _res
     cls = finfields_module.PrimeFieldArray
     orig = {name: cls.__dict__[name] for name in ('_reciprocal', '_pow', '_sqrt', '_is_sqr')}
     _saved_ff.update({'cls': cls, **orig})
@@ -90,6 +91,11 @@ def _install_finfields(finfields_module, min_size):
 
     def _sqrt(klass, a, INV=False):
         theirs = lambda x, INV=False: orig['_sqrt'].__func__(klass, x, INV=INV)   # noqa: E731
+        if type(a) is _res.ModValue:
+            # np_random_bits: `field.array._sqrt(r2, INV=True)` on an opened value (runtime.py:4265) stays on the device
+            if a.store is not None and a.exact and klass.field.modulus & 3 == 3:
+                return a.sqrt(INV=INV)
+            a = a._materialise()
         return ours.sqrt(klass, a, INV=INV, _fallback=theirs) if use_gpu(klass, a) else theirs(a, INV=INV)
 
     def _is_sqr(klass, a):
@@ -113,7 +119,7 @@ def _install_operators(finfields_module, min_size):
     resident.min_size = int(min_size)
     cls = finfields_module.FiniteFieldArray
     names = ('__init__', '__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__neg__', '__matmul__',
-             '__rmatmul__')
+             '__rmatmul__', '__lshift__', '__rshift__', '__ilshift__', '__irshift__')
     orig = {name: cls.__dict__[name] for name in names}
     _saved_ops.update({'cls': cls, 'module': finfields_module, **orig})
     MISS = resident._MISS
@@ -125,8 +131,8 @@ def _install_operators(finfields_module, min_size):
         if lv is not None:
             slot_set(self, lv)         # canonical residues by construction: nothing to check, nothing to copy
             return
-        if type(value) is resident.LimbValue:
-            value = value._ints
+        if type(value) is resident.LimbValue or type(value) is resident.ModValue:
+            value = value._ints        # already an object array (canonical residues)
         orig['__init__'](self, value, check=check, copy=copy)
 
     def make(op, name, reflected=False):
@@ -149,6 +155,24 @@ def _install_operators(finfields_module, min_size):
         r = resident.matmul(self, other, reflected=True)
         return orig['__rmatmul__'](self, other) if r is MISS else r
 
+    def make_shift(name, right, inplace):
+        # `a << n` = a * 2^n, `a >> n` = a * (2^n)^-1 for an integer n (finfields.py:1227-1271); limb-backed arrays only
+        def method(self, other):
+            r = resident.shift(self, other, right)
+            if r is MISS:
+                return orig[name](self, other)
+            if inplace:
+                slot_set(self, resident.raw_value(r))
+                return self
+            return r
+        method.__name__ = name
+        method.__doc__ = orig[name].__doc__
+        return method
+
+    cls.__lshift__ = make_shift('__lshift__', False, False)
+    cls.__rshift__ = make_shift('__rshift__', True, False)
+    cls.__ilshift__ = make_shift('__ilshift__', False, True)
+    cls.__irshift__ = make_shift('__irshift__', True, True)
     cls.value = value_property
     cls.__init__ = __init__
     cls.__add__ = make(_cabi.OP_ADD, '__add__')
@@ -163,7 +187,7 @@ def _install_operators(finfields_module, min_size):
 
 
 def install(thresha_module=None, strict=False, device=0, finfields_module=None, finfields_min_size=256,
-            limb_wire=False, min_size=0, operators=False, operators_min_size=1024, resident=False):
+            limb_wire=False, min_size=0, operators=False, operators_min_size=1024, resident=False, local_algebra=True):
     """Patch `mpyc.thresha` (or the module passed in); with finfields_module also the batched
     inverse/pow/sqrt/is_sqr of PrimeFieldArray.  limb_wire=True: shares travel between parties as limb
     buffers (mpyc_b200.wire; every party must run mpyc_b200).  min_size > 0: calls on fewer elements are left to
@@ -172,7 +196,8 @@ def install(thresha_module=None, strict=False, device=0, finfields_module=None, 
     operators=True: FiniteFieldArray's + - * neg @ (finfields.py:1056-1146) run on the K1 / K1c kernels for operands
     of at least operators_min_size elements (mpyc_b200.resident).  resident=True (implies operators and limb_wire):
     recombined / pseudorandom shares stay limb-backed in HBM between protocol steps; Python ints are created only
-    where a value is actually looked at (input, output, raw-value arithmetic).
+    where a value is actually looked at (input, output, raw-value arithmetic).  local_algebra (with resident): the raw-value
+    arithmetic of Runtime.np_random_bits / np_trunc / np_sgn runs mod p on the device as well (resident.ModValue, K6 kernels).
     Returns the list of patched names."""
     if thresha_module is None:
         import mpyc.thresha as thresha_module
@@ -186,6 +211,7 @@ def install(thresha_module=None, strict=False, device=0, finfields_module=None, 
         _install_operators(finfields_module, operators_min_size)
     from mpyc_b200 import resident as res
     res.resident = bool(resident)
+    res.local_algebra = bool(local_algebra and resident)
     res.backend.device = device
     engine.device = device
     engine.limb_wire = bool(limb_wire or resident)

@@ -37,7 +37,7 @@ import sys
 
 resident = False      # np_recombine / PRSS results stay limb-backed (set by install(resident=True))
 min_size = 1024       # plain object-array operands of fewer elements are left to the reference's operators
-calls = {'limb_ops': 0, 'materialised': 0, 'packed': 0}    # counters (tests, profiling)
+calls = {'limb_ops': 0, 'materialised': 0, 'packed': 0, 'mod_values': 0}    # counters (tests, profiling)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -103,6 +103,38 @@ class CudaBackend:
         rows = [self.to_store(ctx, r) for r in rows]
         out = dev.shamir_recombine(ctx, xs, rows, list(pts))
         return [out.row(r) for r in range(len(pts))]
+
+    # ---- protocol-local algebra (csrc/local.cuh), used by ModValue ----
+    def fma(self, ctx, a, b, c):
+        dev, _ = self._dev()
+        return dev.fma(self.to_store(ctx, a), None if b is None else self.to_store(ctx, b), self.to_store(ctx, c))
+
+    def axpb(self, ctx, a, s, t):
+        dev, _ = self._dev()
+        return dev.axpb(self.to_store(ctx, a), s, t)
+
+    def low_bits(self, ctx, a, nbits):
+        dev, _ = self._dev()
+        return dev.low_bits(self.to_store(ctx, a), nbits)
+
+    def nonzero(self, ctx, a):
+        """(bool ndarray a != 0, count)"""
+        dev, _ = self._dev()
+        mask, count = dev.nonzero(self.to_store(ctx, a))
+        return mask.cpu().numpy(), count
+
+    def bits_compose(self, ctx, bits, n, f, descending):
+        dev, _ = self._dev()
+        return dev.bits_compose(self.to_store(ctx, bits), n, f, descending)
+
+    def sqrt(self, ctx, a, INV):
+        return self.to_store(ctx, a).sqrt(INV=INV)
+
+    def slice(self, ctx, store, start, stop):
+        if isinstance(store, np.ndarray):
+            return store[start:stop]
+        dev, _ = self._dev()
+        return dev.DeviceArray(ctx, store.t[start:stop])
 
 
 backend = CudaBackend()
@@ -251,6 +283,343 @@ for _name in ('getitem', 'setitem', 'iter', 'contains', 'add', 'radd', 'iadd', '
     setattr(LimbValue, f'__{_name}__', _delegate(f'__{_name}__'))
 
 
+
+# ---------------------------------------------------------------------------------------------
+# ModValue: raw-value algebra of whitelisted protocol functions, mod p on the device
+# ---------------------------------------------------------------------------------------------
+
+class ModValue:
+    """What `array.value` returns to np_random_bits / np_trunc / np_sgn (`_MOD_SOURCES`) while the elements are limbs.
+
+    Those functions compute on raw share values with NumPy object arithmetic -- `_r.value**2 + z.value`,
+    `np.sum(r_bits.value.reshape((n, f)) << np.arange(f), axis=1)`, `ar_modf + (1 << l-1) + (r_divf << f)`,
+    `c.value & ((1<<f) - 1)`, `bits += 1; bits *= (p+1) >> 1` (mpyc/runtime.py:856-872, 3644-3658, 4252-4271) -- over
+    the integers, and reduce when the result enters `Zp.array(...)`.  A ModValue runs the same expressions mod p on the
+    K1 / K6 kernels: reduction is a ring homomorphism, so the field array that comes out is identical.  Operations that
+    are not ring operations (`&`, `!= 0`, `%` by a power of two) are only accepted on EXACT values -- residues read
+    straight from a field array (an opened value) -- where the canonical residue IS the reference's integer; on a
+    modular intermediate they raise instead of returning something that could differ.
+
+    Scalar steps are kept as a pending affine map (value = store * s + t) and applied by one k_axpb launch when the
+    elements are needed.  Anything not covered here turns the value into the settled object array (canonical
+    residues) and continues with NumPy, like LimbValue."""
+
+    __slots__ = ('ctx', 'shape', 'store', '_s', '_t', '_sq', 'exact', '_ints')
+    __hash__ = None
+    dtype = np.dtype(object)
+
+    def __init__(self, ctx, store, shape, exact=False, s=1, t=0, sq=False):
+        self.ctx, self.store, self.shape = ctx, store, tuple(shape)
+        self._s, self._t, self._sq = s, t, sq
+        self.exact = exact and s == 1 and t == 0 and not sq
+        self._ints = None
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError('len() of unsized object')
+        return self.shape[0]
+
+    def _flush(self):
+        """Apply the pending square / affine map; afterwards store holds the canonical residues of the value."""
+        if self._sq:
+            self.store = backend.binop(self.ctx, _cabi.OP_MUL, self.store, self.store)
+            self._sq = False
+            calls['limb_ops'] += 1
+        if self._s != 1 or self._t != 0:
+            self.store = backend.axpb(self.ctx, self.store, self._s, self._t)
+            self._s, self._t = 1, 0
+            calls['limb_ops'] += 1
+        return self.store
+
+    def limb_value(self):
+        """The value as a LimbValue (for FiniteFieldArray.__init__), or None once it has become an object array."""
+        if self.store is None:
+            return None
+        return LimbValue(self.ctx, self._flush(), self.shape)
+
+    def _new(self, store, shape=None, exact=False, s=1, t=0, sq=False):
+        return ModValue(self.ctx, store, self.shape if shape is None else shape, exact, s, t, sq)
+
+    def _materialise(self):
+        if self._ints is None:
+            lv = LimbValue(self.ctx, self._flush(), self.shape)
+            self._ints = lv._materialise()
+            self.store = None
+        return self._ints
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._materialise()
+        if dtype is not None and dtype != object:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        return getattr(self._materialise(), name)
+
+    def __repr__(self):
+        if self.store is None:
+            return repr(self._ints)
+        return f'ModValue(shape={self.shape}, exact={self.exact}, {self.ctx!r})'
+
+    def reshape(self, *shape, **kwargs):
+        if self.store is None or kwargs:
+            return self._materialise().reshape(*shape, **kwargs)
+        return self._new(self.store, _norm_shape(self.size, shape), self.exact, self._s, self._t, self._sq)
+
+    def ravel(self, *args, **kwargs):
+        if self.store is None or args or kwargs:
+            return self._materialise().ravel(*args, **kwargs)
+        return self.reshape(-1)
+
+    flatten = ravel
+
+    def copy(self, *args, **kwargs):
+        if self.store is None:
+            return self._ints.copy(*args, **kwargs)
+        return self._new(self.store, None, self.exact, self._s, self._t, self._sq)
+
+    def __getitem__(self, key):
+        if (self.store is not None and len(self.shape) == 1 and isinstance(key, slice) and key.step in (None, 1)):
+            start, stop, _ = key.indices(self.shape[0])
+            stop = max(stop, start)
+            return self._new(backend.slice(self.ctx, self._flush(), start, stop), (stop - start,), self.exact)
+        return self._materialise()[key]
+
+    def __setitem__(self, key, value):
+        self._materialise()[key] = value
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    # ---- ring operations ----------------------------------------------------------------------------
+    def _scalar(self, x):
+        return int(x) if isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_)) else None
+
+    def _other_store(self, other):
+        """Store of an array operand of the same shape (packed from ints if need be), else None."""
+        if type(other) is ModValue:
+            if other.store is None:
+                other = other._ints
+            elif other.ctx is self.ctx and other.shape == self.shape:
+                return other._flush()
+            else:
+                return None
+        if type(other) is LimbValue:
+            if other.store is not None:
+                return other.store if (other.ctx is self.ctx and other.shape == self.shape) else None
+            other = other._ints
+        if isinstance(other, np.ndarray) and other.shape == self.shape and other.dtype.kind in 'Oiu' and other.size:
+            calls['packed'] += 1
+            if other.dtype != object:
+                other = other.astype(object)
+            return codec.ints_to_limbs(other.reshape(-1), self.ctx)      # reduces: raw values may be negative / >= p
+        return None
+
+    def _ring(self, other, op, reflected=False):
+        """self (op) other, op in '+', '-', '*'; reflected: other (op) self."""
+        if self.store is None:
+            return _NUMPY_OPS[op](other, self._ints) if reflected else _NUMPY_OPS[op](self._ints, other)
+        p = self.ctx.modulus
+        k = self._scalar(other)
+        if k is not None:
+            s, t = self._s, self._t
+            if self._sq:
+                self._flush()
+                s, t = 1, 0
+            if op == '+':
+                t = (t + k) % p
+            elif op == '-':
+                s, t = ((-s) % p, (k - t) % p) if reflected else (s, (t - k) % p)
+            else:
+                s, t = (s * k) % p, (t * k) % p
+            return self._new(self.store, None, False, s, t)
+        b = self._other_store(other)
+        if b is None:
+            a = self._materialise()
+            return _NUMPY_OPS[op](other, a) if reflected else _NUMPY_OPS[op](a, other)
+        calls['limb_ops'] += 1
+        if op == '+' and self._sq and self._s == 1 and self._t == 0:                      # a*a + c in one pass
+            return self._new(backend.fma(self.ctx, self.store, None, b))
+        a = self._flush()
+        code = {'+': _cabi.OP_ADD, '-': _cabi.OP_SUB, '*': _cabi.OP_MUL}[op]
+        x, y = (b, a) if reflected else (a, b)
+        return self._new(backend.binop(self.ctx, code, x, y))
+
+    def __add__(self, other):
+        return self._ring(other, '+')
+
+    __radd__ = __iadd__ = __add__
+
+    def __sub__(self, other):
+        return self._ring(other, '-')
+
+    __isub__ = __sub__
+
+    def __rsub__(self, other):
+        return self._ring(other, '-', reflected=True)
+
+    def __mul__(self, other):
+        return self._ring(other, '*')
+
+    __rmul__ = __imul__ = __mul__
+
+    def __neg__(self):
+        return self._ring(-1, '*')
+
+    def __pos__(self):
+        return self
+
+    def __pow__(self, e):
+        if self.store is not None and self._scalar(e) == 2 and not self._sq:
+            self._flush()
+            return self._new(self.store, None, False, sq=True)
+        return self._materialise() ** e
+
+    def __lshift__(self, k):
+        if self.store is None:
+            return self._ints << k
+        n = self._scalar(k)
+        if n is not None and n >= 0:
+            return self._ring(pow(2, n, self.ctx.modulus), '*')
+        if (isinstance(k, np.ndarray) and k.ndim == 1 and k.dtype.kind in 'iu' and len(self.shape) == 2
+                and k.shape[0] == self.shape[1] and k.shape[0] > 0):
+            f = k.shape[0]
+            if np.array_equal(k, np.arange(f)):
+                return _ShiftedBits(self, k, False)
+            if np.array_equal(k, np.arange(f - 1, -1, -1)):
+                return _ShiftedBits(self, k, True)
+        return self._materialise() << k
+
+    __ilshift__ = __lshift__
+
+    def sqrt(self, INV=False):
+        """PrimeFieldArray._sqrt on the limbs (Blum primes; finfields.py:1424-1438): an exact value again."""
+        return self._new(backend.sqrt(self.ctx, self._flush(), INV), None, True)
+
+    # ---- operations that are not ring operations: exact values only -----------------------------------------
+    def _need_exact(self, what):
+        if not self.exact:
+            raise AssertionError(f'mpyc_b200: {what} on a modular intermediate (only opened / stored residues are exact)')
+
+    def __and__(self, mask):
+        if self.store is None:
+            return self._ints & mask
+        m = self._scalar(mask)
+        if m is not None and m >= 0 and (m + 1) & m == 0:           # 2^b - 1
+            self._need_exact('bit mask')
+            calls['limb_ops'] += 1
+            return self._new(backend.low_bits(self.ctx, self.store, m.bit_length()), None, True)
+        self._need_exact('bitwise and')
+        return self._materialise() & mask
+
+    __rand__ = __and__
+
+    def __mod__(self, q):
+        if self.store is None:
+            return self._ints % q
+        m = self._scalar(q)
+        if m == self.ctx.modulus:
+            return self if not self._sq and self._s == 1 and self._t == 0 else self._new(self._flush())
+        if m is not None and m > 0 and m & (m - 1) == 0:
+            return self & (m - 1)
+        self._need_exact('%')
+        return self._materialise() % q
+
+    __imod__ = __mod__
+
+    def __ne__(self, other):
+        if self.store is not None and self._scalar(other) == 0:
+            self._need_exact('!= 0')
+            mask, _ = backend.nonzero(self.ctx, self.store)
+            return np.asarray(mask, dtype=bool).reshape(self.shape)
+        if self.store is not None:
+            self._need_exact('comparison')
+        return self._materialise() != other
+
+    def __eq__(self, other):
+        if self.store is not None:
+            self._need_exact('comparison')
+        return self._materialise() == other
+
+    # ---- NumPy protocol: `ndarray (op) ModValue` and direct ufunc calls -----------------------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method == '__call__' and len(inputs) == 2 and not kwargs and ufunc in _UFUNC_OPS:
+            a, b = inputs
+            if a is self:
+                return self._ring(b, _UFUNC_OPS[ufunc]) if ufunc is not np.left_shift else self.__lshift__(b)
+            if ufunc is not np.left_shift:
+                return self._ring(a, _UFUNC_OPS[ufunc], reflected=True)
+        if method in ('__call__', 'outer') and ufunc in (np.right_shift, np.bitwise_and, np.not_equal, np.equal, np.remainder):
+            for x in inputs:
+                if type(x) is ModValue and x.store is not None:
+                    x._need_exact(ufunc.__name__)
+        args = [x._materialise() if type(x) in (ModValue, LimbValue) else x for x in inputs]
+        if 'out' in kwargs:
+            kwargs['out'] = tuple(x._materialise() if type(x) in (ModValue, LimbValue) else x for x in kwargs['out'])
+        return getattr(ufunc, method)(*args, **kwargs)
+
+
+import operator as _operator   # noqa: E402
+
+_NUMPY_OPS = {'+': _operator.add, '-': _operator.sub, '*': _operator.mul}
+_UFUNC_OPS = {np.add: '+', np.subtract: '-', np.multiply: '*', np.left_shift: '<<'}
+
+
+def _delegate_mod(name):
+    def method(self, *args, **kwargs):
+        return getattr(self._materialise(), name)(*args, **kwargs)
+    method.__name__ = name
+    return method
+
+
+for _name in ('contains', 'matmul', 'rmatmul', 'imatmul', 'rmod', 'floordiv', 'rfloordiv', 'ifloordiv', 'truediv', 'rtruediv',
+              'itruediv', 'rpow', 'ipow', 'abs', 'invert', 'rlshift', 'rshift', 'rrshift', 'irshift', 'iand', 'or', 'ror', 'ior',
+              'xor', 'rxor', 'ixor', 'lt', 'le', 'gt', 'ge', 'bool', 'int', 'index', 'float', 'divmod', 'rdivmod', 'str',
+              'format'):
+    setattr(ModValue, f'__{_name}__', _delegate_mod(f'__{_name}__'))
+
+
+class _ShiftedBits:
+    """`value.reshape((n, f)) << shifts` with shifts = arange(f) or arange(f-1, -1, -1): summed along axis 1 by the
+    k_bits_compose kernel (runtime.py:860, 3650-3651); any other use evaluates the shift on the object array."""
+
+    def __init__(self, base, shifts, descending):
+        self.base, self.shifts, self.descending = base, shifts, descending
+
+    def sum(self, axis=None, out=None, **kwargs):
+        b = self.base
+        if b.store is not None and axis in (1, -1) and out is None and not kwargs:
+            n, f = b.shape
+            calls['limb_ops'] += 1
+            return b._new(backend.bits_compose(b.ctx, b._flush(), n, f, self.descending), (n,))
+        return self._eval().sum(axis=axis, out=out, **kwargs)
+
+    def _eval(self):
+        return self.base._materialise() << self.shifts
+
+    def __array__(self, dtype=None, copy=None):
+        return self._eval()
+
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        return getattr(self._eval(), name)
+
+
 def _from_wire(modulus, binary, shape, data):
     ctx = context_for(modulus, binary=binary)
     limbs = codec.wire_to_limbs(data, ctx)
@@ -267,9 +636,11 @@ def _from_ints(ints):
 
 
 def as_limb_value(value):
-    """LimbValue for a limb-backed LimbValue / ShareRow, else None."""
+    """LimbValue for a limb-backed LimbValue / ShareRow / ModValue, else None."""
     if type(value) is LimbValue:
         return value if value.store is not None else None
+    if type(value) is ModValue:
+        return value.limb_value()
     if type(value) is ShareRow and value._ints is None:
         return LimbValue(value.ctx, value.limbs, (len(value),), value._poly)
     return None
@@ -281,7 +652,18 @@ def as_limb_value(value):
 
 _slot = None            # the member descriptor FiniteFieldArray.__dict__['value'] of the patched finfields module
 _lazy_codes = set()     # code objects that may see a LimbValue (see module docstring)
+_mod_codes = set()      # code objects that get a ModValue: their arithmetic on raw values runs mod p on the device
 _runtime_seen = [False]
+local_algebra = True    # hand ModValues to the functions below (install(local_algebra=...))
+
+# Runtime methods whose raw-value algebra is known to be ring operations ending in `Zp.array(...)` (plus `&` / `!= 0` on
+# opened, canonical values): sha256 of their source in lschoe/mpyc v0.11.2.  A function whose source differs is not
+# whitelisted -- its `.value` reads settle to the reference's object arrays as for every other reader.
+_MOD_SOURCES = {
+    'np_random_bits': '26b092e612b3091d4ac89237593b4069fa5eee590abcbe21077d13b992bf3868',     # runtime.py:4187-4273
+    'np_trunc': 'e6354dbb71d6369d8bef9b065bef0cb65b1dc55631634954792f7945e087e3ad',           # runtime.py:838-872
+    'np_sgn': '936eb16da844a41f636537f44306b80fff9aea3834ba205e187e6ba5a24547ad',             # runtime.py:3622-3694
+}
 
 
 def raw_value(arr):
@@ -304,6 +686,17 @@ def _collect_runtime_codes(finfields_module):
         fn = getattr(fn, '__wrapped__', fn)
         if fn is not None and hasattr(fn, '__code__'):
             _lazy_codes.add(fn.__code__)
+    if local_algebra:
+        import hashlib
+        import inspect
+        for name, digest in _MOD_SOURCES.items():
+            fn = getattr(rt.Runtime, name, None)
+            fn = getattr(fn, '__wrapped__', fn)
+            try:
+                if hashlib.sha256(inspect.getsource(fn).encode()).hexdigest() == digest:
+                    _mod_codes.add(fn.__code__)
+            except (OSError, TypeError):
+                pass
     _runtime_seen[0] = True
 
 
@@ -313,6 +706,7 @@ def make_value_property(finfields_module):
     _slot = cls.__dict__['value']
     slot_get, slot_set = _slot.__get__, _slot.__set__
     _lazy_codes.clear()
+    _mod_codes.clear()
     _runtime_seen[0] = False
     for name in ('reshape', 'ravel', 'flatten', 'copy', '__len__'):
         fn = cls.__dict__.get(name)
@@ -331,8 +725,12 @@ def make_value_property(finfields_module):
         if v.store is not None:
             if not _runtime_seen[0]:
                 _collect_runtime_codes(finfields_module)
-            if sys._getframe(1).f_code in _lazy_codes:
+            code = sys._getframe(1).f_code
+            if code in _lazy_codes:
                 return v
+            if code in _mod_codes and not v.ctx.binary:
+                calls['mod_values'] += 1
+                return ModValue(v.ctx, v.store, v.shape, exact=True)
         a = v._materialise()
         slot_set(self, a)           # settled: from here on this array is an ordinary reference array
         return a
@@ -368,7 +766,7 @@ def _operand(ctx, cls, x, want_shape=None):
     lv = as_limb_value(x)
     if lv is not None:
         return (lv.store, lv.shape) if lv.ctx is ctx else None
-    if type(x) is LimbValue:
+    if type(x) is LimbValue or type(x) is ModValue:
         x = x._ints
     if isinstance(x, np.ndarray) and x.dtype == object and x.size >= min_size and not ctx.binary:
         calls['packed'] += 1
@@ -430,6 +828,21 @@ def binop(self, other, op, reflected=False):
         return _MISS
     x, y = (b[0], a[0]) if reflected else (a[0], b[0])
     return _wrap(cls, ctx, backend.binop(ctx, op, x, y), a[1])
+
+
+def shift(self, other, right):
+    """self << n / self >> n for a limb-backed array and an integer n >= 0; _MISS otherwise."""
+    cls = type(self)
+    ctx = _ctx_of(cls)
+    if ctx is None or ctx.binary or as_limb_value(raw_value(self)) is None:
+        return _MISS
+    if not isinstance(other, (int, np.integer)) or isinstance(other, (bool, np.bool_)) or other < 0:
+        return _MISS
+    k = pow(2, int(other), ctx.modulus)
+    if right:
+        k = pow(k, -1, ctx.modulus)
+    a = _operand(ctx, cls, self)
+    return _wrap(cls, ctx, backend.binop_scalar(ctx, _cabi.OP_MUL, a[0], k), a[1])
 
 
 def negate(self):

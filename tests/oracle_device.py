@@ -131,6 +131,31 @@ class OracleBackend:
     def split(self, ctx, sec, t, m, coeffs=None):
         return split_generate(ctx, sec, t, m) if coeffs is None else split_limbs(ctx, sec, coeffs, t, m)
 
+    # ---- protocol-local algebra (the K6 kernels' stand-ins: oracle.local_*) ----
+    def fma(self, ctx, a, b, c):
+        x = self._ints(ctx, a)
+        return codec.ints_to_limbs(orc.local_fma(ctx.modulus, x, x if b is None else self._ints(ctx, b), self._ints(ctx, c)), ctx)
+
+    def axpb(self, ctx, a, s, t):
+        p = ctx.modulus
+        return codec.ints_to_limbs(orc.local_axpb(p, self._ints(ctx, a), int(s) % p, int(t) % p), ctx)
+
+    def low_bits(self, ctx, a, nbits):
+        return codec.ints_to_limbs(orc.local_low_bits(self._ints(ctx, a), nbits), ctx)
+
+    def nonzero(self, ctx, a):
+        mask = np.array(orc.local_nonzero(self._ints(ctx, a)), dtype=bool)
+        return mask, int(mask.sum())
+
+    def bits_compose(self, ctx, bits, n, f, descending):
+        return codec.ints_to_limbs(orc.local_bits_compose(ctx.modulus, self._ints(ctx, bits), n, f, descending), ctx)
+
+    def sqrt(self, ctx, a, INV):
+        return codec.ints_to_limbs(orc.ff_sqrt(ctx.modulus, self._ints(ctx, a), INV=INV), ctx)
+
+    def slice(self, ctx, store, start, stop):
+        return store[start:stop]
+
     def recombine(self, ctx, xs, rows, pts):
         out = recombine_limbs(ctx, xs, rows, pts)
         return [out[r] for r in range(len(pts))]

@@ -15,6 +15,7 @@ the child parties too:
     MPYC_B200_MIN_SIZE       install(min_size=...)
     MPYC_B200_FORCE_PRIME    hex prime: SecInt/SecFxp types are built over this prime (BASELINE configs[4]: 256-bit)
     MPYC_B200_CALL_LOG       file: one line per engine call (name, field bits, elements), appended per process
+    MPYC_B200_STATS          1: print mpyc_b200.resident.calls (limb ops, materialisations, packs, ModValues) at exit
 """
 import os
 import runpy
@@ -75,6 +76,14 @@ def main():
         _force_prime(mpc, int(prime, 16))
     program = sys.argv[1]
     sys.argv = [program] + sys.argv[2:]
+    if os.environ.get('MPYC_B200_STATS'):          # conversion / limb-op counters of this party on stderr at exit
+        import atexit
+        import json
+
+        def _stats():
+            from mpyc_b200 import resident
+            sys.stderr.write('MPYC_B200_STATS ' + json.dumps({'pid': mpc.pid, **resident.calls}) + '\n')
+        atexit.register(_stats)
     runpy.run_path(program, run_name='__main__')
 
 
