@@ -636,6 +636,58 @@ def run_extras(peak, local):
         out['prss'] = {k: v for k, v in r.items() if k not in ('window', 'prf', 'ctx', 'coef', 'wl', 'party')}
     except Exception as exc:   # noqa: BLE001
         out['prss'] = {'error': repr(exc)[:300]}
+    try:
+        out['local'] = measure_local(peak)
+    except Exception as exc:   # noqa: BLE001
+        out['local'] = {'error': repr(exc)[:300]}
+    return out
+
+
+def measure_local(peak, steps=5, warmup=3):
+    """The protocol-local kernels (csrc/local.cuh) at sizes beyond L2, CUDA events on the launching
+    stream: algorithmic bytes / duration against the copy peak.  np_sgn's shape: l = 37 bit positions per element."""
+    import torch
+    import mpyc_b200
+    from mpyc_b200 import device as dev
+    from mpyc_b200.device import DeviceArray
+    out = {}
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def entry(bytes_, ms, **kw):
+        g = bytes_ / ms / 1e6
+        return {'ms': round(ms, 4), 'algorithmic_bytes': bytes_, 'achieved': round(g, 1), 'frac': round(g / peak, 4), **kw}
+
+    for label, p in (('p128', 2**128 - 173), ('p64', 2**64 - 189), ('p256', 2**256 - 189)):
+        ctx = mpyc_b200.context_for(p)
+        E = 8 * ctx.nlimbs
+        n = (1 << 29) // E                                   # 512 MiB per operand
+        A = DeviceArray.random(ctx, n, seed=5, stream_id=1)
+        C = DeviceArray.random(ctx, n, seed=5, stream_id=3)
+        res = {'fma_square_add': entry(3 * E * n, timed(lambda: dev.fma(A, None, C)), n=n),
+               'axpb': entry(2 * E * n, timed(lambda: dev.axpb(A, (p + 1) >> 1, 12345)), n=n),
+               'low_bits': entry(2 * E * n, timed(lambda: dev.low_bits(A, 37)), n=n)}
+        for f in (6, 37):
+            rows = n // f
+            bits = DeviceArray(ctx, A.t[:rows * f])
+            res[f'bits_compose_f{f}'] = entry((f + 1) * E * rows, timed(lambda: dev.bits_compose(bits, rows, f, descending=(f == 37))),
+                                              n=rows, f=f)
+        rows = n // 37
+        c = DeviceArray(ctx, C.t[:rows])
+        res['bits_decompose_l37'] = entry(38 * E * rows, timed(lambda: dev.bits_decompose(c, 37, descending=True)), n=rows, l=37)
+        out[label] = res
+        del A, C, bits, c
+        torch.cuda.empty_cache()
     return out
 
 

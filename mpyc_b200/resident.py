@@ -130,6 +130,10 @@ class CudaBackend:
     def sqrt(self, ctx, a, INV):
         return self.to_store(ctx, a).sqrt(INV=INV)
 
+    def conv2d(self, ctx, X, W, B, k, r, m, n, v, s):
+        dev, _ = self._dev()
+        return dev.conv2d(self.to_store(ctx, X), self.to_store(ctx, W), self.to_store(ctx, B), k, r, m, n, v, s)
+
     def slice(self, ctx, store, start, stop):
         if isinstance(store, np.ndarray):
             return store[start:stop]
@@ -891,3 +895,29 @@ def matmul(self, other, reflected=False):
         return cls.field(LimbValue(ctx, out, (1,), poly)._materialise()[0])
     shape = (c,) if len(sa) == 1 else ((r,) if len(sb) == 1 else (r, c))
     return _wrap(cls, ctx, out, shape)
+
+
+def conv2d(x, W, b):
+    """The local step of np_cnnmnist's convolvetensor (demos/np_cnnmnist.py:69-82) as one kernel call: x (k, r, m, n),
+    W (v, r, s, s), b (v) -- field arrays of one covered prime field, as `mpc.gather` returns them -- to the field array
+    Y (k, v, m, n) with Y[i, j] = b[j] + sum_l correlate2d(x[i, l], W[j, l], 'same'), limb-backed, ready for
+    `mpc._reshare(Y)`.  The demo is caller code that install() cannot reach; INTEGRATION.md section 5 shows the edit."""
+    cls = type(x)
+    ctx = _ctx_of(cls)
+    if ctx is None or ctx.binary or type(W) is not cls or type(b) is not cls:
+        raise _cabi.UnsupportedFieldError('conv2d: operands must be arrays of one covered prime field')
+    sx, sw, sb = (getattr(raw_value(a), 'shape', None) for a in (x, W, b))
+    if len(sx) != 4 or len(sw) != 4 or len(sb) != 1 or sx[1] != sw[1] or sw[2] != sw[3] or sb[0] != sw[0]:
+        raise ValueError(f'conv2d: shapes {sx}, {sw}, {sb} do not fit (k,r,m,n), (v,r,s,s), (v,)')
+    saved = min_size
+    try:
+        globals()['min_size'] = 0
+        ops = [_operand(ctx, cls, a) for a in (x, W, b)]
+    finally:
+        globals()['min_size'] = saved
+    if any(o is None for o in ops):
+        raise _cabi.UnsupportedFieldError('conv2d: operands must be limb-backed or object arrays of the field')
+    k, r, m, n = sx
+    v, s = sw[0], sw[2]
+    out = backend.conv2d(ctx, ops[0][0], ops[1][0], ops[2][0], k, r, m, n, v, s)
+    return _wrap(cls, ctx, out, (k, v, m, n))

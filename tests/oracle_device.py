@@ -153,6 +153,12 @@ class OracleBackend:
     def sqrt(self, ctx, a, INV):
         return codec.ints_to_limbs(orc.ff_sqrt(ctx.modulus, self._ints(ctx, a), INV=INV), ctx)
 
+    def conv2d(self, ctx, X, W, B, k, r, m, n, v, s):
+        if s % 2 == 0 or n < s:
+            raise _cabi.UnsupportedFieldError('conv2d: even or oversized filters are not covered')
+        return codec.ints_to_limbs(orc.local_conv2d(ctx.modulus, self._ints(ctx, X), self._ints(ctx, W), self._ints(ctx, B),
+                                                    k, r, m, n, v, s), ctx)
+
     def slice(self, ctx, store, start, stop):
         return store[start:stop]
 

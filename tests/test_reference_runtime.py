@@ -160,6 +160,37 @@ def test_secure_ops_program_installed_equals_reference(mode, parties, flags):
 
 
 @pytest.mark.parametrize('parties', [1, 3])
+def test_conv_layer_bound_to_the_engine_equals_the_object_loops(mode, parties):
+    """tests/programs/cnn_conv.py: a secure convolution layer written like the CNN demo's (gather, correlate on raw values,
+    field.array, _reshare) with the local step bound to mpyc_b200.resident.conv2d (K6 k_conv2d) -- INTEGRATION.md
+    section 5 -- against the same program running its NumPy object loops on the plain reference."""
+    trim_for_gpu(mode, parties == 3)
+    want = run(mode, os.path.join(HERE, 'programs', 'cnn_conv.py'), ['2'], ('off',), parties=parties)
+    got = run(mode, os.path.join(HERE, 'programs', 'cnn_conv.py'), ['2'], ('install', 'resident'), parties=parties,
+              env_extra=EVERYTHING)
+    assert got.count('digest=') == 2 and got == want
+
+
+@pytest.mark.parametrize('parties', [1, 3])
+def test_local_algebra_of_protocols_runs_on_limbs(mode, parties):
+    """Secure comparisons, random bits and fixed-point products (np_sgn, np_random_bits, np_trunc) with
+    install(resident=True): the whitelisted protocol functions receive ModValues (their raw-value algebra runs mod p on the
+    K1 / K6 kernels), and the opened results equal the plain reference's."""
+    import json
+    trim_for_gpu(mode, parties == 3)
+    want = run(mode, PROGRAM, ['300'], ('off',), parties=parties)
+    out = subprocess.run([sys.executable, LAUNCHER, PROGRAM, '300', '--no-log'] + ([f'-M{parties}', '-B', str(next(_ports))] if parties > 1 else []),
+                         cwd=HERE, capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MPYC_REFERENCE=REF, PYTHONDONTWRITEBYTECODE='1', MPYC_B200_STATS='1', MPYC_B200_OPS_MIN_SIZE='64',
+                                  MPYC_B200_HARNESS='install,resident' + (',oracle' if mode == 'oracle' else '')))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stdout == want
+    stats = [json.loads(line.split(' ', 1)[1]) for line in out.stderr.splitlines() if line.startswith('MPYC_B200_STATS ')]
+    mine = [s for s in stats if s['pid'] == 0]
+    assert mine and mine[0]['mod_values'] >= 10 and mine[0]['limb_ops'] >= 30
+
+
+@pytest.mark.parametrize('parties', [1, 3])
 def test_resident_chain_creates_no_python_ints_between_input_and_output(mode, parties):
     """input -> a*b -> _reshare -> (a*b)*a -> _reshare -> output over a 128-bit prime with install(resident=True):
     the product code performs no int <-> limb conversion between the arrival of the input shares and output()
