@@ -119,7 +119,7 @@ def _install_operators(finfields_module, min_size):
     resident.min_size = int(min_size)
     cls = finfields_module.FiniteFieldArray
     names = ('__init__', '__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__neg__', '__matmul__',
-             '__rmatmul__', '__lshift__', '__rshift__', '__ilshift__', '__irshift__')
+             '__rmatmul__', '__lshift__', '__rshift__', '__ilshift__', '__irshift__', '__getitem__', '__array_function__')
     orig = {name: cls.__dict__[name] for name in names}
     _saved_ops.update({'cls': cls, 'module': finfields_module, **orig})
     MISS = resident._MISS
@@ -169,6 +169,20 @@ def _install_operators(finfields_module, min_size):
         method.__doc__ = orig[name].__doc__
         return method
 
+    def __getitem__(self, key):
+        r = resident.getitem(self, key)
+        return orig['__getitem__'](self, key) if r is MISS else r
+
+    def __array_function__(self, func, types, args, kwargs):
+        import numpy as np
+        if func is np.concatenate and isinstance(self, cls) and len(args) == 1 and set(kwargs) <= {'axis'}:
+            r = resident.concatenate(type(self), list(args[0]), kwargs.get('axis', 0))
+            if r is not MISS:
+                return r
+        return orig['__array_function__'](self, func, types, args, kwargs)
+
+    cls.__getitem__ = __getitem__
+    cls.__array_function__ = __array_function__
     cls.__lshift__ = make_shift('__lshift__', False, False)
     cls.__rshift__ = make_shift('__rshift__', True, False)
     cls.__ilshift__ = make_shift('__ilshift__', False, True)

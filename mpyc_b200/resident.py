@@ -140,6 +140,15 @@ class CudaBackend:
         dev, _ = self._dev()
         return dev.DeviceArray(ctx, store.t[start:stop])
 
+    def concat(self, ctx, stores):
+        """One store holding the elements of `stores` back to back (a device-to-device copy; torch is the allocator)."""
+        import torch
+        dev, _ = self._dev()
+        parts = [self.to_store(ctx, st) for st in stores]
+        out = dev.DeviceArray.empty(ctx, sum(p.n for p in parts), parts[0].t.device)
+        torch.cat([p.t for p in parts], out=out.t)
+        return out
+
 
 backend = CudaBackend()
 
@@ -832,6 +841,55 @@ def binop(self, other, op, reflected=False):
         return _MISS
     x, y = (b[0], a[0]) if reflected else (a[0], b[0])
     return _wrap(cls, ctx, backend.binop(ctx, op, x, y), a[1])
+
+
+def getitem(self, key):
+    """self[key] for a limb-backed array when the selection is one contiguous run of the C-ordered elements: an int or a
+    step-1 slice along axis 0 (what np_prod's halving loop, runtime.py:2198-2204, and row selections use).  The result
+    shares the limbs (FiniteFieldArray.__getitem__ returns a no-copy view, finfields.py:1004-1009; limb stores are
+    immutable, a later write settles the array that is written to).  _MISS otherwise."""
+    cls = type(self)
+    lv = as_limb_value(raw_value(self))
+    if lv is None:
+        return _MISS
+    shape = lv.shape
+    if not shape:
+        return _MISS
+    if isinstance(key, tuple):
+        if len(key) != 1:
+            return _MISS
+        key = key[0]
+    inner = 1
+    for d in shape[1:]:
+        inner *= d
+    if isinstance(key, slice):
+        if key.step not in (None, 1):
+            return _MISS
+        start, stop, _ = key.indices(shape[0])
+        stop = max(stop, start)
+        new_shape = (stop - start,) + shape[1:]
+    elif isinstance(key, (int, np.integer)) and not isinstance(key, (bool, np.bool_)) and len(shape) >= 2:
+        start = int(key) + (shape[0] if key < 0 else 0)
+        if not 0 <= start < shape[0]:
+            return _MISS                 # NumPy raises the IndexError
+        stop, new_shape = start + 1, shape[1:]
+    else:
+        return _MISS
+    store = backend.slice(lv.ctx, lv.store, start * inner, stop * inner)
+    return cls(LimbValue(lv.ctx, store, new_shape, lv._poly), check=False)
+
+
+def concatenate(cls, arrays, axis):
+    """np.concatenate(arrays, axis=0) of limb-backed arrays of one field (np_prod's odd step, runtime.py:2202); _MISS otherwise."""
+    if axis != 0 or not arrays:
+        return _MISS
+    lvs = [as_limb_value(raw_value(a)) if isinstance(a, cls) else None for a in arrays]
+    if any(v is None or v.ctx is not lvs[0].ctx or v.shape[1:] != lvs[0].shape[1:] or not v.shape for v in lvs):
+        return _MISS
+    ctx = lvs[0].ctx
+    calls['limb_ops'] += 1
+    store = backend.concat(ctx, [v.store for v in lvs])
+    return cls(LimbValue(ctx, store, (sum(v.shape[0] for v in lvs),) + lvs[0].shape[1:], lvs[0]._poly), check=False)
 
 
 def shift(self, other, right):

@@ -162,6 +162,9 @@ class OracleBackend:
     def slice(self, ctx, store, start, stop):
         return store[start:stop]
 
+    def concat(self, ctx, stores):
+        return np.concatenate([np.ascontiguousarray(st) for st in stores], axis=0)
+
     def recombine(self, ctx, xs, rows, pts):
         out = recombine_limbs(ctx, xs, rows, pts)
         return [out[r] for r in range(len(pts))]
