@@ -137,6 +137,14 @@ int mpyc_b200_ff_bits_compose(const mpyc_b200_field* f, const void* d_bits, size
  * `np.right_shift.outer(c, shifts).T & 1` (runtime.py:3660, 4423) */
 int mpyc_b200_ff_bits_decompose(const mpyc_b200_field* f, const void* d_c, size_t n, int nbits, int descending,
                                 void* d_out, size_t out_stride, void* stream);
+/* (rows, cols) matrices of elements, row-major and contiguous -- the (l, n) bit-matrix algebra of np_sgn:
+ * out (cols, rows) = in^T (`r_bits.T`, runtime.py:3661; not in place);
+ * out[j][i] = sum_{j' <= j} in[j'][i] (`np.cumsum(..., axis=0)`, runtime.py:3667);
+ * out[j][i] = a[j][i] (op) b[i], reflected: b[i] (op) a[j][i] (`s_sign - <matrix>`, NumPy row broadcast, runtime.py:3670). */
+int mpyc_b200_ff_transpose(const mpyc_b200_field* f, const void* d_in, size_t rows, size_t cols, void* d_out, void* stream);
+int mpyc_b200_ff_cumsum_rows(const mpyc_b200_field* f, const void* d_in, size_t rows, size_t cols, void* d_out, void* stream);
+int mpyc_b200_ff_binop_rows(const mpyc_b200_field* f, int op, int reflected, const void* d_a, const void* d_b, void* d_out,
+                            size_t rows, size_t cols, void* stream);
 /* Y[k][v][m][n] = B[v] + 'same' 2-D correlation of X[k][r][m][n] with W[v][r][s][s] summed over the r input channels,
  * mod p, s odd -- demos/np_cnnmnist.py:69-81 (convolvetensor's np.correlate loops followed by field.array(Y)).
  * All arrays contiguous, row-major. */

@@ -62,6 +62,9 @@ _SIGNATURES = {
     'mpyc_b200_ff_nonzero': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpyc_b200_ff_bits_compose': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     'mpyc_b200_ff_bits_decompose': (c_int, [_field_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'mpyc_b200_ff_transpose': (c_int, [_field_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    'mpyc_b200_ff_cumsum_rows': (c_int, [_field_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    'mpyc_b200_ff_binop_rows': (c_int, [_field_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     'mpyc_b200_ff_conv2d': (c_int, [_field_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
     'mpyc_b200_shamir_split': (c_int, [_field_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t,

@@ -701,6 +701,40 @@ MPYC_API int mpyc_b200_ff_bits_decompose(const mpyc_b200_field* f, const void* d
     });
 }
 
+MPYC_API int mpyc_b200_ff_transpose(const mpyc_b200_field* f, const void* d_in, size_t rows, size_t cols, void* d_out, void* stream) {
+    if (int rc = prime_only(f, "ff_transpose: field is null")) return rc;
+    if (rows && cols && (!d_in || !d_out)) return fail(MPYC_B200_EINVAL, "ff_transpose: null buffer");
+    if (d_in == d_out && rows > 1 && cols > 1) return fail(MPYC_B200_EINVAL, "ff_transpose: in place is not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::transpose(f->fp, (const u64*)d_in, (u64*)d_out, rows, cols, st), "ff_transpose launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_cumsum_rows(const mpyc_b200_field* f, const void* d_in, size_t rows, size_t cols, void* d_out, void* stream) {
+    if (int rc = prime_only(f, "ff_cumsum_rows: field is null")) return rc;
+    if (rows && cols && (!d_in || !d_out)) return fail(MPYC_B200_EINVAL, "ff_cumsum_rows: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::cumsum_rows(f->fp, (const u64*)d_in, (u64*)d_out, rows, cols, st), "ff_cumsum_rows launch");
+    });
+}
+
+MPYC_API int mpyc_b200_ff_binop_rows(const mpyc_b200_field* f, int op, int reflected, const void* d_a, const void* d_b, void* d_out,
+                                     size_t rows, size_t cols, void* stream) {
+    if (int rc = prime_only(f, "ff_binop_rows: field is null")) return rc;
+    if (op < 0 || op > 2) return fail(MPYC_B200_EINVAL, "ff_binop_rows: op must be ADD, SUB or MUL");
+    if (rows && cols && (!d_a || !d_b || !d_out)) return fail(MPYC_B200_EINVAL, "ff_binop_rows: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    return with_limbs((int)f->fp.L, [&](auto Lc) {
+        constexpr int L = decltype(Lc)::value;
+        return launch_status(Launch<L>::binop_rows(f->fp, op, reflected != 0, (const u64*)d_a, (const u64*)d_b, (u64*)d_out, rows, cols, st),
+                             "ff_binop_rows launch");
+    });
+}
+
 MPYC_API int mpyc_b200_ff_conv2d(const mpyc_b200_field* f, const void* d_x, const void* d_w, const void* d_b, void* d_y,
                                  int k, int r, int m, int n, int v, int s, void* stream) {
     if (int rc = prime_only(f, "ff_conv2d: field is null")) return rc;

@@ -460,21 +460,33 @@ cudaError_t Launch<L>::low_bits(const FieldParams& fp, const u64* a, int nbits, 
 template <int L>
 cudaError_t Launch<L>::nonzero(const FieldParams& fp, const u64* a, unsigned char* out8, unsigned long long* count, size_t n,
                                cudaStream_t st) {
-    if (L % 2 == 0 && !aligned16(a)) return cudaErrorMisalignedAddress;
-    return launch_kernel(k_nonzero<L>, n, 0, st, a, out8, count, n);
+    constexpr int E = VecItem<L>::E;
+    if constexpr (L != 3) {
+        if (aligned32(a)) return launch_kernel(k_nonzero<L, true>, (n + E - 1) / E, 0, st, a, out8, count, n);
+    }
+    return launch_kernel(k_nonzero<L, false>, n, 0, st, a, out8, count, n);
 }
 
 template <int L>
 cudaError_t Launch<L>::bits_compose(const FieldParams& fp, const u64* bits, u64* out, size_t n, int f, bool descending,
                                     cudaStream_t st) {
     if (L % 2 == 0 && (!aligned16(bits) || !aligned16(out))) return cudaErrorMisalignedAddress;
-    constexpr size_t smem = ComposeCfg<L>::SMEM;
-#define M(K)                                                                                                  \
-    {                                                                                                         \
-        auto kernel = k_bits_compose<L, K>;                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                       \
-        return launch_kernel(kernel, n, smem, st, fp, bits, out, n, f, (int)descending);                      \
+    if (n == 0) return cudaSuccess;
+    const size_t smem = (size_t)ComposeCfg<L>::smem(f);
+    // the shared-memory footprint depends on f, so the wave size is computed per launch (not cached per kernel)
+#define M(K)                                                                                                        \
+    {                                                                                                               \
+        auto kernel = k_bits_compose<L, K>;                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ComposeCfg<L>::smem(1 << 20)); \
+        if (e != cudaSuccess) return e;                                                                             \
+        int occ = 0;                                                                                                \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, MPYC_THREADS, smem);                        \
+        if (e != cudaSuccess) return e;                                                                             \
+        const size_t tiles = (n + MPYC_THREADS - 1) / MPYC_THREADS;                                                 \
+        const int grid = (int)std::min<size_t>(tiles, (size_t)mpyc_sm_count() * (size_t)std::max(occ, 1));          \
+        kernel<<<grid, MPYC_THREADS, smem, st>>>(fp, bits, out, n, f, (int)descending);                             \
+        g_mpyc_launches.fetch_add(1, std::memory_order_relaxed);                                                    \
+        return cudaGetLastError();                                                                                  \
     }
     KIND_SWITCH(fp.kind, M)
 #undef M
@@ -509,5 +521,41 @@ cudaError_t Launch<L>::conv2d(const FieldParams& fp, const u64* X, const u64* W,
     }
     KIND_SWITCH(fp.kind, M)
 #undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::transpose(const FieldParams& fp, const u64* in, u64* out, size_t R, size_t C, cudaStream_t st) {
+    const size_t tiles = ((R + 31) / 32) * ((C + 31) / 32);
+    return launch_kernel(k_transpose<L>, tiles * MPYC_THREADS, 0, st, in, out, R, C);
+}
+
+template <int L>
+cudaError_t Launch<L>::cumsum_rows(const FieldParams& fp, const u64* in, u64* out, size_t R, size_t C, cudaStream_t st) {
+    if (L % 2 == 0 && (!aligned16(in) || !aligned16(out))) return cudaErrorMisalignedAddress;
+#define M(K) return launch_kernel(k_cumsum_rows<L, K>, C, 0, st, fp, in, out, R, C)
+    KIND_SWITCH(fp.kind, M)
+#undef M
+    return cudaErrorInvalidValue;
+}
+
+template <int L>
+cudaError_t Launch<L>::binop_rows(const FieldParams& fp, int op, bool reflected, const u64* a, const u64* b, u64* out, size_t R,
+                                  size_t C, cudaStream_t st) {
+    if (L % 2 == 0 && (!aligned16(a) || !aligned16(out))) return cudaErrorMisalignedAddress;
+    const size_t total = R * C;
+#define ROWS_CASE(K, OPC)                                                                                   \
+    return reflected ? launch_kernel(k_binop_rows<L, K, OPC, true>, total, 0, st, fp, a, b, out, R, C)      \
+                     : launch_kernel(k_binop_rows<L, K, OPC, false>, total, 0, st, fp, a, b, out, R, C)
+#define M(K)                                   \
+    switch (op) {                              \
+        case OP_ADD: ROWS_CASE(K, OP_ADD);     \
+        case OP_SUB: ROWS_CASE(K, OP_SUB);     \
+        case OP_MUL: ROWS_CASE(K, OP_MUL);     \
+        default: return cudaErrorInvalidValue; \
+    }
+    KIND_SWITCH(fp.kind, M)
+#undef M
+#undef ROWS_CASE
     return cudaErrorInvalidValue;
 }

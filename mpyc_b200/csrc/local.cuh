@@ -11,6 +11,8 @@
 //   k_bits_decompose (c[i] >> e(j)) & 1        np_sgn / np_to_bits: `np.right_shift.outer(c, shifts).T & 1`  :3660, :4423
 //   k_conv2d         'same' 2-D correlation over input channels + bias, mod p
 //                                              demos/np_cnnmnist.py:69-81 (convolvetensor's np.correlate loops)
+//   k_transpose, k_cumsum_rows, k_binop_rows   np_sgn's (l, n) bit-matrix algebra: `r_bits.T`, `np.cumsum(.., axis=0)`,
+//                                              `s_sign - <matrix>` (row broadcast)                 :3661-3672
 //
 // The reference computes these over the integers and reduces when the result enters a field array
 // (`Zp.array(...)`, finfields.py:717-725); reduction is a ring homomorphism, so computing mod p throughout gives the
@@ -138,19 +140,32 @@ k_low_bits(ScalarParam mask, const u64* __restrict__ a, u64* __restrict__ out, s
 }
 
 // out8[h] = a[h] != 0 (may be null); *count += number of non-zero elements
-template <int L>
+template <int L, bool VEC>
 __global__ void MPYC_LB
 k_nonzero(const u64* __restrict__ a, unsigned char* __restrict__ out8, unsigned long long* count, size_t n) {
+    constexpr int E = VEC ? VecItem<L>::E : 1;
     constexpr int N = 2 * L;
-    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = n / E;
     unsigned int mine = 0;
-    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += nth) {
-        u32 x[N];
-        ldg_elem<L>(x, a + h * L);
-        const bool nz = !is_zero_n<N>(x);
-        if (out8) out8[h] = nz;
-        mine += nz;
+    for (size_t it = tid; it < n_items; it += nth) {
+        u32 x[E * N];
+        load_limbs<E * L, VEC>(x, a + it * (size_t)(E * L));
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const bool nz = !is_zero_n<N>(x + e * N);
+            if (out8) out8[it * E + e] = nz;
+            mine += nz;
+        }
     }
+    if constexpr (E > 1)
+        for (size_t h = n_items * E + tid; h < n; h += nth) {
+            u32 x[N];
+            load_limbs<L, false>(x, a + h * L);
+            const bool nz = !is_zero_n<N>(x);
+            if (out8) out8[h] = nz;
+            mine += nz;
+        }
     mine = __reduce_add_sync(0xffffffffu, mine);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, (unsigned long long)mine);
 }
@@ -214,22 +229,32 @@ k_bits_decompose(const u64* __restrict__ c, u64* __restrict__ out, size_t ostrid
 //
 // Memory: row i of the (n, f) input is f*E contiguous bytes -- a thread walking its own row would touch one sector
 // per warp lane and instruction.  So a CTA stages a tile of 256 rows x JB columns (~128 bytes of each row) in shared
-// memory with cp.async pieces issued in row-major piece order (8 consecutive threads fetch the 128 contiguous bytes of
-// one row), three stages in flight across tile boundaries; the row pitch in shared memory is padded to an odd number
-// of pieces so that the per-thread reads (thread = row) are bank-conflict free.
+// memory with 16-byte cp.async pieces issued in row-major piece order (8 consecutive threads fetch the 128 contiguous
+// bytes of one row), three stages in flight across tile boundaries.  The row pitch in shared memory is sized from
+// min(f, JB) at run time (narrow inputs such as np_trunc's f = 6 leave room for 4-5 CTAs per SM instead of 2) and is an
+// odd number of 16-byte units so that the per-thread reads (thread = row) spread over the banks.  For odd L a row chunk
+// may start on an odd 8-byte boundary: it gets an 8-byte head piece and is stored 8 bytes into its pitch, so that the
+// rest still moves in aligned 16-byte pieces.
 // ---------------------------------------------------------------------------------------
 
 template <int L>
 struct ComposeCfg {
     static constexpr int EB = 8 * L;                      // bytes per element
-    static constexpr int CP = (L % 2 == 0) ? 16 : 8;      // cp.async piece (source alignment: 16 bytes for even L)
-    static constexpr int JB = L == 1 ? 16 : (L == 2 ? 8 : (L == 3 ? 5 : 4));   // columns per stage
-    static constexpr int RB = JB * EB;                    // bytes of one row per stage
-    static constexpr int PPR = RB / CP;                   // pieces per row
-    static constexpr int PITCH = ((PPR + 1) | 1) * CP;    // odd number of pieces >= PPR + 1
+    static constexpr bool WIDE = (L % 2 == 0);            // even L: every element is 16-byte aligned
+    static constexpr int JB = L == 1 ? 14 : (L == 2 ? 8 : 4);   // columns per stage: a row chunk is at most 8 copy slots
+    static constexpr int G = 8;                           // copy slots per row (8 consecutive threads serve one row)
     static constexpr int STAGES = 3;
-    static constexpr int STAGE_BYTES = MPYC_THREADS * PITCH;
-    static constexpr int SMEM = STAGES * STAGE_BYTES;
+    // row pitch in shared memory for stages of at most `cols` columns: a multiple of 16 bytes with room for the row
+    // chunk plus the 8-byte shift of rows that start on an odd 8-byte boundary (odd L), and an odd number of 16-byte
+    // units so that the per-thread reads (thread = row) spread over the banks
+    static __host__ __device__ int pitch(int cols) {
+        const int units = (cols * EB + (WIDE ? 0 : 8) + 15) / 16;
+        return ((units + 1) | 1) * 16;
+    }
+    // cp.async slots a row chunk needs: 16-byte pieces, plus for odd L an 8-byte head (misaligned rows) and tail
+    static constexpr int slots(int cols) { return WIDE ? cols * EB / 16 : (cols * EB + 8) / 16 + 1; }
+    static_assert((WIDE ? JB * EB / 16 : (JB * EB + 8) / 16 + 1) <= G, "a row chunk must fit the copy slots of its 8 threads");
+    static __host__ __device__ int smem(int fcols) { return STAGES * MPYC_THREADS * pitch(fcols < JB ? fcols : JB); }
 };
 
 template <int L>
@@ -246,6 +271,13 @@ __device__ __forceinline__ void lds_elem(u32* v, u32 saddr) {
     }
 }
 
+__device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(u32 dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int L, int KIND>
 __global__ void MPYC_LB
 k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ out, size_t n, int fcols, int descending) {
@@ -256,9 +288,12 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
     const u32 smem0 = smem_u32(smem_raw);
     const int t = threadIdx.x;
     const int nblk = (fcols + C::JB - 1) / C::JB;
+    const int pitch = C::pitch(min(fcols, C::JB));
+    const u32 stage_bytes = (u32)MPYC_THREADS * pitch;
     const size_t tiles = (n + MPYC_THREADS - 1) / MPYC_THREADS;
     const size_t my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x - 1) / gridDim.x + 1 : 0;
     const size_t units = my_tiles * (size_t)nblk;
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(bits);
 
     // column block b (in Horner order, top exponent first) of a row: first column and number of columns
     auto block_cols = [&](int b, int& col0, int& ncols) {
@@ -271,6 +306,15 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
             ncols = hi - col0;
         }
     };
+    // a row whose chunk starts on an odd 8-byte boundary is stored 8 bytes into its pitch, so that 16-byte aligned
+    // global addresses land on 16-byte aligned shared addresses (odd L only)
+    auto row_shift = [&](size_t row, int col0) -> u32 {
+        if constexpr (C::WIDE) return 0u;
+        return (u32)((reinterpret_cast<uintptr_t>(gbase) + (row * (size_t)fcols + col0) * C::EB) & 8u);
+    };
+    // copy slot k of row (t >> 3) + 32 r: 8 consecutive threads fetch the contiguous chunk of one row, a warp 4 rows
+    const int kslot = t & (C::G - 1), rsub = t >> 3;
+    const size_t row_bytes = (size_t)fcols * C::EB;
     auto issue = [&](size_t u) {
         if (u < units) {
             const size_t tile = blockIdx.x + (u / nblk) * gridDim.x;
@@ -278,20 +322,24 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
             block_cols((int)(u % nblk), col0, ncols);
             const size_t row0 = tile * MPYC_THREADS;
             const int rows = (int)min((size_t)MPYC_THREADS, n - row0);
-            const int pieces = ncols * C::EB / C::CP;   // per row (EB is a multiple of CP)
-            const u32 stage = smem0 + (u32)(u % C::STAGES) * C::STAGE_BYTES;
+            const int rb = ncols * C::EB;               // bytes of one row chunk
+            const unsigned char* tbase = gbase + (row0 * (size_t)fcols + col0) * C::EB;
+            const u32 stage = smem0 + (u32)(u % C::STAGES) * stage_bytes;
 #pragma unroll
-            for (int r = 0; r < C::PPR; r++) {
-                const int q = t + MPYC_THREADS * r;
-                const int row = q / C::PPR, pc = q % C::PPR;
-                if (row < rows && pc < pieces) {
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(bits) +
-                                               ((row0 + row) * (size_t)fcols + col0) * C::EB + (size_t)pc * C::CP;
-                    const u32 dst = stage + row * C::PITCH + pc * C::CP;
-                    if constexpr (C::CP == 16)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                    else
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+            for (int r = 0; r < MPYC_THREADS / (MPYC_THREADS / C::G); r++) {
+                const int row = rsub + (MPYC_THREADS / C::G) * r;
+                if (row < rows) {
+                    const unsigned char* src = tbase + row * row_bytes;
+                    if constexpr (C::WIDE) {
+                        if (16 * kslot < rb) cp_async16(stage + row * pitch + 16 * kslot, src + 16 * kslot);
+                    } else {
+                        const u32 mis = (u32)(reinterpret_cast<uintptr_t>(src) & 8u);   // 0 or 8
+                        const int off = mis ? (kslot == 0 ? 0 : 16 * kslot - 8) : 16 * kslot;
+                        const int size = (mis && kslot == 0) ? 8 : min(16, rb - off);
+                        const u32 dst = stage + row * pitch + mis + off;
+                        if (size == 16) cp_async16(dst, src + off);
+                        else if (size == 8) cp_async8(dst, src + off);
+                    }
                 }
             }
         }
@@ -313,7 +361,7 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
         int col0, ncols;
         block_cols(b, col0, ncols);
         if (row < n) {
-            const u32 base = smem0 + (u32)(u % C::STAGES) * C::STAGE_BYTES + t * C::PITCH;
+            const u32 base = smem0 + (u32)(u % C::STAGES) * stage_bytes + t * pitch + row_shift(row, col0);
             for (int cidx = 0; cidx < ncols; cidx++) {
                 const int lc = descending ? cidx : ncols - 1 - cidx;
                 u32 x[N];
@@ -411,5 +459,81 @@ k_conv2d(FieldParams f, const u64* __restrict__ X, const u64* __restrict__ W, co
         load_limbs<L, false>(bias, B + (size_t)j * L);
         F::add(res, res, bias, f);
         store_limbs<L, false>(Y + (((size_t)i * v + j) * pix + px) * L, res);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// (R, C) matrices of elements: transpose, running sum down the rows, row-vector broadcast -- the (l, n) bit-matrix
+// algebra of np_sgn (runtime.py:3659-3672): `r_bits.T`, `np.cumsum(np.vstack((zeros, Xor)), axis=0)`,
+// `s_sign - np.vstack((c_bits - r_bits, ones)) + 3*SumXors`.
+// ---------------------------------------------------------------------------------------
+
+// out (C, R) = in (R, C)^T: 32 x 32 element tiles through shared memory, both sides coalesced along their rows
+template <int L>
+__global__ void MPYC_LB
+k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t C) {
+    __shared__ u64 tile[32][33 * L];
+    const size_t tc = (C + 31) / 32, tr = (R + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+    for (size_t w = blockIdx.x; w < tc * tr; w += gridDim.x) {
+        const size_t r0 = (w / tc) * 32, c0 = (w % tc) * 32;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const size_t r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < R && c < C) {
+#pragma unroll
+                for (int q = 0; q < L; q++) tile[ty + 8 * k][tx * L + q] = in[(r * C + c) * L + q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const size_t c = c0 + ty + 8 * k, r = r0 + tx;       // out row = input column
+            if (r < R && c < C) {
+#pragma unroll
+                for (int q = 0; q < L; q++) out[(c * R + r) * L + q] = tile[tx][(ty + 8 * k) * L + q];
+            }
+        }
+    }
+}
+
+// out[j][i] = sum_{j' <= j} in[j'][i] mod p (np.cumsum(axis=0)): a thread walks its column, rows are coalesced
+template <int L, int KIND>
+__global__ void MPYC_LB
+k_cumsum_rows(FieldParams f, const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t C) {
+    constexpr int N = 2 * L;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += nth) {
+        u32 acc[N];
+        zero_n<N>(acc);
+        for (size_t j = 0; j < R; j++) {
+            u32 x[N];
+            ldg_elem<L>(x, in + (j * C + i) * L);
+            Fp<L, KIND>::add(acc, acc, x, f);
+            stg_elem<L>(out + (j * C + i) * L, acc);
+        }
+    }
+}
+
+// out[j][i] = a[j][i] (op) b[i], or b[i] (op) a[j][i] when REFLECT; a: (R, C), b: (C)
+template <int L, int KIND, int OP, bool REFLECT>
+__global__ void MPYC_LB
+k_binop_rows(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, size_t R, size_t C) {
+    constexpr int N = 2 * L;
+    const size_t nth = (size_t)gridDim.x * blockDim.x, total = R * C;
+    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < total; h += nth) {
+        u32 x[N], y[N], r[N];
+        ldg_elem<L>(x, a + h * L);
+        const u64* bp = b + (h % C) * L;
+#pragma unroll
+        for (int q = 0; q < L; q++) {
+            const u64 w = __ldg(bp + q);
+            y[2 * q] = (u32)w;
+            y[2 * q + 1] = (u32)(w >> 32);
+        }
+        if constexpr (REFLECT) apply_op<L, KIND, OP>(r, y, x, f);
+        else apply_op<L, KIND, OP>(r, x, y, f);
+        stg_elem<L>(out + h * L, r);
     }
 }

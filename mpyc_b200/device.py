@@ -404,3 +404,43 @@ def conv2d(X: DeviceArray, W: DeviceArray, B: DeviceArray, k, r, m, n, v, s):
     out = DeviceArray.empty(X.ctx, k * v * m * n, X.t.device)
     check(lib.mpyc_b200_ff_conv2d(X.ctx.handle, X.ptr, W.ptr, B.ptr, out.ptr, k, r, m, n, v, s, _stream_ptr()))
     return out
+
+
+def bits_decompose_flat(c: DeviceArray, l, descending=False):
+    """As bits_decompose, into ONE contiguous buffer of l*n elements (row-major (l, n), no row padding)."""
+    c._check_contiguous()
+    out = DeviceArray.empty(c.ctx, l * c.n, c.t.device)
+    if l and c.n:
+        check(lib.mpyc_b200_ff_bits_decompose(c.ctx.handle, c.ptr, c.n, l, 1 if descending else 0, out.ptr, c.n, _stream_ptr()))
+    return out
+
+
+def transpose(a: DeviceArray, rows, cols):
+    """(rows, cols) row-major -> (cols, rows): `r_bits.T` (mpyc/runtime.py:3661)."""
+    if a.n != rows * cols:
+        raise ValueError('transpose: buffer does not hold rows*cols elements')
+    a._check_contiguous()
+    out = a._like()
+    check(lib.mpyc_b200_ff_transpose(a.ctx.handle, a.ptr, rows, cols, out.ptr, _stream_ptr()))
+    return out
+
+
+def cumsum_rows(a: DeviceArray, rows, cols):
+    """Running sums down the rows of a (rows, cols) matrix: `np.cumsum(x, axis=0)` mod p (mpyc/runtime.py:3667)."""
+    if a.n != rows * cols:
+        raise ValueError('cumsum_rows: buffer does not hold rows*cols elements')
+    a._check_contiguous()
+    out = a._like()
+    check(lib.mpyc_b200_ff_cumsum_rows(a.ctx.handle, a.ptr, rows, cols, out.ptr, _stream_ptr()))
+    return out
+
+
+def binop_rows(a: DeviceArray, b: DeviceArray, op, rows, cols, reflected=False):
+    """a (rows, cols) (op) b (cols) broadcast over the rows; reflected: b (op) a (mpyc/runtime.py:3670)."""
+    if a.n != rows * cols or b.n != cols or a.ctx is not b.ctx:
+        raise ValueError('binop_rows: shapes do not match the buffers')
+    a._check_contiguous()
+    b._check_contiguous()
+    out = a._like()
+    check(lib.mpyc_b200_ff_binop_rows(a.ctx.handle, op, 1 if reflected else 0, a.ptr, b.ptr, out.ptr, rows, cols, _stream_ptr()))
+    return out

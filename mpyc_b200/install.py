@@ -119,10 +119,11 @@ def _install_operators(finfields_module, min_size):
     resident.min_size = int(min_size)
     cls = finfields_module.FiniteFieldArray
     names = ('__init__', '__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__neg__', '__matmul__',
-             '__rmatmul__', '__lshift__', '__rshift__', '__ilshift__', '__irshift__', '__getitem__', '__array_function__')
+             '__rmatmul__', '__lshift__', '__rshift__', '__ilshift__', '__irshift__', '__getitem__', '__array_function__', '__eq__', '__ne__')
     orig = {name: cls.__dict__[name] for name in names}
     _saved_ops.update({'cls': cls, 'module': finfields_module, **orig})
     MISS = resident._MISS
+    orig_hash = cls.__hash__          # assigning __eq__ on a class does not touch __hash__, kept explicit for clarity
     value_property = resident.make_value_property(finfields_module)
     slot_set = resident._slot.__set__
 
@@ -181,6 +182,17 @@ def _install_operators(finfields_module, min_size):
                 return r
         return orig['__array_function__'](self, func, types, args, kwargs)
 
+    def __eq__(self, other):
+        r = resident.equals(self, other, False)
+        return orig['__eq__'](self, other) if r is MISS else r
+
+    def __ne__(self, other):
+        r = resident.equals(self, other, True)
+        return orig['__ne__'](self, other) if r is MISS else r
+
+    cls.__eq__ = __eq__
+    cls.__ne__ = __ne__
+    cls.__hash__ = orig_hash
     cls.__getitem__ = __getitem__
     cls.__array_function__ = __array_function__
     cls.__lshift__ = make_shift('__lshift__', False, False)

@@ -130,6 +130,23 @@ class CudaBackend:
     def sqrt(self, ctx, a, INV):
         return self.to_store(ctx, a).sqrt(INV=INV)
 
+    def bits_decompose(self, ctx, c, l, descending):
+        """store of l*n elements, row-major (l, n)"""
+        dev, _ = self._dev()
+        return dev.bits_decompose_flat(self.to_store(ctx, c), l, descending)
+
+    def transpose(self, ctx, a, rows, cols):
+        dev, _ = self._dev()
+        return dev.transpose(self.to_store(ctx, a), rows, cols)
+
+    def cumsum_rows(self, ctx, a, rows, cols):
+        dev, _ = self._dev()
+        return dev.cumsum_rows(self.to_store(ctx, a), rows, cols)
+
+    def binop_rows(self, ctx, op, a, b, rows, cols, reflected):
+        dev, _ = self._dev()
+        return dev.binop_rows(self.to_store(ctx, a), self.to_store(ctx, b), op, rows, cols, reflected)
+
     def conv2d(self, ctx, X, W, B, k, r, m, n, v, s):
         dev, _ = self._dev()
         return dev.conv2d(self.to_store(ctx, X), self.to_store(ctx, W), self.to_store(ctx, B), k, r, m, n, v, s)
@@ -141,12 +158,14 @@ class CudaBackend:
         return dev.DeviceArray(ctx, store.t[start:stop])
 
     def concat(self, ctx, stores):
-        """One store holding the elements of `stores` back to back (a device-to-device copy; torch is the allocator)."""
-        import torch
+        """One store holding the elements of `stores` back to back (device-to-device copies; torch is the allocator)."""
         dev, _ = self._dev()
         parts = [self.to_store(ctx, st) for st in stores]
         out = dev.DeviceArray.empty(ctx, sum(p.n for p in parts), parts[0].t.device)
-        torch.cat([p.t for p in parts], out=out.t)
+        at = 0
+        for p in parts:                       # contiguous device-to-device copies (cudaMemcpyAsync)
+            out.t[at:at + p.n].copy_(p.t)
+            at += p.n
         return out
 
 
@@ -320,6 +339,11 @@ class ModValue:
     __slots__ = ('ctx', 'shape', 'store', '_s', '_t', '_sq', 'exact', '_ints')
     __hash__ = None
     dtype = np.dtype(object)
+    # sectypes.SecureArray subclasses accept raw values only as `isinstance(value, np.ndarray)` (sectypes.py:1402,1440)
+    # and then hand them to `field.array(value)` -- which is hooked and takes the limbs.  isinstance() consults
+    # __class__; type() -- which every check in this package uses -- does not.  NumPy's C code is not fooled either
+    # (PyArray_Check looks at the type), it goes through __array__ / __array_ufunc__ / __array_function__ below.
+    __class__ = property(lambda self: np.ndarray)
 
     def __init__(self, ctx, store, shape, exact=False, s=1, t=0, sq=False):
         self.ctx, self.store, self.shape = ctx, store, tuple(shape)
@@ -388,10 +412,22 @@ class ModValue:
             return repr(self._ints)
         return f'ModValue(shape={self.shape}, exact={self.exact}, {self.ctx!r})'
 
+    def __reduce__(self):
+        return _from_ints, (self._materialise(),)
+
     def reshape(self, *shape, **kwargs):
         if self.store is None or kwargs:
             return self._materialise().reshape(*shape, **kwargs)
         return self._new(self.store, _norm_shape(self.size, shape), self.exact, self._s, self._t, self._sq)
+
+    @property
+    def T(self):
+        """`r_bits.T` (runtime.py:3661): a 2-D value is transposed on the device (k_transpose)."""
+        if self.store is not None and len(self.shape) == 2:
+            r, c = self.shape
+            calls['limb_ops'] += 1
+            return self._new(backend.transpose(self.ctx, self._flush(), r, c), (c, r), self.exact)
+        return self._materialise().T
 
     def ravel(self, *args, **kwargs):
         if self.store is None or args or kwargs:
@@ -462,6 +498,9 @@ class ModValue:
             return self._new(self.store, None, False, s, t)
         b = self._other_store(other)
         if b is None:
+            r = self._ring_rows(other, op, reflected)
+            if r is not None:
+                return r
             a = self._materialise()
             return _NUMPY_OPS[op](other, a) if reflected else _NUMPY_OPS[op](a, other)
         calls['limb_ops'] += 1
@@ -471,6 +510,33 @@ class ModValue:
         code = {'+': _cabi.OP_ADD, '-': _cabi.OP_SUB, '*': _cabi.OP_MUL}[op]
         x, y = (b, a) if reflected else (a, b)
         return self._new(backend.binop(self.ctx, code, x, y))
+
+    def _ring_rows(self, other, op, reflected):
+        """NumPy's row broadcast between a vector (C,) and a matrix (R, C) -- `s_sign - <matrix>` (runtime.py:3670)."""
+        oshape = getattr(other, 'shape', None)
+        if oshape is None or not self.shape:
+            return None
+        if len(self.shape) == 1 and len(oshape) == 2 and oshape[1] == self.shape[0]:
+            vec, mat, vec_is_self = self, other, True
+        elif len(self.shape) == 2 and len(oshape) == 1 and oshape[0] == self.shape[1]:
+            vec, mat, vec_is_self = other, self, False
+        else:
+            return None
+        R, C = mat.shape
+        if R == 0 or C == 0:
+            return None
+        holder = ModValue(self.ctx, None, tuple(oshape))     # only for its _other_store: accepts operands of other's shape
+        holder.store = True
+        other_store = holder._other_store(other)
+        if other_store is None:
+            return None
+        mine = self._flush()
+        mstore, vstore = (other_store, mine) if vec_is_self else (mine, other_store)
+        code = {'+': _cabi.OP_ADD, '-': _cabi.OP_SUB, '*': _cabi.OP_MUL}[op]
+        # kernel computes matrix (op) vector, or vector (op) matrix when `refl`
+        refl = (vec_is_self and not reflected) or (not vec_is_self and reflected)
+        calls['limb_ops'] += 1
+        return ModValue(self.ctx, backend.binop_rows(self.ctx, code, mstore, vstore, R, C, refl), (R, C))
 
     def __add__(self, other):
         return self._ring(other, '+')
@@ -576,6 +642,15 @@ class ModValue:
                 return self._ring(b, _UFUNC_OPS[ufunc]) if ufunc is not np.left_shift else self.__lshift__(b)
             if ufunc is not np.left_shift:
                 return self._ring(a, _UFUNC_OPS[ufunc], reflected=True)
+        if (method == 'outer' and ufunc is np.right_shift and len(inputs) == 2 and not kwargs and inputs[0] is self
+                and self.store is not None and len(self.shape) == 1 and self.exact):
+            k = inputs[1]
+            if isinstance(k, np.ndarray) and type(k) is np.ndarray and k.ndim == 1 and k.dtype.kind in 'iu' and k.shape[0] > 0:
+                l = k.shape[0]
+                if np.array_equal(k, np.arange(l)):
+                    return _OuterBits(self, k, False, False)
+                if np.array_equal(k, np.arange(l - 1, -1, -1)):
+                    return _OuterBits(self, k, True, False)
         if method in ('__call__', 'outer') and ufunc in (np.right_shift, np.bitwise_and, np.not_equal, np.equal, np.remainder):
             for x in inputs:
                 if type(x) is ModValue and x.store is not None:
@@ -584,6 +659,59 @@ class ModValue:
         if 'out' in kwargs:
             kwargs['out'] = tuple(x._materialise() if type(x) in (ModValue, LimbValue) else x for x in kwargs['out'])
         return getattr(ufunc, method)(*args, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        """np.vstack / np.cumsum(axis=0) of 2-D values stay on the device (runtime.py:3667-3670); every other NumPy
+        function gets the settled object arrays."""
+        if func is np.vstack and len(args) == 1 and not kwargs:
+            r = _vstack(self.ctx, args[0])
+            if r is not None:
+                return r
+        elif (func is np.cumsum and len(args) == 1 and args[0] is self and kwargs == {'axis': 0} and self.store is not None
+              and len(self.shape) == 2 and self.size):
+            calls['limb_ops'] += 1
+            return self._new(backend.cumsum_rows(self.ctx, self._flush(), self.shape[0], self.shape[1]))
+        return func(*_settled(args), **_settled(kwargs))
+
+
+def _settled(x):
+    """x with every ModValue / LimbValue inside (tuples, lists, dicts) replaced by its object array."""
+    if type(x) in (ModValue, LimbValue):
+        return x._materialise()
+    if type(x) is _OuterBits or type(x) is _ShiftedBits:
+        return x._eval()
+    if isinstance(x, tuple):
+        return tuple(_settled(v) for v in x)
+    if isinstance(x, list):
+        return [_settled(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _settled(v) for k, v in x.items()}
+    return x
+
+
+def _vstack(ctx, parts):
+    """np.vstack of 2-D pieces with the same number of columns, at least one limb-backed: ModValue, else None."""
+    parts = list(parts)
+    stores, rows, cols = [], 0, None
+    for part in parts:
+        shape = getattr(part, 'shape', None)
+        if shape is None or len(shape) != 2 or (cols is not None and shape[1] != cols) or shape[0] == 0 or shape[1] == 0:
+            return None
+        cols = shape[1]
+        if type(part) is ModValue and part.store is not None and part.ctx is ctx:
+            stores.append(part._flush())
+        else:
+            if type(part) in (ModValue, LimbValue):
+                part = part._materialise()
+            if type(part) is not np.ndarray or part.dtype.kind not in 'Oiu':
+                return None
+            calls['packed'] += 1
+            stores.append(codec.ints_to_limbs(part.astype(object).reshape(-1), ctx))
+        rows += shape[0]
+    if not any(type(part) is ModValue for part in parts):
+        return None
+    calls['limb_ops'] += 1
+    return ModValue(ctx, backend.concat(ctx, stores), (rows, cols))
 
 
 import operator as _operator   # noqa: E402
@@ -623,6 +751,49 @@ class _ShiftedBits:
 
     def _eval(self):
         return self.base._materialise() << self.shifts
+
+    def __array__(self, dtype=None, copy=None):
+        return self._eval()
+
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        return getattr(self._eval(), name)
+
+
+class _OuterBits:
+    """`np.right_shift.outer(c, shifts)` for an opened value c and shifts = arange(l) or arange(l-1, -1, -1): `.T & 1`
+    (runtime.py:3660) is the k_bits_decompose kernel; any other use evaluates the shifts on the object array."""
+
+    def __init__(self, base, shifts, descending, transposed):
+        self.base, self.shifts, self.descending, self.transposed = base, shifts, descending, transposed
+
+    @property
+    def shape(self):
+        n, l = self.base.shape[0], self.shifts.shape[0]
+        return (l, n) if self.transposed else (n, l)
+
+    @property
+    def T(self):
+        return _OuterBits(self.base, self.shifts, self.descending, not self.transposed)
+
+    def __and__(self, mask):
+        b = self.base
+        if b.store is not None and isinstance(mask, (int, np.integer)) and not isinstance(mask, (bool, np.bool_)) and mask == 1:
+            n, l = b.shape[0], self.shifts.shape[0]
+            calls['limb_ops'] += 1
+            bits = backend.bits_decompose(b.ctx, b._flush(), l, self.descending)         # (l, n)
+            if self.transposed:
+                return b._new(bits, (l, n), True)
+            calls['limb_ops'] += 1
+            return b._new(backend.transpose(b.ctx, bits, l, n), (n, l), True)
+        return self._eval() & mask
+
+    __rand__ = __and__
+
+    def _eval(self):
+        a = np.right_shift.outer(self.base._materialise(), self.shifts)
+        return a.T if self.transposed else a
 
     def __array__(self, dtype=None, copy=None):
         return self._eval()
@@ -699,6 +870,10 @@ def _collect_runtime_codes(finfields_module):
         fn = getattr(fn, '__wrapped__', fn)
         if fn is not None and hasattr(fn, '__code__'):
             _lazy_codes.add(fn.__code__)
+    st = sys.modules.get(pkg + '.sectypes')
+    fn = getattr(getattr(st, 'SecureArray', None), '__init__', None)
+    if fn is not None and hasattr(fn, '__code__') and fn.__code__.co_names.count('value') and 'shape' in fn.__code__.co_names:
+        _lazy_codes.add(fn.__code__)          # `shape = value.value.shape` (sectypes.py:1019): asks the shape only
     if local_algebra:
         import hashlib
         import inspect
@@ -890,6 +1065,24 @@ def concatenate(cls, arrays, axis):
     calls['limb_ops'] += 1
     store = backend.concat(ctx, [v.store for v in lvs])
     return cls(LimbValue(ctx, store, (sum(v.shape[0] for v in lvs),) + lvs[0].shape[1:], lvs[0]._poly), check=False)
+
+
+def equals(self, other, negate):
+    """self == other / self != other (FiniteFieldArray.__eq__ / __ne__, finfields.py:1030-1042) for a limb-backed array and
+    an integer: a bool ndarray from the k_nonzero kernel (np_is_zero_public's `a == 0`, runtime.py:966); _MISS otherwise."""
+    cls = type(self)
+    ctx = _ctx_of(cls)
+    lv = as_limb_value(raw_value(self))
+    if ctx is None or ctx.binary or lv is None or lv.ctx is not ctx or not lv.size:
+        return _MISS
+    if not isinstance(other, (int, np.integer)) or isinstance(other, (bool, np.bool_)):
+        return _MISS
+    k = int(other) % ctx.modulus
+    store = lv.store if k == 0 else backend.binop_scalar(ctx, _cabi.OP_SUB, lv.store, k)
+    calls['limb_ops'] += 1
+    mask, _ = backend.nonzero(ctx, store)
+    mask = np.asarray(mask, dtype=bool).reshape(lv.shape)
+    return mask if negate else ~mask
 
 
 def shift(self, other, right):

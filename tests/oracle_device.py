@@ -153,6 +153,27 @@ class OracleBackend:
     def sqrt(self, ctx, a, INV):
         return codec.ints_to_limbs(orc.ff_sqrt(ctx.modulus, self._ints(ctx, a), INV=INV), ctx)
 
+    def bits_decompose(self, ctx, c, l, descending):
+        rows = orc.local_bits_decompose(self._ints(ctx, c), l, descending)
+        return codec.ints_to_limbs([b for row in rows for b in row], ctx)
+
+    def transpose(self, ctx, a, rows, cols):
+        a = np.ascontiguousarray(a)
+        return np.ascontiguousarray(a.reshape((rows, cols) + a.shape[1:]).swapaxes(0, 1)).reshape(a.shape)
+
+    def cumsum_rows(self, ctx, a, rows, cols):
+        x = self._ints(ctx, a)
+        p, out, acc = ctx.modulus, [], [0] * cols
+        for j in range(rows):
+            acc = [(s + v) % p for s, v in zip(acc, x[j * cols:(j + 1) * cols])]
+            out.extend(acc)
+        return codec.ints_to_limbs(out, ctx)
+
+    def binop_rows(self, ctx, op, a, b, rows, cols, reflected):
+        x, y = self._ints(ctx, a), self._ints(ctx, b)
+        yy = y * rows
+        return self._op(ctx, op, yy, x) if reflected else self._op(ctx, op, x, yy)
+
     def conv2d(self, ctx, X, W, B, k, r, m, n, v, s):
         if s % 2 == 0 or n < s:
             raise _cabi.UnsupportedFieldError('conv2d: even or oversized filters are not covered')

@@ -80,9 +80,36 @@ def main():
         import atexit
         import json
 
+        sites = {}
+        if os.environ['MPYC_B200_STATS'] == 'sites':     # where limb-backed values become Python ints / get packed
+            from mpyc_b200 import resident, codec
+
+            def caller():
+                f = sys._getframe(2)
+                while f is not None and ('mpyc_b200' in f.f_code.co_filename or 'numpy' in f.f_code.co_filename):
+                    f = f.f_back
+                return f'{os.path.basename(f.f_code.co_filename)}:{f.f_code.co_name}:{f.f_lineno}' if f else '?'
+            orig_mat = resident.LimbValue._materialise
+
+            def mat(self):
+                if self._ints is None:
+                    key = 'materialise ' + caller()
+                    sites[key] = sites.get(key, 0) + 1
+                return orig_mat(self)
+            resident.LimbValue._materialise = mat
+            orig_pack = codec.ints_to_limbs
+
+            def pack(values, ctx, reduce=True):
+                key = 'pack ' + caller()
+                sites[key] = sites.get(key, 0) + 1
+                return orig_pack(values, ctx, reduce=reduce)
+            codec.ints_to_limbs = pack
+
         def _stats():
             from mpyc_b200 import resident
             sys.stderr.write('MPYC_B200_STATS ' + json.dumps({'pid': mpc.pid, **resident.calls}) + '\n')
+            for key, cnt in sorted(sites.items(), key=lambda kv: -kv[1])[:25]:
+                sys.stderr.write(f'MPYC_B200_SITE pid={mpc.pid} {cnt:5d} {key}\n')
         atexit.register(_stats)
     runpy.run_path(program, run_name='__main__')
 

@@ -99,6 +99,21 @@ def test_bits_compose_vs_oracle(p, n, f):
     assert ints(dev.bits_compose(Bt, n, f, descending=True)) == orc.local_bits_compose(p, bits, n, f, descending=True)
 
 
+@pytest.mark.parametrize('p', [P61, P64G, GEN[192], P128], ids=lambda p: f'p{p.bit_length()}_{p % 10000}')
+@pytest.mark.parametrize('f', [1, 2, 5, 6, 16, 17, 37])
+@pytest.mark.parametrize('skip', [1, 2, 3])
+def test_bits_compose_on_a_view_that_starts_mid_buffer(p, f, skip):
+    """Rows of 8- and 24-byte elements start on odd 8-byte boundaries depending on row, f and where the view begins:
+    the head / tail pieces of the staged copy (local.cuh) must agree with the plain result."""
+    ctx = mpyc_b200.context_for(p)
+    n = 519
+    bits = orc.synth_elements(p, n * f + skip, 41 + f, stream=4)
+    whole = DeviceArray.from_ints(ctx, bits)
+    view = DeviceArray(ctx, whole.t[skip:])
+    assert ints(dev.bits_compose(view, n, f)) == orc.local_bits_compose(p, bits[skip:], n, f)
+    assert ints(dev.bits_compose(view, n, f, descending=True)) == orc.local_bits_compose(p, bits[skip:], n, f, descending=True)
+
+
 @pytest.mark.parametrize('p', PRIMES, ids=lambda p: f'p{p.bit_length()}_{p % 10000}')
 @pytest.mark.parametrize('n,l', [(1, 1), (5, 6), (256, 37), (259, 16), (1026, 3)])
 def test_bits_decompose_vs_oracle(p, n, l):
@@ -130,6 +145,45 @@ def test_conv2d_rejects_even_filters():
     z = DeviceArray.from_ints(ctx, [1] * 64)
     with pytest.raises(mpyc_b200.UnsupportedFieldError):
         dev.conv2d(z, DeviceArray.from_ints(ctx, [1] * 4), DeviceArray.from_ints(ctx, [1]), 1, 1, 8, 8, 1, 2)
+
+
+@pytest.mark.parametrize('p', PRIMES, ids=lambda p: f'p{p.bit_length()}_{p % 10000}')
+@pytest.mark.parametrize('R,C', [(1, 1), (3, 5), (38, 33), (32, 64), (5, 1000), (70, 31), (1, 300)])
+def test_matrix_kernels_vs_numpy(p, R, C):
+    """k_transpose / k_cumsum_rows / k_binop_rows / contiguous decompose against NumPy object arithmetic mod p."""
+    ctx = mpyc_b200.context_for(p)
+    m = orc.synth_elements(p, R * C, 43, stream=1)
+    v = orc.synth_elements(p, C, 43, stream=2)
+    m[0] = v[0] = p - 1
+    M, V = DeviceArray.from_ints(ctx, m), DeviceArray.from_ints(ctx, v)
+    Mo, Vo = np.array(m, dtype=object).reshape(R, C), np.array(v, dtype=object)
+    flat = lambda a: [int(t) % p for t in a.reshape(-1)]   # noqa: E731
+    assert ints(dev.transpose(M, R, C)) == flat(Mo.T)
+    assert ints(dev.cumsum_rows(M, R, C)) == flat(np.cumsum(Mo, axis=0))
+    from mpyc_b200 import _cabi
+    assert ints(dev.binop_rows(M, V, _cabi.OP_ADD, R, C)) == flat(Mo + Vo)
+    assert ints(dev.binop_rows(M, V, _cabi.OP_SUB, R, C)) == flat(Mo - Vo)
+    assert ints(dev.binop_rows(M, V, _cabi.OP_SUB, R, C, reflected=True)) == flat(Vo - Mo)
+    assert ints(dev.binop_rows(M, V, _cabi.OP_MUL, R, C)) == flat(Mo * Vo)
+    l = min(p.bit_length(), 37)
+    for desc in (False, True):
+        rows = orc.local_bits_decompose(v, l, descending=desc)
+        assert ints(dev.bits_decompose_flat(V, l, descending=desc)) == [b for row in rows for b in row]
+
+
+def test_transpose_twice_and_cumsum_of_ones_at_size():
+    ctx = mpyc_b200.context_for(P128)
+    R, C = 38, 200_003
+    M = DeviceArray.random(ctx, R * C, seed=47, stream_id=1)
+    assert dev.transpose(dev.transpose(M, R, C), C, R).count_mismatch(M) == 0
+    ones = dev.axpb(M, 0, 1)
+    cs = dev.cumsum_rows(ones, R, C)
+    assert ints(DeviceArray(ctx, cs.t[(R - 1) * C:(R - 1) * C + 3])) == [R, R, R]
+    last = DeviceArray(ctx, dev.cumsum_rows(M, R, C).t[(R - 1) * C:])
+    total = DeviceArray(ctx, M.t[:C])
+    for j in range(1, R):
+        total = total + DeviceArray(ctx, M.t[j * C:(j + 1) * C])
+    assert last.count_mismatch(total) == 0
 
 
 # ---- size-independent properties at sizes the oracle does not reach --------------------------------------------

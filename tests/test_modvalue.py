@@ -109,9 +109,11 @@ def test_np_sgn_prefix_expressions(p):
         z2 = z + (h << l - 1)
         return s_sign, opened, z, Xor, e, z2
     want = run(obj(r_bits), obj(a), obj(rdiv), obj(c_open))
+    before = resident.calls['materialised']
     got = run(mv(ctx, r_bits), mv(ctx, a), mv(ctx, rdiv), mv(ctx, c_open))
-    assert type(got[1]) is ModValue and type(got[5]) is ModValue
-    assert isinstance(got[3], np.ndarray) and isinstance(got[4], np.ndarray)     # matrices of the bit algebra: plain arrays
+    assert resident.calls['materialised'] == before                              # the whole bit-matrix algebra ran on limbs
+    assert all(type(g) is ModValue and g.store is not None for g in got)
+    assert got[3].shape == (l, n) and got[4].shape == (l + 1, n)
     for g, w in zip(got, want):
         assert reduced(ctx, g) == reduced(ctx, w)
 
@@ -168,8 +170,11 @@ def test_unknown_uses_fall_back_to_the_object_array():
     ctx = mpyc_b200.context_for(PRIMES[1])
     vals = [3, 4, 5, 6]
     x = mv(ctx, vals, (2, 2))
-    assert x.T.tolist() == [[3, 5], [4, 6]] and x.store is None                 # .T: settled
+    xt = x.T
+    assert type(xt) is ModValue and xt.shape == (2, 2) and reduced(ctx, xt) == [3, 5, 4, 6]    # 2-D transpose: k_transpose
+    assert x[1, 0] == 5 and x.store is None                                     # fancy indexing: settled
     assert (x + 1).tolist() == [[4, 5], [6, 7]]                                 # a plain array from here on
+    assert isinstance(x, np.ndarray) and type(x) is ModValue                    # what sectypes' isinstance checks see
     y = mv(ctx, vals)
     assert (y + np.array([[1], [2]], dtype=object)).shape == (2, 4)             # broadcasting: NumPy's job
     w = mv(ctx, vals)
@@ -180,3 +185,30 @@ def test_unknown_uses_fall_back_to_the_object_array():
     assert v[np.array([True, False, True, False])].tolist() == [3, 5]
     lv = (mv(ctx, vals) * 2 + 1).limb_value()
     assert type(lv) is LimbValue and [int(t) for t in codec.limbs_to_ints(lv.host_limbs(), ctx)] == [7, 9, 11, 13]
+
+
+
+@pytest.mark.parametrize('p', [PRIMES[1], PRIMES[3]], ids=lambda p: f'p{p.bit_length()}')
+def test_matrix_steps_against_numpy(p):
+    """vstack / cumsum(axis=0) / row broadcast / transpose / right_shift.outer(..).T & 1 on ModValues == NumPy on objects."""
+    ctx = mpyc_b200.context_for(p)
+    R, C = 5, 7
+    m = orc.synth_elements(p, R * C, 9, stream=1)
+    v = orc.synth_elements(p, C, 9, stream=2)
+    M, V = mv(ctx, m, (R, C)), mv(ctx, v)
+    Mo, Vo = obj(m, (R, C)), obj(v)
+    ones = np.ones((1, C), dtype=object)
+    for got, want in ((np.vstack((ones, M)), np.vstack((ones, Mo))), (np.cumsum(M, axis=0), np.cumsum(Mo, axis=0)),
+                      (V - M, Vo - Mo), (M - V, Mo - Vo), (M * V + 3 * M, Mo * Vo + 3 * Mo), (M.T, Mo.T),
+                      (np.vstack((M, M * 2, ones)), np.vstack((Mo, Mo * 2, ones)))):
+        assert type(got) is ModValue and got.shape == want.shape
+        assert reduced(ctx, got) == reduced(ctx, want)
+    for shifts in (np.arange(9), np.arange(8, -1, -1)):
+        assert reduced(ctx, np.right_shift.outer(V, shifts).T & 1) == reduced(ctx, np.right_shift.outer(Vo, shifts).T & 1)
+        assert reduced(ctx, np.right_shift.outer(V, shifts) & 1) == reduced(ctx, np.right_shift.outer(Vo, shifts) & 1)
+    # anything else is NumPy's: settled arrays in, plain arrays out
+    assert np.cumsum(M, axis=1).tolist() == np.cumsum(Mo, axis=1).tolist()
+    assert np.where(np.array([True] * C), mv(ctx, v), 0).tolist() == v
+    assert np.hstack((mv(ctx, v), Vo)).tolist() == v + v
+    import pickle
+    assert pickle.loads(pickle.dumps(mv(ctx, v))).tolist() == v

@@ -45,11 +45,21 @@ def line(name, p, bytes_, ms, **extra):
 def main():
     quick = '--quick' in sys.argv
     torch.cuda.set_device(0)
-    primes = [2**64 - 189, 2**128 - 173, 2**256 - 189, 9409569905028393239]
+    primes = [2**64 - 189, 2**128 - 173, 2**256 - 189, 9409569905028393239, 2**69 - 93,
+              0x8000000000000000000000000000000000000000000004c7]    # the last: a generic 192-bit prime (3 limbs)
+    if '--only-compose' in sys.argv:      # short run for an ncu capture: k_bits_compose on the 128-bit field, f = 37 and 6
+        p = 2**128 - 173
+        ctx = mpyc_b200.context_for(p)
+        A = DeviceArray.random(ctx, 1 << 26, seed=5, stream_id=1)
+        for f in (37, 6):
+            rows = A.n // f
+            bits = DeviceArray(ctx, A.t[:rows * f])
+            line('bits_compose', p, (f + 1) * 16 * rows, timed(lambda: dev.bits_compose(bits, rows, f), reps=3, warm=2), n=rows, f=f)
+        return
     for p in primes:
         ctx = mpyc_b200.context_for(p)
         E = 8 * ctx.nlimbs
-        n = (1 << 26) * 8 // E if not quick else (1 << 22)
+        n = (1 << 30) // E if not quick else (1 << 22)          # 1 GiB per operand
         A, B, C = (DeviceArray.random(ctx, n, seed=5, stream_id=i) for i in (1, 2, 3))
         line('fma a*b+c', p, 4 * E * n, timed(lambda: dev.fma(A, B, C)), n=n)
         line('fma a*a+c', p, 3 * E * n, timed(lambda: dev.fma(A, None, C)), n=n)
@@ -57,7 +67,7 @@ def main():
         line('low_bits', p, 2 * E * n, timed(lambda: dev.low_bits(A, 37)), n=n)
         line('nonzero(count)', p, E * n, timed(lambda: dev.nonzero(A, want_mask=False)), n=n)
         del B
-        for f in (6, 37, 64):
+        for f in (6, 16, 37, 64):
             rows = n // f
             bits = DeviceArray(ctx, A.t[:rows * f])
             for desc in (False, True):
