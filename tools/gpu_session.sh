@@ -11,6 +11,8 @@
 #   scale_N      (gpurun --gpus N) the driver's N-GPU launch line: multi_selftest, gather timing, e2e over all ranks; N=2 also tests/test_gpu_multi.py
 #   overlap      tools/time_e2e_overlap.py at three pipeline chunk sizes
 #   variants_<cfg>  bench a config with every libmpyc_b200_*.so tuning build present
+#   local        K6 protocol-local kernels: tests/test_gpu_local.py, tools/time_local.py, ncu capture of k_bits_compose
+#   demos2       np_cnnmnist -M3 (batch 1 and 4) with / without the engine, -M7 -T3 256-bit with the engine
 #   sass         per-kernel SASS / ptxas summary (no GPU needed, also runs in the build container)
 set -u
 OUT=gpurun_out
@@ -91,6 +93,27 @@ for step in "$@"; do
         echo "# $lib" >> $OUT/r02_variants_$cfg.txt
         MPYC_B200_LIB=$lib python bench.py --config $cfg --steps 10 --no-cpu --no-e2e --no-extras --sustain 0 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print(r['kernel'], round(r['frac'],4), round(r['ms'],4), 'rec', round(r.get('recombine',{}).get('frac',0),4), 'value', d['value'])" >> $OUT/r02_variants_$cfg.txt 2>&1
       done; cat $OUT/r02_variants_$cfg.txt ;;
+    local)
+      # the protocol-local kernels (K6): parity tests, timings, one ncu --set full capture of k_bits_compose
+      bash tools/gpu_local_session.sh ;;
+    demos2)
+      # np_cnnmnist with the engine (resident + local algebra) after the K6 work, and the plain reference on the same box
+      : > $OUT/r02_demos2.txt
+      P256=0xffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffff43
+      cd $REFDIR/_checkout/demos
+      run_demo2() {   # label, harness, extra env, args...
+        label=$1; h=$2; extra=$3; shift 3
+        s=$(date +%s.%N)
+        res=$(env $extra MPYC_B200_STATS=1 MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h MPYC_REFERENCE=$REFDIR timeout 900 python $OLDPWD/tests/run_installed.py "$@" -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | grep -E "predicted|pid\": 0|^ *\[|^ *-?[0-9]" | tail -n 4 | tr '\n' ' ')
+        e=$(date +%s.%N)
+        echo "$label | harness=$h | wall=$(python -c "print(round($e - $s, 2))") s | $res" >> $OLDPWD/$OUT/r02_demos2.txt
+      }
+      run_demo2 "np_cnnmnist -M3 (69-bit default field)" off "X=1" np_cnnmnist.py 1 0 -M3
+      run_demo2 "np_cnnmnist -M3 (69-bit default field)" install,resident "X=1" np_cnnmnist.py 1 0 -M3
+      run_demo2 "np_cnnmnist -M3 batch 4" off "X=1" np_cnnmnist.py 4 0 -M3
+      run_demo2 "np_cnnmnist -M3 batch 4" install,resident "X=1" np_cnnmnist.py 4 0 -M3
+      run_demo2 "np_cnnmnist -M7 -T3 256-bit prime (configs[4])" install,resident,spread "MPYC_B200_FORCE_PRIME=$P256" np_cnnmnist.py 1 0 -M7 -T3
+      cd $OLDPWD; cat $OUT/r02_demos2.txt ;;
     sass)
       python tools/sass_summary.py > $OUT/r02_sass_summary.txt 2>&1; tail -5 $OUT/r02_sass_summary.txt ;;
     *) echo "unknown step $step" ;;
