@@ -224,8 +224,8 @@ k_bits_decompose(const u64* __restrict__ c, u64* __restrict__ out, size_t ostrid
 
 // ---------------------------------------------------------------------------------------
 // k_bits_compose: out[i] = sum_j bits[i*f + j] * 2^e(j) mod p;  e(j) = j or f-1-j.  `bits` are arbitrary residues
-// (shares of bits).  Horner in the bit position from the top exponent: acc = 2 acc + x over an (L+1)-limb
-// accumulator, one reduction per 32 columns.
+// (shares of bits).  Horner over groups of 32 bit positions from the top exponent; inside a group every 32-bit limb of an
+// element is multiplied by its power of two and accumulated with one IMAD.WIDE (no carries), one reduction per group.
 //
 // Memory: row i of the (n, f) input is f*E contiguous bytes -- a thread walking its own row would touch one sector
 // per warp lane and instruction.  So a CTA stages a tile of 256 rows x JB columns (~128 bytes of each row) in shared
@@ -348,9 +348,17 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
 
 #pragma unroll
     for (int s = 0; s < C::STAGES - 1; s++) issue(s);
-    u32 acc[N + 2];
-    zero_n<N + 2>(acc);
-    int since = 0;                                       // columns folded into acc since the last reduction
+    // Horner over groups of up to 32 columns; inside a group column q (in Horner order) has the weight 2^(cnt-1-q), and
+    // every 32-bit limb of the element is accumulated on its own: wacc[i] += x[i] * 2^(cnt-1-q) is ONE IMAD.WIDE.U32 and
+    // cannot overflow 64 bits within 32 columns -- no carry chains in the inner loop.  A finished group G < 2^32 p is
+    // folded as res = (res << cnt) + G mod p.
+    u64 wacc[N];
+    u32 res[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) wacc[i] = 0;
+    zero_n<N>(res);
+    int idx = 0, cnt = 0;                                // column index within the row (Horner order), size of its group
+    u32 w = 0;
     for (size_t u = 0; u < units; u++) {
         asm volatile("cp.async.wait_group %0;" ::"n"(C::STAGES - 2) : "memory");
         __syncthreads();                                 // stage u has landed for every thread; stage u-1 is free
@@ -360,31 +368,50 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
         const size_t row = tile * MPYC_THREADS + t;
         int col0, ncols;
         block_cols(b, col0, ncols);
+        if (b == 0) idx = 0;
         if (row < n) {
             const u32 base = smem0 + (u32)(u % C::STAGES) * stage_bytes + t * pitch + row_shift(row, col0);
-            for (int cidx = 0; cidx < ncols; cidx++) {
+            for (int cidx = 0; cidx < ncols; cidx++, idx++) {
                 const int lc = descending ? cidx : ncols - 1 - cidx;
                 u32 x[N];
                 lds_elem<L>(x, base + lc * C::EB);
+                if ((idx & 31) == 0) {                   // a new group starts (warp-uniform)
+                    cnt = min(32, fcols - idx);
+                    w = 1u << (cnt - 1);
+                }
 #pragma unroll
-                for (int i = N + 1; i > 0; i--) acc[i] = __funnelshift_l(acc[i - 1], acc[i], 1);
-                acc[0] <<= 1;
-                acc_add<N, N + 2>(acc, x);
-                if (++since == 32) {                     // acc < 2^33 p: fold (warp-uniform)
-                    u32 r[N];
-                    F::reduce_small(r, acc, f);
-                    zero_n<N + 2>(acc);
-                    copy_n<N>(acc, r);
-                    since = 0;
+                for (int i = 0; i < N; i++) wacc[i] += (u64)x[i] * w;
+                w >>= 1;
+                if (w == 0) {                            // group complete: fold it into the running result
+                    u32 acc[N + 2];
+                    u64 c = wacc[0];
+                    acc[0] = (u32)c;
+                    c >>= 32;
+#pragma unroll
+                    for (int i = 1; i < N; i++) {
+                        c += wacc[i];                    // < 2^64: wacc[i] <= (2^32-1)^2, carry-in <= 2^32
+                        acc[i] = (u32)c;
+                        c >>= 32;
+                    }
+                    acc[N] = (u32)c;
+                    acc[N + 1] = (u32)(c >> 32);
+                    u32 sh[N + 1];                       // res << cnt, cnt in 1..32 (clamping funnel shift: 32 moves whole limbs)
+                    sh[0] = __funnelshift_lc(0u, res[0], cnt);
+#pragma unroll
+                    for (int i = 1; i < N; i++) sh[i] = __funnelshift_lc(res[i - 1], res[i], cnt);
+                    sh[N] = __funnelshift_lc(res[N - 1], 0u, cnt);
+                    acc_add<N + 1, N + 2>(acc, sh);      // < 2^33 p
+                    F::reduce_small(res, acc, f);
+#pragma unroll
+                    for (int i = 0; i < N; i++) wacc[i] = 0;
                 }
             }
-            if (b == nblk - 1) {
-                u32 r[N];
-                F::reduce_small(r, acc, f);
-                stg_elem<L>(out + row * L, r);
-                zero_n<N + 2>(acc);
-                since = 0;
+            if (b == nblk - 1) {                         // the last group ended with the row's last column
+                stg_elem<L>(out + row * L, res);
+                zero_n<N>(res);
             }
+        } else if (b == nblk - 1) {
+            idx = 0;
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
