@@ -671,7 +671,7 @@ def measure_local(peak, steps=5, warmup=3):
     for label, p in (('p128', 2**128 - 173), ('p64', 2**64 - 189), ('p256', 2**256 - 189)):
         ctx = mpyc_b200.context_for(p)
         E = 8 * ctx.nlimbs
-        n = (1 << 29) // E                                   # 512 MiB per operand
+        n = (1 << 30) // E                                   # 1 GiB per operand
         A = DeviceArray.random(ctx, n, seed=5, stream_id=1)
         C = DeviceArray.random(ctx, n, seed=5, stream_id=3)
         res = {'fma_square_add': entry(3 * E * n, timed(lambda: dev.fma(A, None, C)), n=n),
