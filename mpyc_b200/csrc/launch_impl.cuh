@@ -542,8 +542,8 @@ cudaError_t Launch<L>::cumsum_rows(const FieldParams& fp, const u64* in, u64* ou
 template <int L>
 cudaError_t Launch<L>::binop_rows(const FieldParams& fp, int op, bool reflected, const u64* a, const u64* b, u64* out, size_t R,
                                   size_t C, cudaStream_t st) {
-    if (L % 2 == 0 && (!aligned16(a) || !aligned16(out))) return cudaErrorMisalignedAddress;
-    const size_t total = R * C;
+    if (L % 2 == 0 && (!aligned16(a) || !aligned16(b) || !aligned16(out))) return cudaErrorMisalignedAddress;
+    const size_t total = C;            // a thread per column
 #define ROWS_CASE(K, OPC)                                                                                   \
     return reflected ? launch_kernel(k_binop_rows<L, K, OPC, true>, total, 0, st, fp, a, b, out, R, C)      \
                      : launch_kernel(k_binop_rows<L, K, OPC, false>, total, 0, st, fp, a, b, out, R, C)

@@ -315,16 +315,24 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
     // copy slot k of row (t >> 3) + 32 r: 8 consecutive threads fetch the contiguous chunk of one row, a warp 4 rows
     const int kslot = t & (C::G - 1), rsub = t >> 3;
     const size_t row_bytes = (size_t)fcols * C::EB;
+    // (tile, column block) of the next unit to fetch and of the next unit to consume, advanced without divisions
+    size_t itile = blockIdx.x, ctile = blockIdx.x;
+    int ib = 0, cb = 0;
+    u32 istage = 0, cstage = 0;                          // shared-memory stage of the next fetch / of the next consume
     auto issue = [&](size_t u) {
         if (u < units) {
-            const size_t tile = blockIdx.x + (u / nblk) * gridDim.x;
+            const size_t tile = itile;
             int col0, ncols;
-            block_cols((int)(u % nblk), col0, ncols);
+            block_cols(ib, col0, ncols);
+            if (++ib == nblk) {
+                ib = 0;
+                itile += gridDim.x;
+            }
             const size_t row0 = tile * MPYC_THREADS;
             const int rows = (int)min((size_t)MPYC_THREADS, n - row0);
             const int rb = ncols * C::EB;               // bytes of one row chunk
             const unsigned char* tbase = gbase + (row0 * (size_t)fcols + col0) * C::EB;
-            const u32 stage = smem0 + (u32)(u % C::STAGES) * stage_bytes;
+            const u32 stage = smem0 + istage * stage_bytes;
 #pragma unroll
             for (int r = 0; r < MPYC_THREADS / (MPYC_THREADS / C::G); r++) {
                 const int row = rsub + (MPYC_THREADS / C::G) * r;
@@ -343,6 +351,7 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
                 }
             }
         }
+        if (++istage == C::STAGES) istage = 0;
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -363,14 +372,18 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
         asm volatile("cp.async.wait_group %0;" ::"n"(C::STAGES - 2) : "memory");
         __syncthreads();                                 // stage u has landed for every thread; stage u-1 is free
         issue(u + C::STAGES - 1);
-        const size_t tile = blockIdx.x + (u / nblk) * gridDim.x;
-        const int b = (int)(u % nblk);
+        const size_t tile = ctile;
+        const int b = cb;
+        if (++cb == nblk) {
+            cb = 0;
+            ctile += gridDim.x;
+        }
         const size_t row = tile * MPYC_THREADS + t;
         int col0, ncols;
         block_cols(b, col0, ncols);
         if (b == 0) idx = 0;
         if (row < n) {
-            const u32 base = smem0 + (u32)(u % C::STAGES) * stage_bytes + t * pitch + row_shift(row, col0);
+            const u32 base = smem0 + cstage * stage_bytes + t * pitch + row_shift(row, col0);
             for (int cidx = 0; cidx < ncols; cidx++, idx++) {
                 const int lc = descending ? cidx : ncols - 1 - cidx;
                 u32 x[N];
@@ -410,9 +423,8 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
                 stg_elem<L>(out + row * L, res);
                 zero_n<N>(res);
             }
-        } else if (b == nblk - 1) {
-            idx = 0;
         }
+        if (++cstage == C::STAGES) cstage = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -534,7 +546,18 @@ k_cumsum_rows(FieldParams f, const u64* __restrict__ in, u64* __restrict__ out, 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += nth) {
         u32 acc[N];
         zero_n<N>(acc);
-        for (size_t j = 0; j < R; j++) {
+        size_t j = 0;
+        for (; j + 4 <= R; j += 4) {                     // four rows requested before the first addition
+            u32 x[4][N];
+#pragma unroll
+            for (int q = 0; q < 4; q++) ldg_elem<L>(x[q], in + ((j + q) * C + i) * L);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                Fp<L, KIND>::add(acc, acc, x[q], f);
+                stg_elem<L>(out + ((j + q) * C + i) * L, acc);
+            }
+        }
+        for (; j < R; j++) {
             u32 x[N];
             ldg_elem<L>(x, in + (j * C + i) * L);
             Fp<L, KIND>::add(acc, acc, x, f);
@@ -543,24 +566,36 @@ k_cumsum_rows(FieldParams f, const u64* __restrict__ in, u64* __restrict__ out, 
     }
 }
 
-// out[j][i] = a[j][i] (op) b[i], or b[i] (op) a[j][i] when REFLECT; a: (R, C), b: (C)
+// out[j][i] = a[j][i] (op) b[i], or b[i] (op) a[j][i] when REFLECT; a: (R, C), b: (C).  A thread owns a column (b[i] is
+// loaded once) and walks down the rows, which are coalesced across the warp; ROWS_PER rows are in flight per trip.
 template <int L, int KIND, int OP, bool REFLECT>
 __global__ void MPYC_LB
 k_binop_rows(FieldParams f, const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, size_t R, size_t C) {
     constexpr int N = 2 * L;
-    const size_t nth = (size_t)gridDim.x * blockDim.x, total = R * C;
-    for (size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x; h < total; h += nth) {
-        u32 x[N], y[N], r[N];
-        ldg_elem<L>(x, a + h * L);
-        const u64* bp = b + (h % C) * L;
+    constexpr int ROWS_PER = 4;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += nth) {
+        u32 y[N];
+        ldg_elem<L>(y, b + i * L);
+        size_t j = 0;
+        for (; j + ROWS_PER <= R; j += ROWS_PER) {
+            u32 x[ROWS_PER][N];
 #pragma unroll
-        for (int q = 0; q < L; q++) {
-            const u64 w = __ldg(bp + q);
-            y[2 * q] = (u32)w;
-            y[2 * q + 1] = (u32)(w >> 32);
+            for (int q = 0; q < ROWS_PER; q++) ldg_elem<L>(x[q], a + ((j + q) * C + i) * L);
+#pragma unroll
+            for (int q = 0; q < ROWS_PER; q++) {
+                u32 r[N];
+                if constexpr (REFLECT) apply_op<L, KIND, OP>(r, y, x[q], f);
+                else apply_op<L, KIND, OP>(r, x[q], y, f);
+                stg_elem<L>(out + ((j + q) * C + i) * L, r);
+            }
         }
-        if constexpr (REFLECT) apply_op<L, KIND, OP>(r, y, x, f);
-        else apply_op<L, KIND, OP>(r, x, y, f);
-        stg_elem<L>(out + h * L, r);
+        for (; j < R; j++) {
+            u32 x[N], r[N];
+            ldg_elem<L>(x, a + (j * C + i) * L);
+            if constexpr (REFLECT) apply_op<L, KIND, OP>(r, y, x, f);
+            else apply_op<L, KIND, OP>(r, x, y, f);
+            stg_elem<L>(out + (j * C + i) * L, r);
+        }
     }
 }

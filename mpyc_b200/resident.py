@@ -321,7 +321,8 @@ for _name in ('getitem', 'setitem', 'iter', 'contains', 'add', 'radd', 'iadd', '
 # ---------------------------------------------------------------------------------------------
 
 class ModValue:
-    """What `array.value` returns to np_random_bits / np_trunc / np_sgn (`_MOD_SOURCES`) while the elements are limbs.
+    """What `array.value` returns to np_random_bits / np_trunc / np_sgn / np_to_bits (`_MOD_SOURCES`) while the elements are
+    limbs.
 
     Those functions compute on raw share values with NumPy object arithmetic -- `_r.value**2 + z.value`,
     `np.sum(r_bits.value.reshape((n, f)) << np.arange(f), axis=1)`, `ar_modf + (1 << l-1) + (r_divf << f)`,
@@ -574,8 +575,8 @@ class ModValue:
         n = self._scalar(k)
         if n is not None and n >= 0:
             return self._ring(pow(2, n, self.ctx.modulus), '*')
-        if (isinstance(k, np.ndarray) and k.ndim == 1 and k.dtype.kind in 'iu' and len(self.shape) == 2
-                and k.shape[0] == self.shape[1] and k.shape[0] > 0):
+        if (isinstance(k, np.ndarray) and type(k) is np.ndarray and k.ndim == 1 and k.dtype.kind in 'iu' and len(self.shape) >= 2
+                and k.shape[0] == self.shape[-1] and k.shape[0] > 0 and self.size):
             f = k.shape[0]
             if np.array_equal(k, np.arange(f)):
                 return _ShiftedBits(self, k, False)
@@ -735,18 +736,20 @@ for _name in ('contains', 'matmul', 'rmatmul', 'imatmul', 'rmod', 'floordiv', 'r
 
 
 class _ShiftedBits:
-    """`value.reshape((n, f)) << shifts` with shifts = arange(f) or arange(f-1, -1, -1): summed along axis 1 by the
-    k_bits_compose kernel (runtime.py:860, 3650-3651); any other use evaluates the shift on the object array."""
+    """`value << shifts` for a value of shape (..., f) and shifts = arange(f) or arange(f-1, -1, -1): summed along the last
+    axis by the k_bits_compose kernel (runtime.py:860, 3650-3651, 4415); any other use evaluates the shift on the object
+    array."""
 
     def __init__(self, base, shifts, descending):
         self.base, self.shifts, self.descending = base, shifts, descending
 
     def sum(self, axis=None, out=None, **kwargs):
         b = self.base
-        if b.store is not None and axis in (1, -1) and out is None and not kwargs:
-            n, f = b.shape
+        if b.store is not None and axis in (len(b.shape) - 1, -1) and out is None and not kwargs:
+            f = b.shape[-1]                              # the bit positions are the last axis (runtime.py:860, 4415)
+            n = b.size // f
             calls['limb_ops'] += 1
-            return b._new(backend.bits_compose(b.ctx, b._flush(), n, f, self.descending), (n,))
+            return b._new(backend.bits_compose(b.ctx, b._flush(), n, f, self.descending), b.shape[:-1])
         return self._eval().sum(axis=axis, out=out, **kwargs)
 
     def _eval(self):
@@ -847,6 +850,7 @@ _MOD_SOURCES = {
     'np_random_bits': '26b092e612b3091d4ac89237593b4069fa5eee590abcbe21077d13b992bf3868',     # runtime.py:4187-4273
     'np_trunc': 'e6354dbb71d6369d8bef9b065bef0cb65b1dc55631634954792f7945e087e3ad',           # runtime.py:838-872
     'np_sgn': '936eb16da844a41f636537f44306b80fff9aea3834ba205e187e6ba5a24547ad',             # runtime.py:3622-3694
+    'np_to_bits': 'fb87bacf263e7c49f50422bba78d6bbf24fb200bc068983a511619da6bd16c1a',         # runtime.py:4391-4441
 }
 
 

@@ -212,3 +212,28 @@ def test_matrix_steps_against_numpy(p):
     assert np.hstack((mv(ctx, v), Vo)).tolist() == v + v
     import pickle
     assert pickle.loads(pickle.dumps(mv(ctx, v))).tolist() == v
+
+
+@pytest.mark.parametrize('p', [PRIMES[1], PRIMES[3]], ids=lambda p: f'p{p.bit_length()}')
+def test_np_to_bits_expressions(p):
+    """runtime.py:4413-4433: bit positions on the LAST axis of an N-d value; `c % (1<<l)`; public bits through np.int8."""
+    ctx = mpyc_b200.context_for(p)
+    shape, l, bl = (3, 2), 9, 20
+    n = 6
+    r_bits = orc.synth_elements(p, n * l, 21, stream=1)
+    rdiv = orc.synth_elements(p, n, 21, stream=2)
+    c_open = orc.synth_elements(p, n, 21, stream=3)
+    shifts = np.arange(l)
+
+    def run(rb, rd, cv):
+        r_modl = np.sum(rb.reshape(shape + (l,)) << shifts, axis=-1)                 # :4415
+        masked = (1 << bl) + (rd.reshape(shape) << l) - r_modl                        # :4431
+        c = cv % (1 << l)                                                             # :4432
+        c_bits = np.int8(np.right_shift.outer(c, shifts) & 1)                         # :4433
+        return r_modl, masked, c, c_bits
+    want = run(obj(r_bits), obj(rdiv), obj(c_open))
+    got = run(mv(ctx, r_bits), mv(ctx, rdiv), mv(ctx, c_open))
+    assert type(got[0]) is ModValue and got[0].shape == shape and type(got[1]) is ModValue and type(got[2]) is ModValue
+    for g, w in zip(got[:3], want[:3]):
+        assert reduced(ctx, g) == reduced(ctx, w)
+    assert got[3].dtype == np.int8 and got[3].tolist() == want[3].tolist()

@@ -77,7 +77,15 @@ def main():
             rows = n // l
             c = DeviceArray(ctx, C.t[:rows])
             line('bits_decompose', p, (l + 1) * E * rows, timed(lambda: dev.bits_decompose(c, l, descending=True)), n=rows, l=l)
-        del A, C
+        R = 38                                                  # np_sgn's matrices: (l + 1, n) with l = 37
+        cols = n // R
+        Mx = DeviceArray(ctx, A.t[:R * cols])
+        Vx = DeviceArray(ctx, C.t[:cols])
+        from mpyc_b200 import _cabi
+        line('transpose', p, 2 * E * R * cols, timed(lambda: dev.transpose(Mx, cols, R)), rows=cols, cols=R)
+        line('cumsum_rows', p, 2 * E * R * cols, timed(lambda: dev.cumsum_rows(Mx, R, cols)), rows=R, cols=cols)
+        line('binop_rows', p, (2 * R + 1) * E * cols, timed(lambda: dev.binop_rows(Mx, Vx, _cabi.OP_SUB, R, cols, reflected=True)), rows=R, cols=cols)
+        del A, C, Mx, Vx
         # np_cnnmnist's two convolution layers at batch 8 (demos/np_cnnmnist.py: 1->16 5x5 on 28x28, 16->16 5x5 on 14x14)
         for (k, r, m, nn, v, s) in ((8, 1, 28, 28, 16, 5), (8, 16, 14, 14, 16, 5)):
             X = DeviceArray.random(ctx, k * r * m * nn, seed=7, stream_id=1)
