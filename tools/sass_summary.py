@@ -16,7 +16,11 @@ OBJ = os.path.join(ROOT, 'mpyc_b200', 'csrc', '_obj')
 DEFAULT = [r'k_split<2, 1, 3, 0, 1>', r'k_split<2, 0, 3, 0, 1>', r'k_split<1, 1, 2, 0, 1>', r'k_split<4, 1, 4, 0, 1>',
            r'k_split_gen<2, 1, 3, 0, 1, StridedDst>', r'k_recombine_small<2, 1, 1>', r'k_recombine<2, 0, 1>', r'k_recombine<1, 1, 1>',
            r'k_recombine_small<4, 1, 1>', r'k_binop<1, 1, 2, 0, 1>', r'k_binop<1, 0, 2, 0, 1>', r'k_prss_tiles<4, 1, 1, 1, 1>',
-           r'k_prss_tiles<4, 1, 1, 1, 0>', r'k_matmul<2, 1', r'k_inv_batch<2, 1>', r'k_prf_reduce<', r'k_gf_split', r'k_gf_recombine']
+           r'k_prss_tiles<4, 1, 1, 1, 0>', r'k_matmul<2, 1', r'k_inv_batch<2, 1>', r'k_prf_reduce<', r'k_gf_split', r'k_gf_recombine',
+           # K6, the protocols' raw-value algebra (local.cuh): LDGSTS = cp.async pieces of k_bits_compose
+           r'k_bits_compose<2, 1>', r'k_bits_compose<1, 1>', r'k_bits_compose<4, 1>', r'k_bits_decompose<2, 1>', r'k_fma<2, 1, 1, 1>',
+           r'k_axpb<2, 1, 1>', r'k_low_bits<2, 1>', r'k_nonzero<2, 1>', r'k_transpose<2>', r'k_cumsum_rows<2, 1>', r'k_binop_rows<2, 1, 1, 1>',
+           r'k_conv2d<2, 1>']
 
 
 def demangle(names):
@@ -51,9 +55,9 @@ def main():
                 return sum(1 for i in ins if re.match(rx, i))
             reg, stack, shared, local = usage.get(name, (None, None, None, None))
             rows.append((dem, len(ins), cnt(r'UBLKCP'), cnt(r'LDG\.E.*\.256|LDG.*256'), cnt(r'STG\.E.*\.256|STG.*256'), cnt(r'LDG'), cnt(r'STG'),
-                         cnt(r'IMAD\.WIDE'), cnt(r'IMAD'), cnt(r'IADD3|IADD'), cnt(r'LOP3|SHF|SEL'), cnt(r'LDS|STS'),
+                         cnt(r'IMAD\.WIDE'), cnt(r'IMAD'), cnt(r'IADD3|IADD'), cnt(r'LOP3|SHF|SEL'), cnt(r'LDS|STS'), cnt(r'LDGSTS'),
                          cnt(r'HMMA|IMMA|UTCMMA|UTMALDG'), reg, stack, local, shared))
-    hdr = ('kernel', 'SASS', 'UBLKCP', 'LDG256', 'STG256', 'LDG', 'STG', 'IMAD.W', 'IMAD*', 'IADD3', 'LOP/SHF/SEL', 'LDS/STS', 'tensor', 'regs',
+    hdr = ('kernel', 'SASS', 'UBLKCP', 'LDG256', 'STG256', 'LDG', 'STG', 'IMAD.W', 'IMAD*', 'IADD3', 'LOP/SHF/SEL', 'LDS/STS', 'LDGSTS', 'tensor', 'regs',
            'stack', 'local', 'smem')
     print('# static SASS / resource summary of the hot kernels (sm_100a), tools/sass_summary.py')
     print(('%-44s' + ' %7s' * (len(hdr) - 1)) % hdr)
