@@ -507,11 +507,14 @@ k_conv2d(FieldParams f, const u64* __restrict__ X, const u64* __restrict__ W, co
 // `s_sign - np.vstack((c_bits - r_bits, ones)) + 3*SumXors`.
 // ---------------------------------------------------------------------------------------
 
-// out (C, R) = in (R, C)^T: 32 x 32 element tiles through shared memory, both sides coalesced along their rows
+// out (C, R) = in (R, C)^T: 32 x 32 element tiles through shared memory.  A warp moves the 32 elements of a row segment
+// as 32 L consecutive 64-bit words (coalesced whatever L is); the tile is kept limb-planar, tile[limb][row][col], with the
+// planes offset by 32 / L banks so that both the row-wise fill and the column-wise drain are conflict-free.
 template <int L>
 __global__ void MPYC_LB
 k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t C) {
-    __shared__ u64 tile[32][33 * L];
+    constexpr int PLANE = 32 * 33 + (L == 3 ? 5 : 16 / L);
+    __shared__ u64 tile[L * PLANE];
     const size_t tc = (C + 31) / 32, tr = (R + 31) / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
     for (size_t w = blockIdx.x; w < tc * tr; w += gridDim.x) {
@@ -519,19 +522,27 @@ k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t 
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const size_t r = r0 + ty + 8 * k, c = c0 + tx;
-            if (r < R && c < C) {
+            const size_t r = r0 + ty + 8 * k;                    // input row
+            if (r < R) {
+                const u64* src = in + (r * C + c0) * L;
 #pragma unroll
-                for (int q = 0; q < L; q++) tile[ty + 8 * k][tx * L + q] = in[(r * C + c) * L + q];
+                for (int q = 0; q < L; q++) {
+                    const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
+                    if (c0 + e < C) tile[lb * PLANE + (ty + 8 * k) * 33 + e] = src[idx];
+                }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const size_t c = c0 + ty + 8 * k, r = r0 + tx;       // out row = input column
-            if (r < R && c < C) {
+            const size_t c = c0 + ty + 8 * k;                    // output row = input column
+            if (c < C) {
+                u64* dst = out + (c * R + r0) * L;
 #pragma unroll
-                for (int q = 0; q < L; q++) out[(c * R + r) * L + q] = tile[tx][(ty + 8 * k) * L + q];
+                for (int q = 0; q < L; q++) {
+                    const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
+                    if (r0 + e < R) dst[idx] = tile[lb * PLANE + e * 33 + (ty + 8 * k)];
+                }
             }
         }
     }

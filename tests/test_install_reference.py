@@ -185,3 +185,54 @@ def test_coverage_is_decided_per_call_never_raises_where_the_reference_computes(
             thresha.np_pseudorandom_share(F, 1, 0, prfs, b'uci', 9)
     finally:
         inst.uninstall()
+
+
+def test_limb_backed_field_arrays_keep_their_limbs_through_the_hooked_operators(mpyc_thresha, monkeypatch):
+    """install(resident=True) on the reference's own finfields: << >> (+ in place), contiguous __getitem__, np.concatenate
+    (axis 0), == / != with a scalar and + - * on limb-backed arrays give what the reference gives on object arrays, without
+    turning the operands into Python ints; uninstall() restores every method."""
+    thresha, finfields, gfpx = mpyc_thresha
+    import numpy as np
+    from mpyc_b200 import install as inst, resident, codec
+    import mpyc_b200
+    import oracle_device
+    oracle_device.patch(monkeypatch)
+    oracle_device.patch_resident(monkeypatch)
+    p = 2**128 - 173
+    F = finfields.GF(p)
+    ctx = mpyc_b200.context_for(p)
+    vals = [(7 * i * i + 3) % p for i in range(12)] + [0, p - 1]
+    plain = F.array(np.array(vals, dtype=object).reshape(7, 2))
+    before = {name: F.array.__mro__[2].__dict__.get(name) for name in ('__getitem__', '__eq__', '__lshift__')}
+    inst.install(thresha, resident=True, finfields_module=finfields, operators_min_size=1)
+    try:
+        def limb():
+            return F.array(resident.LimbValue(ctx, codec.ints_to_limbs(vals, ctx), (7, 2)), check=False)
+
+        def backed(a):
+            return resident.as_limb_value(resident.raw_value(a)) is not None
+        start = resident.calls['materialised']
+        pairs = [(limb() << 5, plain << 5), (limb() >> 3, plain >> 3), (limb()[2:5], plain[2:5]), (limb()[-1], plain[-1]),
+                 (limb()[1:], plain[1:]), (np.concatenate((limb()[:1], limb()[3:]), axis=0), np.concatenate((plain[:1], plain[3:]), axis=0)),
+                 (limb() * limb() + limb() - 5, plain * plain + plain - 5)]
+        x = limb()
+        x <<= 2
+        x >>= 7
+        y = plain.copy()
+        y <<= 2
+        y >>= 7
+        pairs.append((x, y))
+        assert all(backed(g) for g, _ in pairs)
+        assert resident.calls['materialised'] == start               # nothing became a Python int so far
+        for g, w in pairs:
+            assert g.shape == w.shape and [int(v) for v in g.value.reshape(-1)] == [int(v) for v in w.value.reshape(-1)]
+        for k in (0, p - 1, vals[3], -1):
+            assert ((limb() == k) == (plain == k)).all() and ((limb() != k) == (plain != k)).all()
+        assert (limb() == 0).dtype == bool and (limb() == 0).shape == (7, 2)
+        # selections that are not one contiguous run, and other axes, are the reference's business (object arrays)
+        assert [int(v) for v in limb()[::2].value.reshape(-1)] == [int(v) for v in plain[::2].value.reshape(-1)]
+        assert [int(v) for v in limb()[:, 1].value] == [int(v) for v in plain[:, 1].value]
+        assert np.concatenate((limb(), limb()), axis=1).shape == (7, 4)
+    finally:
+        inst.uninstall()
+    assert all(F.array.__mro__[2].__dict__.get(name) is fn for name, fn in before.items())
