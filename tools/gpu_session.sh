@@ -13,6 +13,7 @@
 #   variants_<cfg>  bench a config with every libmpyc_b200_*.so tuning build present
 #   local        K6 protocol-local kernels: tests/test_gpu_local.py, tools/time_local.py, ncu capture of k_bits_compose
 #   demos2       np_cnnmnist -M3 (batch 1 and 4) with / without the engine, -M7 -T3 256-bit with the engine
+#   compare      tests/programs/resident_compare.py (np_sgn / np_trunc through the runtime), 3 parties: off vs resident
 #   sass         per-kernel SASS / ptxas summary (no GPU needed, also runs in the build container)
 set -u
 OUT=gpurun_out
@@ -114,6 +115,17 @@ for step in "$@"; do
       run_demo2 "np_cnnmnist -M3 batch 4" install,resident "X=1" np_cnnmnist.py 4 0 -M3
       run_demo2 "np_cnnmnist -M7 -T3 256-bit prime (configs[4])" install,resident,spread "MPYC_B200_FORCE_PRIME=$P256" np_cnnmnist.py 1 0 -M7 -T3
       cd $OLDPWD; cat $OUT/r02_demos2.txt ;;
+    compare)
+      # secure comparison (np_sgn) and fixed-point product (np_trunc) through the unmodified runtime, 3 parties on one GPU
+      : > $OUT/r02_compare.jsonl
+      for n in 20000 100000; do
+        for h in off install,resident; do
+          if [ "$h" = "off" ] && [ "$n" != "20000" ]; then continue; fi
+          echo "# harness=$h n=$n" >> $OUT/r02_compare.jsonl
+          MPYC_B200_OPS_MIN_SIZE=256 MPYC_B200_HARNESS=$h launcher tests/programs/resident_compare.py $n -M3 -B $((15000 + RANDOM % 2000)) --no-log 2>&1 | tail -n 1 >> $OUT/r02_compare.jsonl
+        done
+      done
+      cat $OUT/r02_compare.jsonl ;;
     sass)
       python tools/sass_summary.py > $OUT/r02_sass_summary.txt 2>&1; tail -5 $OUT/r02_sass_summary.txt ;;
     *) echo "unknown step $step" ;;
