@@ -241,7 +241,7 @@ template <int L>
 struct ComposeCfg {
     static constexpr int EB = 8 * L;                      // bytes per element
     static constexpr bool WIDE = (L % 2 == 0);            // even L: every element is 16-byte aligned
-    static constexpr int JB = L == 1 ? 14 : (L == 2 ? 8 : 4);   // columns per stage: a row chunk is at most 8 copy slots
+    static constexpr int JB = L == 1 ? 14 : (L == 2 ? 8 : 4);   // columns per stage (even): a row chunk is at most 8 copy slots
     static constexpr int G = 8;                           // copy slots per row (8 consecutive threads serve one row)
     static constexpr int STAGES = 3;
     // row pitch in shared memory for stages of at most `cols` columns: a multiple of 16 bytes with room for the row
@@ -308,8 +308,11 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
     };
     // a row whose chunk starts on an odd 8-byte boundary is stored 8 bytes into its pitch, so that 16-byte aligned
     // global addresses land on 16-byte aligned shared addresses (odd L only)
+    // odd L with an even number of columns on a 16-byte aligned base: every chunk starts and ends on a 16-byte boundary
+    // (JB is even), so the plain 16-byte path applies (warp-uniform)
+    const bool aligned = C::WIDE || ((fcols & 1) == 0 && (reinterpret_cast<uintptr_t>(gbase) & 15u) == 0);
     auto row_shift = [&](size_t row, int col0) -> u32 {
-        if constexpr (C::WIDE) return 0u;
+        if (aligned) return 0u;
         return (u32)((reinterpret_cast<uintptr_t>(gbase) + (row * (size_t)fcols + col0) * C::EB) & 8u);
     };
     // copy slot k of row (t >> 3) + 32 r: 8 consecutive threads fetch the contiguous chunk of one row, a warp 4 rows
@@ -338,7 +341,7 @@ k_bits_compose(FieldParams f, const u64* __restrict__ bits, u64* __restrict__ ou
                 const int row = rsub + (MPYC_THREADS / C::G) * r;
                 if (row < rows) {
                     const unsigned char* src = tbase + row * row_bytes;
-                    if constexpr (C::WIDE) {
+                    if (aligned) {
                         if (16 * kslot < rb) cp_async16(stage + row * pitch + 16 * kslot, src + 16 * kslot);
                     } else {
                         const u32 mis = (u32)(reinterpret_cast<uintptr_t>(src) & 8u);   // 0 or 8
