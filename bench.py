@@ -905,7 +905,7 @@ def run_gpu_arm(a, w):
                     check(lib.mpyc_b200_ff_binop_host(ctx.handle, _cabi.OP_MUL, hs.data_ptr(), hb.data_ptr(), ho.data_ptr(), ne, local))
             h2d, d2h = 2 * eb * ne, eb * ne
             path = 'mpyc_b200_ff_binop_host (pinned host buffers, copies inside)'
-            serial_ms = None
+            serial_ms = explicit_ms = explicit_h2d = None
         else:
             xs = buf['xs']
             hc = torch.empty((t, ne, L), dtype=torch.int64).pin_memory()
@@ -915,8 +915,21 @@ def run_gpu_arm(a, w):
             rowp = [_cabi.ptr_array([h[x - 1].data_ptr() for x in xs]) for h in hsh]
             xs_c, xr_c = _cabi.i64_array(xs), _cabi.i64_array([0])
 
-            def do_split(b):
+            import ctypes
+            import os as _os
+            key32 = (ctypes.c_uint8 * 32).from_buffer_copy(_os.urandom(32))
+            nonce = [0]
+
+            def do_split_explicit(b):
                 check(lib.mpyc_b200_shamir_split_host(ctx.handle, hs.data_ptr(), hc.data_ptr(), ne, hsh[b].data_ptr(), ne, ne, t, m, local))
+
+            def do_split(b):
+                # what thresha.np_random_split(field, s, t, m) is: secrets in, shares out -- the coefficients are the callee's
+                # own randomness (mpyc/thresha.py:58-60 draws them with secrets.randbelow; here an in-kernel ChaCha20 stream
+                # keyed with OS randomness), so only the secrets cross PCIe on the way up
+                nonce[0] += 1
+                check(lib.mpyc_b200_shamir_split_generate_host(ctx.handle, hs.data_ptr(), hsh[b].data_ptr(), ne, ne, t, m, key32,
+                                                               nonce[0], local))
 
             def do_rec(b):
                 check(lib.mpyc_b200_shamir_recombine_host(ctx.handle, rowp[b], xs_c, k, xr_c, 1, hout.data_ptr(), ne, ne, local))
@@ -943,13 +956,25 @@ def run_gpu_arm(a, w):
                         do_rec((j - 1) % 2)
                     if th is not None:
                         th.join()
-            h2d, d2h = (1 + t) * eb * ne + k * eb * ne, m * eb * ne + eb * ne
-            path = ('mpyc_b200_shamir_split_host + mpyc_b200_shamir_recombine_host on pinned host buffers, copies inside; '
-                    'successive batches pipelined from two host threads (split of batch j+1 overlaps recombination of batch j)')
+            h2d, d2h = eb * ne + k * eb * ne, m * eb * ne + eb * ne
+            path = ('mpyc_b200_shamir_split_generate_host (secrets in, shares out: np_random_split\'s signature) + '
+                    'mpyc_b200_shamir_recombine_host on pinned host buffers, copies inside; successive batches pipelined from '
+                    'two host threads (split of batch j+1 overlaps recombination of batch j)')
             e2e_serial(2)
             t0 = time.perf_counter()
             e2e_serial(max(2, a.steps // 4))
             serial_ms = 1e3 * (time.perf_counter() - t0) / max(2, a.steps // 4)
+            # the same step with the coefficients supplied by the caller (parity mode: t more rows go up)
+            generate_split = do_split
+            do_split = do_split_explicit
+            e2e_run(1)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            e2e_run(max(2, a.steps // 2))
+            explicit_ms = 1e3 * (time.perf_counter() - t0) / max(2, a.steps // 2)
+            do_split = generate_split
+            explicit_h2d = (1 + t) * eb * ne + k * eb * ne
         e2e_run(max(1, min(a.warmup, 2)))
         if world > 1:
             dist.barrier()
@@ -972,6 +997,7 @@ def run_gpu_arm(a, w):
         e2e = {'value': world * ne * a.steps / dt, 'unit': 'pairs/s' if not is_mul else 'elem/s', 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': d2h, 'n_per_step': ne, 'ms_per_step': 1e3 * dt / a.steps, 'path': path,
                'serial_two_call_ms_per_step': serial_ms,
+               'explicit_coefficients_ms_per_step': explicit_ms, 'explicit_coefficients_h2d_bytes_per_step': explicit_h2d,
                'pcie_GBps_per_direction': {'h2d': h2d / (dt / a.steps) / 1e9, 'd2h': d2h / (dt / a.steps) / 1e9},
                'pcie_probe': probe,
                'note': 'all ranks concurrently, max over ranks of the host wall clock around the blocking C-ABI calls'}

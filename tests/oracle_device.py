@@ -100,6 +100,10 @@ class OracleBackend:
         return store
 
     def _op(self, ctx, op, x, y):
+        if not ctx.binary:                       # exact integer arithmetic on object arrays, then % p (what the oracle's ff_* do)
+            X, Y, p = np.array(x, dtype=object), np.array(y, dtype=object), ctx.modulus
+            r = (X + Y) if op == _cabi.OP_ADD else ((X - Y) if op == _cabi.OP_SUB else (X * Y))
+            return codec.ints_to_limbs(r % p, ctx)
         F = orc.field_of(ctx.modulus, binary=ctx.binary)
         f = {_cabi.OP_ADD: F.add, _cabi.OP_SUB: F.sub, _cabi.OP_MUL: F.mul}[op]
         return codec.ints_to_limbs([F.red(f(a, b)) for a, b in zip(x, y)], ctx)
@@ -162,12 +166,8 @@ class OracleBackend:
         return np.ascontiguousarray(a.reshape((rows, cols) + a.shape[1:]).swapaxes(0, 1)).reshape(a.shape)
 
     def cumsum_rows(self, ctx, a, rows, cols):
-        x = self._ints(ctx, a)
-        p, out, acc = ctx.modulus, [], [0] * cols
-        for j in range(rows):
-            acc = [(s + v) % p for s, v in zip(acc, x[j * cols:(j + 1) * cols])]
-            out.extend(acc)
-        return codec.ints_to_limbs(out, ctx)
+        x = np.array(self._ints(ctx, a), dtype=object).reshape(rows, cols)
+        return codec.ints_to_limbs((np.cumsum(x, axis=0) % ctx.modulus).reshape(-1), ctx)
 
     def binop_rows(self, ctx, op, a, b, rows, cols, reflected):
         x, y = self._ints(ctx, a), self._ints(ctx, b)
