@@ -510,14 +510,17 @@ k_conv2d(FieldParams f, const u64* __restrict__ X, const u64* __restrict__ W, co
 // `s_sign - np.vstack((c_bits - r_bits, ones)) + 3*SumXors`.
 // ---------------------------------------------------------------------------------------
 
-// out (C, R) = in (R, C)^T: 32 x 32 element tiles through shared memory.  A warp moves the 32 elements of a row segment
-// as 32 L consecutive 64-bit words (coalesced whatever L is); the tile is kept limb-planar, tile[limb][row][col], with the
-// planes offset by 32 / L banks so that both the row-wise fill and the column-wise drain are conflict-free.
+// out (C, R) = in (R, C)^T: 32 x 32 element tiles through shared memory, both sides coalesced along their rows.
+// L <= 3: a lane moves one element (L words) and the tile is element-major.  L = 4: that layout puts the lanes of a warp
+// 8 banks apart (0.36 of the copy peak); there a warp moves the 32 elements of a row segment as 128 consecutive 64-bit
+// words and the tile is limb-planar, tile[limb][row][col], with the planes offset by 32 / L banks -- fill and drain
+// conflict-free (0.58).  Measured at np_sgn's shape (n x 38 matrices: the second column tile is 6/32 full).
 template <int L>
 __global__ void MPYC_LB
 k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t C) {
-    constexpr int PLANE = 32 * 33 + (L == 3 ? 5 : 16 / L);
-    __shared__ u64 tile[L * PLANE];
+    constexpr bool PLANAR = (L == 4);
+    constexpr int PLANE = 32 * 33 + 16 / L;
+    __shared__ u64 tile[PLANAR ? L * PLANE : 32 * 33 * L];
     const size_t tc = (C + 31) / 32, tr = (R + 31) / 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
     for (size_t w = blockIdx.x; w < tc * tr; w += gridDim.x) {
@@ -530,8 +533,12 @@ k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t 
                 const u64* src = in + (r * C + c0) * L;
 #pragma unroll
                 for (int q = 0; q < L; q++) {
-                    const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
-                    if (c0 + e < C) tile[lb * PLANE + (ty + 8 * k) * 33 + e] = src[idx];
+                    if constexpr (PLANAR) {
+                        const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
+                        if (c0 + e < C) tile[lb * PLANE + (ty + 8 * k) * 33 + e] = src[idx];
+                    } else {
+                        if (c0 + tx < C) tile[(ty + 8 * k) * 33 * L + tx * L + q] = src[tx * L + q];
+                    }
                 }
             }
         }
@@ -543,8 +550,12 @@ k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t R, size_t 
                 u64* dst = out + (c * R + r0) * L;
 #pragma unroll
                 for (int q = 0; q < L; q++) {
-                    const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
-                    if (r0 + e < R) dst[idx] = tile[lb * PLANE + e * 33 + (ty + 8 * k)];
+                    if constexpr (PLANAR) {
+                        const int idx = tx + 32 * q, e = idx / L, lb = idx % L;
+                        if (r0 + e < R) dst[idx] = tile[lb * PLANE + e * 33 + (ty + 8 * k)];
+                    } else {
+                        if (r0 + tx < R) dst[tx * L + q] = tile[tx * 33 * L + (ty + 8 * k) * L + q];
+                    }
                 }
             }
         }
