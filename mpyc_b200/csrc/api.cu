@@ -740,6 +740,9 @@ MPYC_API int mpyc_b200_ff_conv2d(const mpyc_b200_field* f, const void* d_x, cons
     if (int rc = prime_only(f, "ff_conv2d: field is null")) return rc;
     if (k < 0 || r < 1 || m < 1 || n < 1 || v < 1 || s < 1) return fail(MPYC_B200_EINVAL, "ff_conv2d: bad shape");
     if (s % 2 == 0) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: even filter sizes are not covered");
+    // rows shorter than the filter: np.correlate(.., 'same') returns max(n, s) values and the demo's row assignment fails --
+    // the engine does not compute where the reference raises
+    if (n < s) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: image rows shorter than the filter");
     if ((size_t)r * s * s > FF_MAX_LAZY_TERMS) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: too many taps for one lazy sum");
     if ((size_t)r * s * s * f->fp.L * 8 > 200u * 1024u) return fail(MPYC_B200_EUNSUPPORTED, "ff_conv2d: filter does not fit shared memory");
     if (k == 0) return MPYC_B200_OK;

@@ -145,6 +145,8 @@ def test_conv2d_rejects_even_filters():
     z = DeviceArray.from_ints(ctx, [1] * 64)
     with pytest.raises(mpyc_b200.UnsupportedFieldError):
         dev.conv2d(z, DeviceArray.from_ints(ctx, [1] * 4), DeviceArray.from_ints(ctx, [1]), 1, 1, 8, 8, 1, 2)
+    with pytest.raises(mpyc_b200.UnsupportedFieldError):       # rows shorter than the filter: the demo's loop raises there
+        dev.conv2d(z, DeviceArray.from_ints(ctx, [1] * 25), DeviceArray.from_ints(ctx, [1]), 1, 1, 16, 4, 1, 5)
 
 
 @pytest.mark.parametrize('p', PRIMES, ids=lambda p: f'p{p.bit_length()}_{p % 10000}')

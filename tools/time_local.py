@@ -56,6 +56,22 @@ def main():
             bits = DeviceArray(ctx, A.t[:rows * f])
             line('bits_compose', p, (f + 1) * 16 * rows, timed(lambda: dev.bits_compose(bits, rows, f), reps=3, warm=2), n=rows, f=f)
         return
+    if '--ncu-all' in sys.argv:           # one pass over every K6 kernel on the 128-bit field (256 MiB operands) for ncu
+        from mpyc_b200 import _cabi
+        p = 2**128 - 173
+        ctx = mpyc_b200.context_for(p)
+        n = 1 << 24
+        A, B, C = (DeviceArray.random(ctx, n, seed=5, stream_id=i) for i in (1, 2, 3))
+        R, cols = 38, n // 38
+        M, V = DeviceArray(ctx, A.t[:R * cols]), DeviceArray(ctx, C.t[:cols])
+        for fn in (lambda: dev.fma(A, B, C), lambda: dev.fma(A, None, C), lambda: dev.axpb(A, (p + 1) >> 1, 5), lambda: dev.low_bits(A, 37),
+                   lambda: dev.nonzero(A, want_mask=False), lambda: dev.bits_decompose(V, 37, descending=True),
+                   lambda: dev.transpose(M, cols, R), lambda: dev.cumsum_rows(M, R, cols),
+                   lambda: dev.binop_rows(M, V, _cabi.OP_SUB, R, cols, reflected=True)):
+            fn()
+            fn()
+        torch.cuda.synchronize()
+        return
     for p in primes:
         ctx = mpyc_b200.context_for(p)
         E = 8 * ctx.nlimbs
