@@ -13,7 +13,7 @@
 #   variants_<cfg>  bench a config with every libmpyc_b200_*.so tuning build present
 #   local        K6 protocol-local kernels: tests/test_gpu_local.py, tools/time_local.py, ncu capture of k_bits_compose
 #   demos2       np_cnnmnist -M3 (batch 1 and 4) with / without the engine, -M7 -T3 256-bit with the engine
-#   ncu_local    ncu --set full of the K6 elementwise / matrix kernels (tools/time_local.py --ncu-all)
+#   localncu     ncu --set full of the K6 elementwise / matrix kernels (tools/time_local.py --ncu-all)
 #   compare      tests/programs/resident_compare.py (np_sgn / np_trunc through the runtime), 3 parties: off vs resident
 #   sass         per-kernel SASS / ptxas summary (no GPU needed, also runs in the build container)
 set -u
@@ -116,7 +116,7 @@ for step in "$@"; do
       run_demo2 "np_cnnmnist -M3 batch 4" install,resident "X=1" np_cnnmnist.py 4 0 -M3
       run_demo2 "np_cnnmnist -M7 -T3 256-bit prime (configs[4])" install,resident,spread "MPYC_B200_FORCE_PRIME=$P256" np_cnnmnist.py 1 0 -M7 -T3
       cd $OLDPWD; cat $OUT/r02_demos2.txt ;;
-    ncu_local)
+    localncu)
       # one ncu --set full capture per K6 elementwise / matrix kernel (second launch of each), 128-bit field
       ncu --set full --clock-control none -k regex:"k_fma|k_axpb|k_low_bits|k_nonzero|k_bits_decompose|k_transpose|k_cumsum_rows|k_binop_rows" \
           -o $OUT/r02_ncu_local -f python tools/time_local.py --ncu-all > $OUT/r02_ncu_local.log 2>&1
