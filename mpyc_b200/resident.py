@@ -459,20 +459,21 @@ class ModValue:
     def _scalar(self, x):
         return int(x) if isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_)) else None
 
-    def _other_store(self, other):
-        """Store of an array operand of the same shape (packed from ints if need be), else None."""
+    def _other_store(self, other, shape=None):
+        """Store of an array operand of the given shape (default: this value's), packed from ints if need be; else None."""
+        shape = self.shape if shape is None else tuple(shape)
         if type(other) is ModValue:
             if other.store is None:
                 other = other._ints
-            elif other.ctx is self.ctx and other.shape == self.shape:
+            elif other.ctx is self.ctx and other.shape == shape:
                 return other._flush()
             else:
                 return None
         if type(other) is LimbValue:
             if other.store is not None:
-                return other.store if (other.ctx is self.ctx and other.shape == self.shape) else None
+                return other.store if (other.ctx is self.ctx and other.shape == shape) else None
             other = other._ints
-        if isinstance(other, np.ndarray) and other.shape == self.shape and other.dtype.kind in 'Oiu' and other.size:
+        if type(other) is np.ndarray and other.shape == shape and other.dtype.kind in 'Oiu' and other.size:
             calls['packed'] += 1
             if other.dtype != object:
                 other = other.astype(object)
@@ -526,9 +527,7 @@ class ModValue:
         R, C = mat.shape
         if R == 0 or C == 0:
             return None
-        holder = ModValue(self.ctx, None, tuple(oshape))     # only for its _other_store: accepts operands of other's shape
-        holder.store = True
-        other_store = holder._other_store(other)
+        other_store = self._other_store(other, oshape)
         if other_store is None:
             return None
         mine = self._flush()
@@ -1016,8 +1015,21 @@ def binop(self, other, op, reflected=False):
     if not isinstance(other, (cls, np.ndarray, LimbValue)):
         return _MISS
     b = _operand(ctx, cls, other)
-    if b is None or b[1] != a[1]:      # broadcasting stays with NumPy
+    if b is None:
         return _MISS
+    if b[1] != a[1]:
+        # NumPy's row broadcast between a matrix (R, C) and a vector (C,) runs on k_binop_rows; any other broadcast stays
+        # with NumPy
+        if ctx.binary:
+            return _MISS
+        if len(a[1]) == 2 and len(b[1]) == 1 and a[1][1] == b[1][0] and a[1][0] and a[1][1]:
+            mat, vec, vec_first = a, b, reflected
+        elif len(a[1]) == 1 and len(b[1]) == 2 and b[1][1] == a[1][0] and b[1][0] and b[1][1]:
+            mat, vec, vec_first = b, a, not reflected
+        else:
+            return _MISS
+        R, C = mat[1]
+        return _wrap(cls, ctx, backend.binop_rows(ctx, op, mat[0], vec[0], R, C, vec_first), (R, C))
     x, y = (b[0], a[0]) if reflected else (a[0], b[0])
     return _wrap(cls, ctx, backend.binop(ctx, op, x, y), a[1])
 

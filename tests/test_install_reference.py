@@ -215,6 +215,9 @@ def test_limb_backed_field_arrays_keep_their_limbs_through_the_hooked_operators(
         pairs = [(limb() << 5, plain << 5), (limb() >> 3, plain >> 3), (limb()[2:5], plain[2:5]), (limb()[-1], plain[-1]),
                  (limb()[1:], plain[1:]), (np.concatenate((limb()[:1], limb()[3:]), axis=0), np.concatenate((plain[:1], plain[3:]), axis=0)),
                  (limb() * limb() + limb() - 5, plain * plain + plain - 5)]
+        row = F.array(resident.LimbValue(ctx, codec.ints_to_limbs(vals[:2], ctx), (2,)), check=False)
+        prow = F.array(np.array(vals[:2], dtype=object))
+        pairs += [(limb() - row, plain - prow), (row - limb(), prow - plain), (limb() * row, plain * prow), (row + limb(), prow + plain)]
         x = limb()
         x <<= 2
         x >>= 7
