@@ -251,8 +251,7 @@ struct ComposeCfg {
         const int units = (cols * EB + (WIDE ? 0 : 8) + 15) / 16;
         return ((units + 1) | 1) * 16;
     }
-    // cp.async slots a row chunk needs: 16-byte pieces, plus for odd L an 8-byte head (misaligned rows) and tail
-    static constexpr int slots(int cols) { return WIDE ? cols * EB / 16 : (cols * EB + 8) / 16 + 1; }
+    // cp.async slots a full row chunk needs: 16-byte pieces, plus for odd L an 8-byte head (misaligned rows) and tail
     static_assert((WIDE ? JB * EB / 16 : (JB * EB + 8) / 16 + 1) <= G, "a row chunk must fit the copy slots of its 8 threads");
     static __host__ __device__ int smem(int fcols) { return STAGES * MPYC_THREADS * pitch(fcols < JB ? fcols : JB); }
 };
