@@ -101,3 +101,33 @@ def test_field_array_operators_random_instances(ref, p):
     assert (A << 5).value.tolist() == orc.ff_lshift(p, a, 5)
     assert (A >> 5).value.tolist() == orc.ff_rshift(p, a, 5)
     assert (A ** 7).value.tolist() == orc.ff_pow(p, a, 7)
+
+
+@pytest.mark.parametrize('p', PRIMES, ids=lambda p: f'p{p.bit_length()}')
+def test_local_algebra_random_instances(ref, p):
+    """oracle.local_* against the expressions of np_random_bits / np_trunc / np_sgn / np_to_bits (mpyc/runtime.py:860,
+    870, 3646-3660, 4252-4271, 4415) evaluated on the reference's field arrays, random sizes and bit counts."""
+    import numpy as np
+    thresha, finfields, gfpx = ref
+    Zp = finfields.GF(p)
+    rnd = random.Random(p % 9973)
+    arr = lambda v: Zp.array(np.array(v, dtype=object))   # noqa: E731
+    for _ in range(6):
+        n, f = rnd.randrange(1, 7), rnd.randrange(1, 75)
+        a, b, c = ([rnd.randrange(p) for _ in range(n)] for _ in range(3))
+        A, B, C = arr(a), arr(b), arr(c)
+        assert Zp.array(A.value**2 + C.value).value.tolist() == orc.local_fma(p, a, a, c)
+        assert Zp.array(A.value * B.value + C.value).value.tolist() == orc.local_fma(p, a, b, c)
+        s, t = rnd.randrange(p), rnd.randrange(p)
+        assert Zp.array(A.value * s + t).value.tolist() == orc.local_axpb(p, a, s, t)
+        nb = rnd.randrange(0, p.bit_length() + 3)
+        assert (C.value & ((1 << nb) - 1)).tolist() == orc.local_low_bits(c, nb)
+        assert (A.value != 0).tolist() == orc.local_nonzero(a)
+        bits = [rnd.randrange(p) for _ in range(n * f)]
+        R = arr(bits)
+        asc = Zp.array(np.sum(R.value.reshape((n, f)) << np.arange(f), axis=1)).value.tolist()
+        desc = Zp.array(np.sum(R.value.reshape((n, f)) << np.arange(f - 1, -1, -1), axis=1)).value.tolist()
+        assert asc == orc.local_bits_compose(p, bits, n, f) and desc == orc.local_bits_compose(p, bits, n, f, descending=True)
+        l = rnd.randrange(1, p.bit_length() + 1)
+        assert (np.right_shift.outer(C.value, np.arange(l - 1, -1, -1)).T & 1).tolist() == orc.local_bits_decompose(c, l, descending=True)
+        assert (np.right_shift.outer(C.value, np.arange(l)).T & 1).tolist() == orc.local_bits_decompose(c, l)
