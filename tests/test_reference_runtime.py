@@ -139,6 +139,9 @@ def test_np_cnnmnist_logits_identical(mode, parties):
         pytest.skip('reference demos/ not available (package-only reference)')
     cwd = DEMOS_DIR
     trim_for_gpu(mode, parties == 3)
+    if mode == 'oracle' and parties == 3 and os.environ.get('MPYC_B200_FULL_CPU_HARNESS') != '1':
+        pytest.skip('45 s of Python modular exponentiations in the oracle stand-in; the -M3 run is covered with the real kernels '
+                    '(-m gpu) and by the 1-party oracle run (MPYC_B200_FULL_CPU_HARNESS=1 runs it here too)')
     want = run(mode, 'np_cnnmnist.py', ['1', '0'], ('off',), cwd=cwd, parties=parties)
     got = run(mode, 'np_cnnmnist.py', ['1', '0'], ('install', 'resident'), cwd=cwd, parties=parties,
               env_extra={'MPYC_B200_OPS_MIN_SIZE': '64'})
