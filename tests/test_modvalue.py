@@ -237,3 +237,39 @@ def test_np_to_bits_expressions(p):
     for g, w in zip(got[:3], want[:3]):
         assert reduced(ctx, g) == reduced(ctx, w)
     assert got[3].dtype == np.int8 and got[3].tolist() == want[3].tolist()
+
+
+def test_np_random_bits_retry_path_with_a_zero_square():
+    """runtime.py:4254-4264: when an opened square is 0 the function keeps the non-zero entries (`_r.value[mask]`,
+    np.append) and draws again -- boolean-mask indexing and np.append turn ModValues into plain arrays, and the rest of
+    the function continues on those exactly as the reference does."""
+    p = PRIMES[0]
+    ctx = mpyc_b200.context_for(p)
+    r1 = [5, 0, 7, 11]                                     # second entry: r = 0, so r^2 opens to 0
+    r2 = [3]                                               # the redraw for the one missing bit
+    sq = lambda v: [(x * x) % p for x in v]   # noqa: E731
+
+    def run(R1, S1, R2, S2):
+        r = np.array([], dtype='O')
+        r2_acc = np.array([], dtype='O')
+        h = 4
+        mask = S1 != 0
+        h -= np.count_nonzero(mask)
+        assert h == 1
+        r = np.append(r, R1[mask])
+        r2_acc = np.append(r2_acc, S1[mask])
+        mask = S2 != 0
+        h -= np.count_nonzero(mask)
+        assert h == 0
+        r = np.append(r, R2)
+        r2_acc = np.append(r2_acc, S2)
+        inv = np.array(orc.ff_sqrt(p, [int(v) for v in r2_acc], INV=True), dtype=object)
+        bits = r * inv
+        bits %= p
+        bits += 1
+        bits *= (p + 1) >> 1
+        return bits
+    want = run(obj(r1), obj(sq(r1)), obj(r2), obj(sq(r2)))
+    got = run(mv(ctx, r1), mv(ctx, sq(r1)), mv(ctx, r2), mv(ctx, sq(r2)))
+    assert isinstance(got, np.ndarray) and type(got) is np.ndarray
+    assert [int(v) % p for v in got] == [int(v) % p for v in want] and set(int(v) % p for v in got) <= {0, 1}
