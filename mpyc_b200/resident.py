@@ -23,6 +23,12 @@ This module lets the SAME objects carry their elements as limb buffers instead:
   * with `resident = True` np_recombine / np_pseudorandom_share return limb-backed arrays and np_random_split
     accepts them, so a chain input -> multiply -> reshare -> multiply -> ... -> output creates Python ints only at
     input and at output.
+  * `ModValue` (with `resident` and `local_algebra`): Runtime.np_random_bits / np_trunc / np_sgn / np_to_bits -- recognised
+    by the hash of their source -- compute on RAW share values between two openings (runtime.py:856-872, 3644-3694,
+    4243-4273, 4413-4433).  Their `.value` reads get a ModValue, which evaluates those NumPy expressions mod p on the
+    K1 / K6 kernels (csrc/local.cuh) instead of settling; see the class docstring for why that is exact.  The hooks
+    around them (<< >>, contiguous __getitem__, np.concatenate(axis=0), == / != with a scalar, matrix/vector row
+    broadcast) keep np_prod's halving loop and np_is_zero_public limb-backed as well.
 
 All arithmetic runs on the GPU through the C ABI (`backend` below); there is no CPU path.  tests/oracle_device.py
 replaces `backend` by the oracle to exercise this module's host logic where no GPU exists.
