@@ -97,20 +97,21 @@ def run(mode, program, args=(), flags=('install',), cwd=None, timeout=900, parti
     return r.stdout
 
 
+WIDER = ('test_sectypes', 'test_secpols', 'test_statistics', 'test_asyncoro', 'test_fingroups', 'test_gfpx', 'test_gmpy',
+         'test_mpctools', 'test_numpy', 'test_random', 'test_secgroups', 'test_seclists')    # + thresha, finfields, runtime: all 84 tests
 EVERYTHING = {'MPYC_B200_OPS_MIN_SIZE': '1'}    # every array operator call goes through the hooks, whatever its size
 
 
 @pytest.mark.parametrize('flags', [('install',), ('install', 'limb_wire'), ('install', 'ops'), ('install', 'resident')],
                          ids=lambda f: '+'.join(f))
-@pytest.mark.parametrize('name', ['test_thresha', 'test_finfields', 'test_runtime', 'test_sectypes', 'test_secpols',
-                                  'test_statistics'])
+@pytest.mark.parametrize('name', ['test_thresha', 'test_finfields', 'test_runtime', *WIDER])
 def test_reference_unittests_under_install(mode, name, flags):
     """The reference's own unit tests, all green with the engine behind mpyc.thresha (and, with 'ops' / 'resident', behind
     the FiniteFieldArray operators, the batched inverse/pow/sqrt and the limb-resident `.value`, with the size
     threshold at 1 so that every operator call takes the hooked path)."""
     if not HAVE_TESTS:
         pytest.skip('reference tests/ directory not available (package-only reference)')
-    if name in ('test_sectypes', 'test_secpols', 'test_statistics') and flags != ('install', 'resident'):
+    if name in WIDER and flags != ('install', 'resident'):
         pytest.skip('the wider suites run once, in the most invasive configuration')
     trim_for_gpu(mode, flags in (('install',), ('install', 'resident')) and name in ('test_thresha', 'test_finfields', 'test_runtime', 'test_secpols'))
     out = run(mode, os.path.join(HERE, 'ref_unittest.py'), [os.path.join(TESTS_DIR, name + '.py')], flags,
